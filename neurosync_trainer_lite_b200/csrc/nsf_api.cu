@@ -1,0 +1,803 @@
+// C ABI over the kernels: contexts, workspace carving, the batched extraction pipeline and the
+// host-buffer (H2D -> kernels -> D2H) pipeline.  See include/nsf.h for the contract.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nsf.h"
+#include "nsf_internal.h"
+#include "nsf_kernels.cuh"
+#include "nsf_stft_tc.cuh"
+
+namespace nsf {
+
+namespace {
+
+constexpr int kStages = 8;
+
+std::string cuda_msg(const char* what, cudaError_t e) {
+  return std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+}
+
+#define NSF_CUDA(call)                                  \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) {                           \
+      set_error(cuda_msg(#call, e__));                  \
+      return NSF_ERR_CUDA;                              \
+    }                                                   \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided (or context-owned) device buffer.
+struct Carver {
+  char* base;
+  size_t cap, used = 0;
+  bool ok = true;
+  Carver(void* b, size_t c) : base(static_cast<char*>(b)), cap(c) {}
+  template <typename T> T* take(size_t count) {
+    const size_t bytes = align_up(count * sizeof(T));
+    if (used + bytes > cap) { ok = false; used += bytes; return nullptr; }
+    T* p = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return p;
+  }
+};
+
+struct Sizes {
+  int64_t total_samples, frames_ub, rows_ub;
+  int32_t n_clips;
+};
+
+// One layout function used both for sizing (base == nullptr) and carving.
+struct Layout {
+  int64_t* clip_off; int64_t* frame_off; int64_t* row_off;
+  uint32_t* peak_bits; uint32_t* dbmax_key; double* sum; double* sumsq;
+  float* y; float* a32; float* power; float* db; float* mfcc_raw; float* ac_raw; float* tmp_out;
+  void* tc_a;  // tcgen05 path: folded fp16 hi/lo operands
+  size_t zero_begin, zero_bytes;  // region that must be cleared before each batch
+};
+
+size_t plan_layout(const Plan& p, const Sizes& z, uint32_t flags, bool need_y, void* base, size_t cap,
+                   Layout* L, bool* ok) {
+  Carver c(base ? base : reinterpret_cast<void*>(0x1000), base ? cap : ~size_t(0) >> 1);
+  const size_t n1 = static_cast<size_t>(z.n_clips) + 1;
+  L->clip_off = c.take<int64_t>(n1);
+  L->frame_off = c.take<int64_t>(n1);
+  L->row_off = c.take<int64_t>(n1);
+  L->zero_begin = c.used;
+  L->peak_bits = c.take<uint32_t>(z.n_clips);
+  L->dbmax_key = c.take<uint32_t>(z.n_clips);
+  L->sum = c.take<double>(static_cast<size_t>(z.n_clips) * p.n_mfcc);
+  L->sumsq = c.take<double>(static_cast<size_t>(z.n_clips) * p.n_mfcc);
+  L->zero_bytes = c.used - L->zero_begin;
+  L->y = need_y ? c.take<float>(z.total_samples) : nullptr;
+  const int bins_ld = p.chain[0].np + (p.chains > 1 ? p.chain[1].np : 0);
+  L->a32 = nullptr;
+  L->tc_a = nullptr;
+  if (flags & NSF_DEBUG_SIMT_DFT) {
+    size_t kp_total = 0;
+    for (int ch = 0; ch < p.chains; ++ch) kp_total += 2 * static_cast<size_t>(p.chain[ch].kp);
+    L->a32 = c.take<float>(kp_total * z.frames_ub);
+  } else {
+    L->tc_a = c.take<char>(stft_tc_operand_bytes(p, z.frames_ub));
+  }
+  L->power = c.take<float>(static_cast<size_t>(z.frames_ub) * bins_ld);
+  L->db = c.take<float>(static_cast<size_t>(z.frames_ub) * p.n_mels);
+  L->mfcc_raw = c.take<float>(static_cast<size_t>(z.frames_ub) * p.n_mfcc);
+  L->ac_raw = (flags & NSF_AC_DELTAS) && !(flags & NSF_NO_AUTOCORR)
+                  ? c.take<float>(static_cast<size_t>(z.frames_ub) * p.n_lags) : nullptr;
+  const int cols = p.n_mfcc * 3 + p.n_lags * 3;
+  L->tmp_out = (flags & NSF_SMOOTH) ? c.take<float>(static_cast<size_t>(z.rows_ub) * cols) : nullptr;
+  if (ok) *ok = c.ok;
+  return c.used;
+}
+
+}  // namespace
+
+struct Arena {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  nsf_status reserve(size_t need) {
+    if (need <= bytes) return NSF_OK;
+    if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+    const size_t want = align_up(need + need / 8, 1 << 20);
+    NSF_CUDA(cudaMalloc(&ptr, want));
+    bytes = want;
+    return NSF_OK;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+};
+
+struct PinnedArena {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  nsf_status reserve(size_t need) {
+    if (need <= bytes) return NSF_OK;
+    if (ptr) { cudaFreeHost(ptr); ptr = nullptr; bytes = 0; }
+    const size_t want = align_up(need + need / 4, 1 << 16);
+    NSF_CUDA(cudaHostAlloc(&ptr, want, cudaHostAllocDefault));
+    bytes = want;
+    return NSF_OK;
+  }
+  void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; bytes = 0; }
+};
+
+struct Slot {  // one in-flight clip group of the host pipeline
+  cudaStream_t stream = nullptr;
+  Arena pcm, out, work, ynorm;
+  cudaEvent_t done = nullptr;
+};
+
+}  // namespace nsf
+
+struct nsf_ctx {
+  const nsf_plan* plan = nullptr;
+  int device = 0;
+  nsf::DeviceTables tables{};
+  nsf::StftTcTables tc{};
+  nsf::Arena table_mem;
+  // descriptor staging (pinned), guarded by an event so back-to-back calls cannot race the copy
+  nsf::PinnedArena desc_host;
+  cudaEvent_t desc_copied = nullptr;
+  bool desc_pending = false;
+  nsf::Slot slot[2];
+  int64_t launches = 0;
+  bool profiling = false;
+  cudaEvent_t stage_ev[nsf::kStages + 1] = {};
+  bool stage_valid = false;
+  nsf::Arena collect_in_a, collect_in_f, collect_out_a, collect_out_f, collect_desc;
+};
+
+namespace nsf {
+namespace {
+
+nsf_status upload_tables(nsf_ctx* ctx) {
+  const Plan& p = ctx->plan->p;
+  // pack everything into one host blob, one cudaMalloc, one copy
+  std::vector<char> blob;
+  auto put = [&](const void* src, size_t bytes) {
+    const size_t off = align_up(blob.size());
+    blob.resize(off + bytes);
+    std::memcpy(blob.data() + off, src, bytes);
+    return off;
+  };
+  size_t off_tap_idx[2] = {}, off_tap_coef[2] = {}, off_mat[2][2] = {};
+  std::vector<float> m32;
+  for (int c = 0; c < p.chains; ++c) {
+    const FoldChain& ch = p.chain[c];
+    off_tap_idx[c] = put(ch.tap_idx.data(), ch.tap_idx.size() * sizeof(int32_t));
+    off_tap_coef[c] = put(ch.tap_coef.data(), ch.tap_coef.size() * sizeof(float));
+    for (int part = 0; part < 2; ++part) {
+      m32.assign(ch.mat[part].begin(), ch.mat[part].end());
+      off_mat[c][part] = put(m32.data(), m32.size() * sizeof(float));
+    }
+  }
+  const size_t off_hann = put(p.hann_sym.data(), p.hann_sym.size() * sizeof(float));
+  // sparse mel runs in the chain-major power layout: natural bin k lives at column
+  // col_off[chain(k)] + index-within-chain(k); a filter's contiguous bin range becomes one run of
+  // consecutive columns per chain
+  int col_off[2] = {0, p.chain[0].np};
+  std::vector<int32_t> run_start(static_cast<size_t>(p.chains) * p.n_mels, 0),
+      run_len(run_start.size(), 0), run_ptr(run_start.size(), 0);
+  std::vector<float> melw;
+  for (int c = 0; c < p.chains; ++c)
+    for (int m = 0; m < p.n_mels; ++m) {
+      const size_t e = static_cast<size_t>(c) * p.n_mels + m;
+      run_ptr[e] = static_cast<int32_t>(melw.size());
+      const int lo = p.mel_start[m], hi = lo + p.mel_len[m];  // natural bins [lo, hi)
+      bool first = true;
+      for (int idx = 0; idx < p.chain[c].nbins; ++idx) {
+        const int k = p.chain[c].bin[idx];
+        if (k < lo || k >= hi) continue;
+        if (first) { run_start[e] = col_off[c] + idx; first = false; }
+        melw.push_back(p.mel_dense[static_cast<size_t>(m) * p.bins + k]);
+        ++run_len[e];
+      }
+    }
+  if (melw.empty()) melw.push_back(0.0f);
+  const size_t off_ms = put(run_start.data(), run_start.size() * sizeof(int32_t));
+  const size_t off_ml = put(run_len.data(), run_len.size() * sizeof(int32_t));
+  const size_t off_mp = put(run_ptr.data(), run_ptr.size() * sizeof(int32_t));
+  const size_t off_mw = put(melw.data(), melw.size() * sizeof(float));
+  std::vector<float> dct_t(static_cast<size_t>(p.n_mels) * 32, 0.0f);
+  for (int k = 0; k < p.n_mfcc; ++k)
+    for (int m = 0; m < p.n_mels; ++m) dct_t[static_cast<size_t>(m) * 32 + k] = p.dct[static_cast<size_t>(k) * p.n_mels + m];
+  const size_t off_dct = put(dct_t.data(), dct_t.size() * sizeof(float));
+  StftTcHostBlob tcblob;
+  build_stft_tc_blob(p, &tcblob);
+  const size_t off_tc = put(tcblob.bytes.data(), tcblob.bytes.size());
+
+  nsf_status st = ctx->table_mem.reserve(blob.size());
+  if (st != NSF_OK) return st;
+  NSF_CUDA(cudaMemcpy(ctx->table_mem.ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  char* base = static_cast<char*>(ctx->table_mem.ptr);
+  DeviceTables& t = ctx->tables;
+  t.F = p.F; t.H = p.H; t.pad = p.pad; t.bins = p.bins;
+  t.bins_ld = p.chain[0].np + (p.chains > 1 ? p.chain[1].np : 0);
+  t.col_off[0] = col_off[0]; t.col_off[1] = col_off[1];
+  t.n_mfcc = p.n_mfcc; t.n_mels = p.n_mels; t.n_lags = p.n_lags; t.chains = p.chains;
+  for (int c = 0; c < 2; ++c) {
+    t.kp[c] = t.np[c] = t.nbins[c] = 0;
+    t.tap_idx[c] = nullptr; t.tap_coef[c] = nullptr;
+    t.mat32[c][0] = t.mat32[c][1] = nullptr;
+  }
+  for (int c = 0; c < p.chains; ++c) {
+    t.kp[c] = p.chain[c].kp; t.np[c] = p.chain[c].np; t.nbins[c] = p.chain[c].nbins;
+    t.tap_idx[c] = reinterpret_cast<const int32_t*>(base + off_tap_idx[c]);
+    t.tap_coef[c] = reinterpret_cast<const float*>(base + off_tap_coef[c]);
+    t.mat32[c][0] = reinterpret_cast<const float*>(base + off_mat[c][0]);
+    t.mat32[c][1] = reinterpret_cast<const float*>(base + off_mat[c][1]);
+  }
+  t.hann_sym = reinterpret_cast<const float*>(base + off_hann);
+  t.mel_start = reinterpret_cast<const int32_t*>(base + off_ms);
+  t.mel_len = reinterpret_cast<const int32_t*>(base + off_ml);
+  t.mel_ptr = reinterpret_cast<const int32_t*>(base + off_mp);
+  t.mel_w = reinterpret_cast<const float*>(base + off_mw);
+  t.dct_t = reinterpret_cast<const float*>(base + off_dct);
+  return bind_stft_tc_tables(p, tcblob, base + off_tc, &ctx->tc);
+}
+
+// Host-side descriptor build + validation shared by the device and host entry points.
+struct HostDesc {
+  std::vector<int64_t> clip_off, frame_off, row_off;
+  int64_t total_samples = 0, total_frames = 0, total_rows = 0;
+};
+
+nsf_status build_desc(const Plan& p, const int64_t* clip_offsets, int32_t n_clips, uint32_t flags,
+                      const int64_t* out_row_offsets, HostDesc* d) {
+  if (!clip_offsets || n_clips <= 0) {
+    set_error("clip_offsets is NULL or n_clips <= 0");
+    return NSF_ERR_BAD_ARG;
+  }
+  d->clip_off.resize(n_clips + 1);
+  d->frame_off.resize(n_clips + 1);
+  d->row_off.resize(n_clips + 1);
+  const int64_t origin = clip_offsets[0];
+  d->frame_off[0] = 0;
+  d->row_off[0] = out_row_offsets ? out_row_offsets[0] : 0;
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t len = clip_offsets[i + 1] - clip_offsets[i];
+    if (len < 0) { set_error("clip_offsets must be non-decreasing"); return NSF_ERR_BAD_ARG; }
+    if (nsf_guard_frames(len, p.F, p.H) < kMinGuardFrames) {
+      char buf[160];
+      std::snprintf(buf, sizeof buf, "clip %d is too short: %lld frames, required: %d frames", i,
+                    static_cast<long long>(nsf_guard_frames(len, p.F, p.H)), kMinGuardFrames);
+      set_error(buf);
+      return NSF_ERR_TOO_SHORT;
+    }
+    const int64_t T = nsf_hop_frames(len, p.F, p.H);
+    const int64_t R = (flags & NSF_NO_REDUCE) ? T : (T + 1) / 2;
+    d->clip_off[i] = clip_offsets[i] - origin;
+    d->frame_off[i + 1] = d->frame_off[i] + T;
+    if (out_row_offsets) {
+      if (out_row_offsets[i + 1] - out_row_offsets[i] != R) {
+        set_error("out_row_offsets is not the prefix sum of the per-clip row counts");
+        return NSF_ERR_BAD_ARG;
+      }
+      d->row_off[i + 1] = out_row_offsets[i + 1];
+    } else {
+      d->row_off[i + 1] = d->row_off[i] + R;
+    }
+  }
+  d->clip_off[n_clips] = clip_offsets[n_clips] - origin;
+  d->total_samples = d->clip_off[n_clips];
+  d->total_frames = d->frame_off[n_clips];
+  d->total_rows = d->row_off[n_clips] - d->row_off[0];
+  return NSF_OK;
+}
+
+struct StageTimer {
+  nsf_ctx* ctx; cudaStream_t s; int next = 0;
+  void mark(int stage) {
+    if (!ctx->profiling) return;
+    while (next <= stage) cudaEventRecord(ctx->stage_ev[next++], s);
+  }
+  void finish() {
+    if (!ctx->profiling) return;
+    while (next <= kStages) cudaEventRecord(ctx->stage_ev[next++], s);
+    ctx->stage_valid = true;
+  }
+};
+
+}  // namespace
+}  // namespace nsf
+
+using namespace nsf;
+
+extern "C" {
+
+int32_t nsf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+nsf_status nsf_host_alloc(void** out_ptr, int64_t bytes) {
+  if (!out_ptr || bytes <= 0) { set_error("nsf_host_alloc: bad argument"); return NSF_ERR_BAD_ARG; }
+  NSF_CUDA(cudaHostAlloc(out_ptr, static_cast<size_t>(bytes), cudaHostAllocDefault));
+  return NSF_OK;
+}
+
+void nsf_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+nsf_status nsf_ctx_create(const nsf_plan* plan, int32_t device, nsf_ctx** out_ctx) {
+  if (!plan || !out_ctx) { set_error("nsf_ctx_create: NULL argument"); return NSF_ERR_BAD_ARG; }
+  *out_ctx = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device is visible; this library has no CPU path");
+    return NSF_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { set_error("nsf_ctx_create: device index out of range"); return NSF_ERR_BAD_ARG; }
+  int major = 0;
+  NSF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    set_error("device is not sm_100 (Blackwell B200); the kernels are compiled for sm_100a only");
+    return NSF_ERR_NO_DEVICE;
+  }
+  NSF_CUDA(cudaSetDevice(device));
+  nsf_ctx* ctx = new nsf_ctx();
+  ctx->plan = plan;
+  ctx->device = device;
+  nsf_status st = upload_tables(ctx);
+  if (st != NSF_OK) { nsf_ctx_destroy(ctx); return st; }
+  if (cudaEventCreateWithFlags(&ctx->desc_copied, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("cudaEventCreate failed"); nsf_ctx_destroy(ctx); return NSF_ERR_CUDA;
+  }
+  for (int i = 0; i <= kStages; ++i) {
+    if (cudaEventCreate(&ctx->stage_ev[i]) != cudaSuccess) {
+      set_error("cudaEventCreate failed"); nsf_ctx_destroy(ctx); return NSF_ERR_CUDA;
+    }
+  }
+  *out_ctx = ctx;
+  return NSF_OK;
+}
+
+void nsf_ctx_destroy(nsf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& s : ctx->slot) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+    s.pcm.release(); s.out.release(); s.work.release(); s.ynorm.release();
+  }
+  for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
+  if (ctx->desc_copied) cudaEventDestroy(ctx->desc_copied);
+  ctx->desc_host.release();
+  ctx->table_mem.release();
+  ctx->collect_in_a.release(); ctx->collect_in_f.release();
+  ctx->collect_out_a.release(); ctx->collect_out_f.release(); ctx->collect_desc.release();
+  delete ctx;
+}
+
+int64_t nsf_launch_count(const nsf_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+void nsf_set_profiling(nsf_ctx* ctx, int32_t enabled) { if (ctx) { ctx->profiling = enabled != 0; ctx->stage_valid = false; } }
+
+int32_t nsf_stage_times_ms(nsf_ctx* ctx, float* ms, int32_t capacity) {
+  if (!ctx || !ms || !ctx->stage_valid) return 0;
+  if (cudaEventSynchronize(ctx->stage_ev[kStages]) != cudaSuccess) return 0;
+  const int n = capacity < kStages ? capacity : kStages;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.0f;
+    if (cudaEventElapsedTime(&t, ctx->stage_ev[i], ctx->stage_ev[i + 1]) != cudaSuccess) t = -1.0f;
+    ms[i] = t;
+  }
+  return n;
+}
+
+int64_t nsf_workspace_bytes(const nsf_plan* plan, int64_t total_samples, int32_t n_clips, uint32_t flags) {
+  if (!plan || total_samples < 0 || n_clips <= 0) return -1;
+  const Plan& p = plan->p;
+  Sizes z;
+  z.total_samples = total_samples;
+  z.n_clips = n_clips;
+  z.frames_ub = n_clips + total_samples / p.H;  // T_i <= 1 + L_i / H
+  z.rows_ub = (flags & NSF_NO_REDUCE) ? z.frames_ub : (z.frames_ub + n_clips + 1) / 2 + n_clips;
+  Layout L;
+  return static_cast<int64_t>(plan_layout(p, z, flags, true, nullptr, 0, &L, nullptr)) + 256;
+}
+
+nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_dev, int32_t pcm_format,
+                             const int64_t* clip_offsets_host, int32_t n_clips, uint32_t flags,
+                             float* out_dev, int64_t out_ld, const int64_t* out_row_offsets_host,
+                             float* y_norm_dev, void* workspace_dev, int64_t workspace_bytes) {
+  if (!ctx || !pcm_dev || !out_dev || !workspace_dev) { set_error("nsf_extract_batch: NULL argument"); return NSF_ERR_BAD_ARG; }
+  if (pcm_format != NSF_PCM_F32 && pcm_format != NSF_PCM_I16) { set_error("unknown pcm_format"); return NSF_ERR_BAD_ARG; }
+  const Plan& p = ctx->plan->p;
+  const int cols = nsf_feature_cols(ctx->plan, flags);
+  if (out_ld < cols) { set_error("out_ld smaller than the feature width"); return NSF_ERR_BAD_ARG; }
+  HostDesc hd;
+  nsf_status st = build_desc(p, clip_offsets_host, n_clips, flags, out_row_offsets_host, &hd);
+  if (st != NSF_OK) return st;
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+
+  const bool normalize = (flags & NSF_PEAK_NORMALIZE) != 0;
+  const bool need_y = normalize || pcm_format == NSF_PCM_I16;
+  Sizes z;
+  z.total_samples = hd.total_samples; z.n_clips = n_clips;
+  z.frames_ub = hd.total_frames; z.rows_ub = hd.total_rows;
+  Layout L;
+  bool fits = false;
+  // 256-byte align the caller's pointer
+  char* wbase = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace_dev)));
+  const size_t wcap = static_cast<size_t>(workspace_bytes) - static_cast<size_t>(wbase - static_cast<char*>(workspace_dev));
+  plan_layout(p, z, flags, need_y && !y_norm_dev, wbase, wcap, &L, &fits);
+  if (!fits) { set_error("workspace too small; size it with nsf_workspace_bytes()"); return NSF_ERR_WORKSPACE; }
+
+  // descriptors: pinned staging -> device, stream ordered
+  const size_t n1 = static_cast<size_t>(n_clips) + 1;
+  if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
+  st = ctx->desc_host.reserve(3 * n1 * sizeof(int64_t));
+  if (st != NSF_OK) return st;
+  int64_t* hstage = static_cast<int64_t*>(ctx->desc_host.ptr);
+  const int64_t row_origin = hd.row_off[0];
+  for (size_t i = 0; i < n1; ++i) {
+    hstage[i] = hd.clip_off[i];
+    hstage[n1 + i] = hd.frame_off[i];
+    hstage[2 * n1 + i] = hd.row_off[i] - row_origin;
+  }
+  NSF_CUDA(cudaMemcpyAsync(L.clip_off, hstage, n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  NSF_CUDA(cudaMemcpyAsync(L.frame_off, hstage + n1, n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  NSF_CUDA(cudaMemcpyAsync(L.row_off, hstage + 2 * n1, n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  NSF_CUDA(cudaEventRecord(ctx->desc_copied, s));
+  ctx->desc_pending = true;
+  NSF_CUDA(cudaMemsetAsync(wbase + L.zero_begin, 0, L.zero_bytes, s));
+
+  BatchView b;
+  b.clip_off = L.clip_off; b.frame_off = L.frame_off; b.row_off = L.row_off;
+  b.n_clips = n_clips; b.total_samples = hd.total_samples; b.total_frames = hd.total_frames;
+  b.total_rows = hd.total_rows;
+  float* out = out_dev + row_origin * out_ld;
+  const DeviceTables& t = ctx->tables;
+  StageTimer timer{ctx, s};
+  int launched = 0;
+#define NSF_LAUNCH(expr)                                                   \
+  do {                                                                     \
+    const int n__ = (expr);                                                \
+    if (n__ < 0) { set_error(cuda_msg(#expr, cudaGetLastError())); return NSF_ERR_CUDA; } \
+    launched += n__;                                                       \
+  } while (0)
+
+  // stage 0: decode / peak normalise
+  timer.mark(0);
+  const float* y = static_cast<const float*>(pcm_dev);
+  if (need_y) {
+    float* ydst = y_norm_dev ? y_norm_dev : L.y;
+    if (normalize) NSF_LAUNCH(launch_absmax(s, pcm_dev, pcm_format, b, L.peak_bits));
+    NSF_LAUNCH(launch_normalize(s, pcm_dev, pcm_format, b, L.peak_bits, normalize, ydst));
+    y = ydst;
+  } else if (y_norm_dev) {
+    NSF_CUDA(cudaMemcpyAsync(y_norm_dev, pcm_dev, hd.total_samples * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+
+  // the smoothing pass needs the un-smoothed rows in a scratch buffer
+  float* stage_out = (flags & NSF_SMOOTH) ? L.tmp_out : out;
+  const int64_t stage_ld = (flags & NSF_SMOOTH) ? cols : out_ld;
+  const bool reduce = !(flags & NSF_NO_REDUCE);
+  const bool deltas = !(flags & NSF_NO_DELTAS);
+  const bool do_mfcc = !(flags & NSF_NO_MFCC);
+  const int mfcc_cols = do_mfcc ? p.n_mfcc * (deltas ? 3 : 1) : 0;
+  if (!do_mfcc && (flags & NSF_NO_AUTOCORR)) { set_error("NSF_NO_MFCC | NSF_NO_AUTOCORR leaves nothing to compute"); return NSF_ERR_BAD_ARG; }
+
+  // stages 1-3: STFT power -> mel -> dB (+ per-clip max)
+  if (!do_mfcc) {
+    // autocorrelation block only
+  } else if (flags & NSF_DEBUG_SIMT_DFT) {
+    timer.mark(1);
+    NSF_LAUNCH(launch_fold32(s, t, b, y, L.a32));
+    timer.mark(2);
+    NSF_LAUNCH(launch_dft_simt(s, t, b, L.a32, L.power));
+  } else {
+    timer.mark(1);
+    NSF_LAUNCH(launch_stft_tc_fold(s, ctx->tc, t, b, y, L.tc_a));
+    timer.mark(2);
+    NSF_LAUNCH(launch_stft_tc_gemm(s, ctx->tc, t, b, L.tc_a, L.power));
+  }
+  timer.mark(3);
+  if (do_mfcc) NSF_LAUNCH(launch_mel_db(s, t, b, L.power, L.db, L.dbmax_key));
+  // stage 4: floor + DCT + CMVN statistics
+  timer.mark(4);
+  if (do_mfcc) {
+    NSF_LAUNCH(launch_dct_sum(s, t, b, L.db, L.dbmax_key, L.mfcc_raw, L.sum));
+    if (!(flags & NSF_NO_CMVN)) NSF_LAUNCH(launch_dev_sq(s, t, b, L.mfcc_raw, L.sum, L.sumsq));
+  }
+  // stage 5: CMVN + deltas + pair reduce -> columns [0, mfcc_cols)
+  timer.mark(5);
+  if (do_mfcc)
+    NSF_LAUNCH(launch_delta_reduce(s, b, L.mfcc_raw, p.n_mfcc, p.n_mfcc, L.sum, L.sumsq,
+                                   !(flags & NSF_NO_CMVN), deltas, reduce, stage_out, stage_ld, 0));
+  // stage 6: autocorrelation -> columns [mfcc_cols, ...)
+  timer.mark(6);
+  if (!(flags & NSF_NO_AUTOCORR)) {
+    if (flags & NSF_AC_DELTAS) {
+      BatchView bf = b;  // un-reduced: one row per hop-frame
+      bf.row_off = L.frame_off; bf.total_rows = hd.total_frames;
+      NSF_LAUNCH(launch_autocorr(s, t, bf, y, false, L.ac_raw, p.n_lags, 0));
+      NSF_LAUNCH(launch_delta_reduce(s, b, L.ac_raw, p.n_lags, p.n_lags, nullptr, nullptr, false, true,
+                                     reduce, stage_out, stage_ld, mfcc_cols));
+    } else {
+      NSF_LAUNCH(launch_autocorr(s, t, b, y, reduce, stage_out, stage_ld, mfcc_cols));
+    }
+  }
+  // stage 7: optional smoothing
+  timer.mark(7);
+  if (flags & NSF_SMOOTH) NSF_LAUNCH(launch_smooth(s, b, L.tmp_out, cols, cols, out, out_ld));
+  timer.finish();
+  ctx->launches += launched;
+#undef NSF_LAUNCH
+  return NSF_OK;
+}
+
+// ---- host-buffer pipeline ------------------------------------------------------------------------
+static nsf_status ensure_slot(Slot* sl) {
+  if (!sl->stream) NSF_CUDA(cudaStreamCreateWithFlags(&sl->stream, cudaStreamNonBlocking));
+  if (!sl->done) NSF_CUDA(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
+  return NSF_OK;
+}
+
+nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
+                            const int64_t* clip_offsets, int32_t n_clips, uint32_t flags,
+                            float* out_host, int64_t out_ld, float* y_norm_host) {
+  if (!ctx || !pcm_host || !out_host || !clip_offsets || n_clips <= 0) {
+    set_error("nsf_extract_host: NULL argument"); return NSF_ERR_BAD_ARG;
+  }
+  if (pcm_format != NSF_PCM_F32 && pcm_format != NSF_PCM_I16) { set_error("unknown pcm_format"); return NSF_ERR_BAD_ARG; }
+  const Plan& p = ctx->plan->p;
+  const int cols = nsf_feature_cols(ctx->plan, flags);
+  if (out_ld < cols) { set_error("out_ld smaller than the feature width"); return NSF_ERR_BAD_ARG; }
+  // validate everything up front so nothing is launched for a bad batch
+  HostDesc all;
+  nsf_status st = build_desc(p, clip_offsets, n_clips, flags, nullptr, &all);
+  if (st != NSF_OK) return st;
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = pcm_format == NSF_PCM_I16 ? 2 : 4;
+  const int64_t kGroupSamples = int64_t(24) << 20;  // ~96 MB of float32 PCM per in-flight group
+  int first = 0, turn = 0;
+  while (first < n_clips) {
+    int last = first;
+    int64_t samples = 0;
+    while (last < n_clips && (last == first || samples + (clip_offsets[last + 1] - clip_offsets[last]) <= kGroupSamples)) {
+      samples += clip_offsets[last + 1] - clip_offsets[last];
+      ++last;
+    }
+    const int gn = last - first;
+    Slot* sl = &ctx->slot[turn & 1];
+    st = ensure_slot(sl);
+    if (st != NSF_OK) return st;
+    // the slot's previous group must have fully drained before its buffers are reused
+    NSF_CUDA(cudaStreamSynchronize(sl->stream));
+    const int64_t rows = all.row_off[last] - all.row_off[first];
+    const int64_t wbytes = nsf_workspace_bytes(ctx->plan, samples, gn, flags);
+    if ((st = sl->pcm.reserve(samples * esz)) != NSF_OK) return st;
+    if ((st = sl->out.reserve(static_cast<size_t>(rows) * cols * sizeof(float))) != NSF_OK) return st;
+    if ((st = sl->work.reserve(wbytes)) != NSF_OK) return st;
+    if (y_norm_host && (st = sl->ynorm.reserve(samples * sizeof(float))) != NSF_OK) return st;
+    const char* src = static_cast<const char*>(pcm_host) + clip_offsets[first] * esz;
+    NSF_CUDA(cudaMemcpyAsync(sl->pcm.ptr, src, samples * esz, cudaMemcpyHostToDevice, sl->stream));
+    st = nsf_extract_batch(ctx, sl->stream, sl->pcm.ptr, pcm_format, clip_offsets + first, gn, flags,
+                           static_cast<float*>(sl->out.ptr), cols, nullptr,
+                           y_norm_host ? static_cast<float*>(sl->ynorm.ptr) : nullptr, sl->work.ptr,
+                           static_cast<int64_t>(sl->work.bytes));
+    if (st != NSF_OK) return st;
+    float* dst = out_host + all.row_off[first] * out_ld;
+    if (out_ld == cols) {
+      NSF_CUDA(cudaMemcpyAsync(dst, sl->out.ptr, static_cast<size_t>(rows) * cols * sizeof(float),
+                               cudaMemcpyDeviceToHost, sl->stream));
+    } else {
+      NSF_CUDA(cudaMemcpy2DAsync(dst, out_ld * sizeof(float), sl->out.ptr, cols * sizeof(float),
+                                 cols * sizeof(float), rows, cudaMemcpyDeviceToHost, sl->stream));
+    }
+    if (y_norm_host) {
+      NSF_CUDA(cudaMemcpyAsync(y_norm_host + (clip_offsets[first] - clip_offsets[0]), sl->ynorm.ptr,
+                               samples * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+    }
+    first = last;
+    ++turn;
+  }
+  for (auto& sl : ctx->slot)
+    if (sl.stream) NSF_CUDA(cudaStreamSynchronize(sl.stream));
+  return NSF_OK;
+}
+
+// ---- collect ---------------------------------------------------------------------------------------
+static nsf_status collect_offsets(const int64_t* a_off, const int64_t* f_off, int32_t n, uint32_t flags,
+                                  int32_t blend_frames, const int64_t* o_off_in, std::vector<int64_t>* o_off) {
+  if (!a_off || !f_off || n <= 0) { set_error("nsf_collect: NULL offsets or n_clips <= 0"); return NSF_ERR_BAD_ARG; }
+  o_off->resize(n + 1);
+  (*o_off)[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const int64_t na = a_off[i + 1] - a_off[i], nf = f_off[i + 1] - f_off[i];
+    if (na < 0 || nf < 0) { set_error("nsf_collect: offsets must be non-decreasing"); return NSF_ERR_BAD_ARG; }
+    const int64_t r = nsf_collect_rows(na, nf, flags, blend_frames);
+    if (o_off_in && o_off_in[i + 1] - o_off_in[i] != r) {
+      set_error("nsf_collect: out_offsets is not the prefix sum of nsf_collect_rows()");
+      return NSF_ERR_BAD_ARG;
+    }
+    (*o_off)[i + 1] = (*o_off)[i] + r;
+  }
+  return NSF_OK;
+}
+
+nsf_status nsf_collect_batch(nsf_ctx* ctx, void* cuda_stream, int32_t dtype, const void* audio_dev,
+                             int32_t audio_cols, const int64_t* audio_offsets_host, const void* facial_dev,
+                             int32_t facial_cols, const int64_t* facial_offsets_host, int32_t n_clips,
+                             uint32_t collect_flags, int32_t blend_frames, void* out_audio_dev,
+                             void* out_facial_dev, const int64_t* out_offsets_host) {
+  if (!ctx || !audio_dev || !facial_dev || !out_audio_dev || !out_facial_dev) {
+    set_error("nsf_collect_batch: NULL argument"); return NSF_ERR_BAD_ARG;
+  }
+  if ((dtype != NSF_F32 && dtype != NSF_F64) || audio_cols <= 0 || facial_cols <= 0) {
+    set_error("nsf_collect_batch: bad dtype or column count"); return NSF_ERR_BAD_ARG;
+  }
+  std::vector<int64_t> o_off;
+  nsf_status st = collect_offsets(audio_offsets_host, facial_offsets_host, n_clips, collect_flags,
+                                  blend_frames, out_offsets_host, &o_off);
+  if (st != NSF_OK) return st;
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t n1 = static_cast<size_t>(n_clips) + 1;
+  if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
+  if ((st = ctx->desc_host.reserve(3 * n1 * sizeof(int64_t))) != NSF_OK) return st;
+  if ((st = ctx->collect_desc.reserve(3 * n1 * sizeof(int64_t))) != NSF_OK) return st;
+  int64_t* h = static_cast<int64_t*>(ctx->desc_host.ptr);
+  const int64_t a0 = audio_offsets_host[0], f0 = facial_offsets_host[0];
+  const int64_t o0 = out_offsets_host ? out_offsets_host[0] : 0;
+  for (size_t i = 0; i < n1; ++i) {
+    h[i] = audio_offsets_host[i] - a0;
+    h[n1 + i] = facial_offsets_host[i] - f0;
+    h[2 * n1 + i] = o_off[i];
+  }
+  int64_t* d = static_cast<int64_t*>(ctx->collect_desc.ptr);
+  NSF_CUDA(cudaMemcpyAsync(d, h, 3 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  NSF_CUDA(cudaEventRecord(ctx->desc_copied, s));
+  ctx->desc_pending = true;
+  CollectView v;
+  v.a_off = d; v.f_off = d + n1; v.o_off = d + 2 * n1;
+  v.n_clips = n_clips; v.total_out_rows = o_off[n_clips]; v.flags = collect_flags; v.blend_frames = blend_frames;
+  const size_t esz = dtype == NSF_F64 ? 8 : 4;
+  const char* a = static_cast<const char*>(audio_dev) + a0 * audio_cols * esz;
+  const char* f = static_cast<const char*>(facial_dev) + f0 * facial_cols * esz;
+  char* oa = static_cast<char*>(out_audio_dev) + o0 * audio_cols * esz;
+  char* of = static_cast<char*>(out_facial_dev) + o0 * facial_cols * esz;
+  const int n = launch_collect(s, dtype, v, a, audio_cols, f, facial_cols, oa, of);
+  if (n < 0) { set_error(cuda_msg("launch_collect", cudaGetLastError())); return NSF_ERR_CUDA; }
+  ctx->launches += n;
+  return NSF_OK;
+}
+
+nsf_status nsf_collect_host(nsf_ctx* ctx, int32_t dtype, const void* audio_host, int32_t audio_cols,
+                            const int64_t* a_off, const void* facial_host, int32_t facial_cols,
+                            const int64_t* f_off, int32_t n_clips, uint32_t collect_flags,
+                            int32_t blend_frames, void* out_audio_host, void* out_facial_host) {
+  if (!ctx || !audio_host || !facial_host || !out_audio_host || !out_facial_host) {
+    set_error("nsf_collect_host: NULL argument"); return NSF_ERR_BAD_ARG;
+  }
+  if (dtype != NSF_F32 && dtype != NSF_F64) { set_error("nsf_collect_host: bad dtype"); return NSF_ERR_BAD_ARG; }
+  std::vector<int64_t> o_off;
+  nsf_status st = collect_offsets(a_off, f_off, n_clips, collect_flags, blend_frames, nullptr, &o_off);
+  if (st != NSF_OK) return st;
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  Slot* sl = &ctx->slot[0];
+  if ((st = ensure_slot(sl)) != NSF_OK) return st;
+  const size_t esz = dtype == NSF_F64 ? 8 : 4;
+  const size_t a_rows = a_off[n_clips] - a_off[0], f_rows = f_off[n_clips] - f_off[0];
+  const size_t o_rows = o_off[n_clips];
+  if ((st = ctx->collect_in_a.reserve(a_rows * audio_cols * esz)) != NSF_OK) return st;
+  if ((st = ctx->collect_in_f.reserve(f_rows * facial_cols * esz)) != NSF_OK) return st;
+  if ((st = ctx->collect_out_a.reserve(o_rows * audio_cols * esz)) != NSF_OK) return st;
+  if ((st = ctx->collect_out_f.reserve(o_rows * facial_cols * esz)) != NSF_OK) return st;
+  const char* ah = static_cast<const char*>(audio_host) + a_off[0] * audio_cols * esz;
+  const char* fh = static_cast<const char*>(facial_host) + f_off[0] * facial_cols * esz;
+  NSF_CUDA(cudaMemcpyAsync(ctx->collect_in_a.ptr, ah, a_rows * audio_cols * esz, cudaMemcpyHostToDevice, sl->stream));
+  NSF_CUDA(cudaMemcpyAsync(ctx->collect_in_f.ptr, fh, f_rows * facial_cols * esz, cudaMemcpyHostToDevice, sl->stream));
+  std::vector<int64_t> a_rel(n_clips + 1), f_rel(n_clips + 1);
+  for (int i = 0; i <= n_clips; ++i) { a_rel[i] = a_off[i] - a_off[0]; f_rel[i] = f_off[i] - f_off[0]; }
+  st = nsf_collect_batch(ctx, sl->stream, dtype, ctx->collect_in_a.ptr, audio_cols, a_rel.data(),
+                         ctx->collect_in_f.ptr, facial_cols, f_rel.data(), n_clips, collect_flags,
+                         blend_frames, ctx->collect_out_a.ptr, ctx->collect_out_f.ptr, nullptr);
+  if (st != NSF_OK) return st;
+  NSF_CUDA(cudaMemcpyAsync(out_audio_host, ctx->collect_out_a.ptr, o_rows * audio_cols * esz, cudaMemcpyDeviceToHost, sl->stream));
+  NSF_CUDA(cudaMemcpyAsync(out_facial_host, ctx->collect_out_f.ptr, o_rows * facial_cols * esz, cudaMemcpyDeviceToHost, sl->stream));
+  NSF_CUDA(cudaStreamSynchronize(sl->stream));
+  return NSF_OK;
+}
+
+nsf_status nsf_rows_host(nsf_ctx* ctx, int32_t op, int32_t dtype, const void* a_host, int64_t na,
+                         const void* b_host, int64_t nb, int32_t cols, int32_t blend_frames, void* out_host) {
+  if (!ctx || !a_host || !out_host || na <= 0 || cols <= 0) { set_error("nsf_rows_host: bad argument"); return NSF_ERR_BAD_ARG; }
+  if (dtype != NSF_F32 && dtype != NSF_F64) { set_error("nsf_rows_host: bad dtype"); return NSF_ERR_BAD_ARG; }
+  int64_t out_rows = 0, k = 0;
+  if (op == NSF_ROWS_INTERP_SLOWER) out_rows = 2 * na - 1;
+  else if (op == NSF_ROWS_SMOOTH) out_rows = na;
+  else if (op == NSF_ROWS_BLEND_STACK) {
+    if (!b_host || nb <= 0) { set_error("nsf_rows_host: blend needs a second array"); return NSF_ERR_BAD_ARG; }
+    k = std::max<int64_t>(0, std::min<int64_t>(std::min<int64_t>(blend_frames, na), nb));
+    out_rows = na + nb - k;
+  } else { set_error("nsf_rows_host: unknown op"); return NSF_ERR_BAD_ARG; }
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  Slot* sl = &ctx->slot[0];
+  nsf_status st = ensure_slot(sl);
+  if (st != NSF_OK) return st;
+  const size_t esz = dtype == NSF_F64 ? 8 : 4;
+  const bool two = op == NSF_ROWS_BLEND_STACK;
+  if ((st = ctx->collect_in_a.reserve(na * cols * esz)) != NSF_OK) return st;
+  if (two && (st = ctx->collect_in_f.reserve(nb * cols * esz)) != NSF_OK) return st;
+  if ((st = ctx->collect_out_a.reserve(out_rows * cols * esz)) != NSF_OK) return st;
+  NSF_CUDA(cudaMemcpyAsync(ctx->collect_in_a.ptr, a_host, na * cols * esz, cudaMemcpyHostToDevice, sl->stream));
+  if (two) NSF_CUDA(cudaMemcpyAsync(ctx->collect_in_f.ptr, b_host, nb * cols * esz, cudaMemcpyHostToDevice, sl->stream));
+  const int n = launch_rows_op(sl->stream, op, dtype, ctx->collect_in_a.ptr, na, two ? ctx->collect_in_f.ptr : nullptr,
+                               nb, cols, k, ctx->collect_out_a.ptr, out_rows);
+  if (n < 0) { set_error(cuda_msg("launch_rows_op", cudaGetLastError())); return NSF_ERR_CUDA; }
+  ctx->launches += n;
+  NSF_CUDA(cudaMemcpyAsync(out_host, ctx->collect_out_a.ptr, out_rows * cols * esz, cudaMemcpyDeviceToHost, sl->stream));
+  NSF_CUDA(cudaStreamSynchronize(sl->stream));
+  return NSF_OK;
+}
+
+nsf_status nsf_post_host(nsf_ctx* ctx, const float* in_host, int64_t T, int32_t Cc, uint32_t pf, float* out_host) {
+  if (!ctx || !in_host || !out_host || T <= 0 || Cc <= 0) { set_error("nsf_post_host: bad argument"); return NSF_ERR_BAD_ARG; }
+  if ((pf & NSF_POST_DELTAS) && T < 9) { set_error("nsf_post_host: delta needs at least 9 frames"); return NSF_ERR_TOO_SHORT; }
+  if ((pf & NSF_POST_EDGEFIX) && T < 2) { set_error("nsf_post_host: edge fix needs 2 frames"); return NSF_ERR_BAD_ARG; }
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  Slot* sl = &ctx->slot[0];
+  nsf_status st = ensure_slot(sl);
+  if (st != NSF_OK) return st;
+  const bool reduce = (pf & NSF_POST_REDUCE) != 0, deltas = (pf & NSF_POST_DELTAS) != 0, cmvn = (pf & NSF_POST_CMVN) != 0;
+  const int64_t rows = reduce ? (T + 1) / 2 : T;
+  const int out_c = Cc * (deltas ? 3 : 1);
+  // device layout: [in T*C floats][out rows*out_c floats][desc 6 x int64][sum C][sumsq C]
+  const size_t in_b = align_up(T * Cc * sizeof(float)), out_b = align_up(rows * out_c * sizeof(float));
+  const size_t desc_b = align_up(6 * sizeof(int64_t)), st_b = align_up(Cc * sizeof(double));
+  if ((st = ctx->collect_in_a.reserve(in_b + out_b + desc_b + 2 * st_b)) != NSF_OK) return st;
+  char* base = static_cast<char*>(ctx->collect_in_a.ptr);
+  float* d_in = reinterpret_cast<float*>(base);
+  float* d_out = reinterpret_cast<float*>(base + in_b);
+  int64_t* d_desc = reinterpret_cast<int64_t*>(base + in_b + out_b);
+  double* d_sum = reinterpret_cast<double*>(base + in_b + out_b + desc_b);
+  double* d_sq = reinterpret_cast<double*>(base + in_b + out_b + desc_b + st_b);
+  if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
+  if ((st = ctx->desc_host.reserve(6 * sizeof(int64_t))) != NSF_OK) return st;
+  int64_t* h = static_cast<int64_t*>(ctx->desc_host.ptr);
+  h[0] = 0; h[1] = 0;           // clip_off (unused by the post kernels)
+  h[2] = 0; h[3] = T;           // frame_off
+  h[4] = 0; h[5] = rows;        // row_off
+  NSF_CUDA(cudaMemcpyAsync(d_desc, h, 6 * sizeof(int64_t), cudaMemcpyHostToDevice, sl->stream));
+  NSF_CUDA(cudaEventRecord(ctx->desc_copied, sl->stream));
+  ctx->desc_pending = true;
+  NSF_CUDA(cudaMemcpyAsync(d_in, in_host, T * Cc * sizeof(float), cudaMemcpyHostToDevice, sl->stream));
+  int launched = 0, n;
+  if (pf & NSF_POST_EDGEFIX) {
+    if ((n = launch_edge_fix(sl->stream, d_in, T, Cc)) < 0) { set_error(cuda_msg("launch_edge_fix", cudaGetLastError())); return NSF_ERR_CUDA; }
+    launched += n;
+  }
+  if (cmvn) {
+    if ((n = launch_col_stats(sl->stream, d_in, T, Cc, d_sum, d_sq)) < 0) { set_error(cuda_msg("launch_col_stats", cudaGetLastError())); return NSF_ERR_CUDA; }
+    launched += n;
+  }
+  BatchView b;
+  b.clip_off = d_desc; b.frame_off = d_desc + 2; b.row_off = d_desc + 4;
+  b.n_clips = 1; b.total_samples = 0; b.total_frames = T; b.total_rows = rows;
+  if ((n = launch_delta_reduce(sl->stream, b, d_in, Cc, Cc, d_sum, d_sq, cmvn, deltas, reduce, d_out, out_c, 0)) < 0) {
+    set_error(cuda_msg("launch_delta_reduce", cudaGetLastError())); return NSF_ERR_CUDA;
+  }
+  launched += n;
+  ctx->launches += launched;
+  NSF_CUDA(cudaMemcpyAsync(out_host, d_out, rows * out_c * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+  NSF_CUDA(cudaStreamSynchronize(sl->stream));
+  return NSF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// Small device helpers shared by the kernel translation units.
+#ifndef NSF_DEVICE_UTILS_CUH_
+#define NSF_DEVICE_UTILS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nsf {
+
+// Largest c in [0, n) with off[c] <= g (off is a non-decreasing prefix sum, off[0] == 0).
+__device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int n, int64_t g) {
+  int lo = 0, hi = n;  // invariant: off[lo] <= g < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(off + mid) <= g) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace nsf
+#endif  // NSF_DEVICE_UTILS_CUH_

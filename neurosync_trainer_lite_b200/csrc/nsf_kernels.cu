@@ -1,0 +1,896 @@
+// Bandwidth- and FMA-bound kernels of the feature front-end (sm_100a).
+//
+//   k_absmax / k_normalize   utils/audio/load_audio.py:12-14       (HBM bound)
+//   k_fold32 / k_dft_simt    validation-only fp32 STFT path (NSF_DEBUG_SIMT_DFT); the product path
+//                            is the tcgen05 kernel in nsf_stft_tc.cu
+//   k_mel_db                 mel projection (sparse: 1.5 % of the 128 x 736 basis is non-zero),
+//                            10 log10(max(1e-10, .)), per-clip max       (HBM bound)
+//   k_dct_sum / k_dev_sq     top_db floor, DCT-II to n_mfcc, CMVN statistics
+//   k_delta_reduce           CMVN, Savitzky-Golay delta / delta-delta, pair reduction
+//   k_autocorr               reflect-pad framing, DC removal, np.hanning, 188 lags, normalise,
+//                            edge fix, pair reduction  (fp32 FMA bound; extract_features_utils.py:54-113)
+//   k_smooth                 smooth_features (extract_features_utils.py:47-51)
+//   k_collect                collect_features augmentation (dataset/data_processing.py:126-197)
+#include <cuda_fp16.h>
+
+#include "nsf.h"
+#include "nsf_device_utils.cuh"
+#include "nsf_kernels.cuh"
+
+namespace nsf {
+
+namespace {
+
+constexpr int kSmCount = 148;
+
+// order-preserving float -> uint32 key (so atomicMax works for negative dB values); 0 = "-inf"
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+template <typename T> __device__ __forceinline__ float decode_pcm(T v);
+template <> __device__ __forceinline__ float decode_pcm<float>(float v) { return v; }
+template <> __device__ __forceinline__ float decode_pcm<int16_t>(int16_t v) {
+  return static_cast<float>(v) * (1.0f / 32768.0f);  // exact: soundfile's int16 -> float32
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: per-clip max|y|.  Each block owns a fixed chunk of the packed signal and walks the clips
+// that intersect it; one atomicMax per (block, clip).
+// ------------------------------------------------------------------------------------------------
+constexpr int kChunk = 16384;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_absmax(const T* __restrict__ pcm, BatchView b,
+                                                uint32_t* __restrict__ peak_bits) {
+  __shared__ float s_part[8];
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kChunk;
+  const int64_t c1 = min(c0 + kChunk, b.total_samples);
+  int clip = find_segment(b.clip_off, b.n_clips, c0);
+  int64_t s = c0;
+  while (s < c1) {
+    const int64_t e = min(c1, __ldg(b.clip_off + clip + 1));
+    float m = 0.0f;
+    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) m = fmaxf(m, fabsf(decode_pcm<T>(pcm[i])));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float r = s_part[0];
+      for (int w = 1; w < 8; ++w) r = fmaxf(r, s_part[w]);
+      atomicMax(peak_bits + clip, __float_as_uint(r));  // r >= 0: bit order == value order
+    }
+    __syncthreads();
+    s = e;
+    ++clip;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_normalize(const T* __restrict__ pcm, BatchView b,
+                                                   const uint32_t* __restrict__ peak_bits,
+                                                   bool use_peak, float* __restrict__ y) {
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kChunk;
+  const int64_t c1 = min(c0 + kChunk, b.total_samples);
+  int clip = find_segment(b.clip_off, b.n_clips, c0);
+  int64_t s = c0;
+  while (s < c1) {
+    const int64_t e = min(c1, __ldg(b.clip_off + clip + 1));
+    const float peak = use_peak ? __uint_as_float(__ldg(peak_bits + clip)) : 0.0f;
+    if (peak > 0.0f) {
+      // IEEE division: bit-identical to numpy's float32 y / max_val
+      for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x)
+        y[i] = __fdiv_rn(decode_pcm<T>(pcm[i]), peak);
+    } else {
+      for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) y[i] = decode_pcm<T>(pcm[i]);
+    }
+    s = e;
+    ++clip;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Validation STFT path, fp32 on CUDA cores: fold (signed 4-tap gather) + small GEMMs + |.|^2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fold32(DeviceTables t, BatchView b,
+                                                const float* __restrict__ y,
+                                                float* __restrict__ a32) {
+  extern __shared__ float s_x[];  // [F]
+  for (int64_t g = blockIdx.x; g < b.total_frames; g += gridDim.x) {
+    const int clip = find_segment(b.frame_off, b.n_clips, g);
+    const int64_t tf = g - __ldg(b.frame_off + clip);
+    const int64_t base = __ldg(b.clip_off + clip);
+    const int64_t len = __ldg(b.clip_off + clip + 1) - base;
+    const int64_t first = tf * t.H - t.pad;  // zero padding (librosa stft center=True, constant)
+    for (int n = threadIdx.x; n < t.F; n += blockDim.x) {
+      const int64_t i = first + n;
+      s_x[n] = (i >= 0 && i < len) ? __ldg(y + base + i) : 0.0f;
+    }
+    __syncthreads();
+    for (int c = 0; c < t.chains; ++c) {
+      const int kp = t.kp[c];
+      for (int e = threadIdx.x; e < 2 * kp; e += blockDim.x) {
+        const int part = e / kp, j = e - part * kp;
+        float acc = 0.0f;
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+          const int o = (part * 4 + tap) * kp + j;
+          acc = fmaf(__ldg(t.tap_coef[c] + o), s_x[__ldg(t.tap_idx[c] + o)], acc);
+        }
+        a32[(static_cast<int64_t>(c * 2 + part) * b.total_frames + g) * kp + j] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// 64 frames x 64 bins per block, both Re and Im accumulators, K chunks of 16.
+__global__ void __launch_bounds__(256) k_dft_simt(DeviceTables t, BatchView b,
+                                                  const float* __restrict__ a32,
+                                                  float* __restrict__ power) {
+  const int c = blockIdx.z;
+  const int kp = t.kp[c], np = t.np[c], nb = t.nbins[c];
+  const int n0 = blockIdx.y * 64;
+  if (n0 >= np) return;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * 64;
+  __shared__ float As[2][16][64 + 4];
+  __shared__ float Bs[2][16][64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][4][4] = {};
+  const float* A0 = a32 + static_cast<int64_t>(c * 2 + 0) * b.total_frames * kp;
+  const float* A1 = a32 + static_cast<int64_t>(c * 2 + 1) * b.total_frames * kp;
+  for (int k0 = 0; k0 < kp; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, kk = e & 15;
+      const int64_t g = g0 + r;
+      const bool ok = g < b.total_frames;
+      As[0][kk][r] = ok ? A0[g * kp + k0 + kk] : 0.0f;
+      As[1][kk][r] = ok ? A1[g * kp + k0 + kk] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      const int kk = e >> 6, n = e & 63;
+      const bool ok = (n0 + n) < np;
+      Bs[0][kk][n] = ok ? __ldg(t.mat32[c][0] + static_cast<int64_t>(k0 + kk) * np + n0 + n) : 0.0f;
+      Bs[1][kk][n] = ok ? __ldg(t.mat32[c][1] + static_cast<int64_t>(k0 + kk) * np + n0 + n) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[2][4], bb[2][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[0][i] = As[0][kk][ty * 4 + i];
+        a[1][i] = As[1][kk][ty * 4 + i];
+        bb[0][i] = Bs[0][kk][tx * 4 + i];
+        bb[1][i] = Bs[1][kk][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[0][i][j] = fmaf(a[0][i], bb[0][j], acc[0][i][j]);
+          acc[1][i][j] = fmaf(a[1][i], bb[1][j], acc[1][i][j]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t g = g0 + ty * 4 + i;
+    if (g >= b.total_frames) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = n0 + tx * 4 + j;
+      if (m < nb) {
+        const float re = acc[0][i][j], im = acc[1][i][j];
+        power[g * t.bins_ld + t.col_off[c] + m] = fmaf(re, re, im * im);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1c: sparse mel projection + dB + per-clip dB max.  One warp per frame; lane handles mels
+// lane, lane+32, ... ; the power row is staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMelWarps = 8;
+__global__ void __launch_bounds__(kMelWarps * 32) k_mel_db(DeviceTables t, BatchView b,
+                                                           const float* __restrict__ power,
+                                                           float* __restrict__ db,
+                                                           uint32_t* __restrict__ dbmax_key) {
+  extern __shared__ float s_pow[];  // [kMelWarps][bins_ld]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = s_pow + warp * t.bins_ld;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kMelWarps;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * kMelWarps + warp; g < b.total_frames;
+       g += stride) {
+    const float4* src = reinterpret_cast<const float4*>(power + g * t.bins_ld);
+    for (int i = lane; i < t.bins_ld / 4; i += 32) reinterpret_cast<float4*>(row)[i] = __ldg(src + i);
+    __syncwarp();
+    float vmax = -INFINITY;
+    for (int m = lane; m < t.n_mels; m += 32) {
+      float acc = 0.0f;
+      for (int c = 0; c < t.chains; ++c) {   // the filter's bins, split into per-chain column runs
+        const int e = c * t.n_mels + m;
+        const int st = __ldg(t.mel_start + e), ln = __ldg(t.mel_len + e);
+        const float* w = t.mel_w + __ldg(t.mel_ptr + e);
+        for (int i = 0; i < ln; ++i) acc = fmaf(__ldg(w + i), row[st + i], acc);
+      }
+      const float v = 10.0f * log10f(fmaxf(1e-10f, acc));
+      db[g * t.n_mels + m] = v;
+      vmax = fmaxf(vmax, v);
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0) {
+      const int clip = find_segment(b.frame_off, b.n_clips, g);
+      atomicMax(dbmax_key + clip, float_key(vmax));
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: top_db floor + DCT-II (first n_mfcc) + per-clip sum.  One warp per run of frames; lane = k.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDctWarps = 8;
+constexpr int kDctRun = 16;  // consecutive frames per warp -> 16x fewer atomics
+__global__ void __launch_bounds__(kDctWarps * 32) k_dct_sum(DeviceTables t, BatchView b,
+                                                            const float* __restrict__ db,
+                                                            const uint32_t* __restrict__ dbmax_key,
+                                                            float* __restrict__ mfcc_raw,
+                                                            double* __restrict__ sum) {
+  __shared__ float s_dct[128 * 32];           // [m][k] (k padded to 32): conflict-free per lane
+  __shared__ float s_v[kDctWarps][128];
+  for (int i = threadIdx.x; i < t.n_mels * 32; i += blockDim.x) s_dct[i] = __ldg(t.dct_t + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_runs = (b.total_frames + kDctRun - 1) / kDctRun;
+  for (int64_t run = static_cast<int64_t>(blockIdx.x) * kDctWarps + warp; run < n_runs;
+       run += static_cast<int64_t>(gridDim.x) * kDctWarps) {
+    const int64_t g_begin = run * kDctRun, g_end = min(g_begin + kDctRun, b.total_frames);
+    int clip = find_segment(b.frame_off, b.n_clips, g_begin);
+    int64_t clip_end = __ldg(b.frame_off + clip + 1);
+    float floor_db = key_float(__ldg(dbmax_key + clip)) - 80.0f;
+    double run_sum = 0.0;
+    for (int64_t g = g_begin; g < g_end; ++g) {
+      if (g >= clip_end) {
+        if (lane < t.n_mfcc) atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sum);
+        run_sum = 0.0;
+        while (g >= clip_end) { ++clip; clip_end = __ldg(b.frame_off + clip + 1); }
+        floor_db = key_float(__ldg(dbmax_key + clip)) - 80.0f;
+      }
+      for (int m = lane; m < t.n_mels; m += 32)
+        s_v[warp][m] = fmaxf(__ldg(db + g * t.n_mels + m), floor_db);
+      __syncwarp();
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int m = 0; m < t.n_mels; ++m) acc = fmaf(s_dct[m * 32 + lane], s_v[warp][m], acc);
+      if (lane < t.n_mfcc) {
+        mfcc_raw[g * t.n_mfcc + lane] = acc;
+        run_sum += static_cast<double>(acc);
+      }
+      __syncwarp();
+    }
+    if (lane < t.n_mfcc) atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sum);
+  }
+}
+
+// K2b: sum of squared deviations from the clip mean (numpy's two-pass std, ddof = 0)
+__global__ void __launch_bounds__(kDctWarps * 32) k_dev_sq(DeviceTables t, BatchView b,
+                                                           const float* __restrict__ mfcc_raw,
+                                                           const double* __restrict__ sum,
+                                                           double* __restrict__ sumsq) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_runs = (b.total_frames + kDctRun - 1) / kDctRun;
+  for (int64_t run = static_cast<int64_t>(blockIdx.x) * kDctWarps + warp; run < n_runs;
+       run += static_cast<int64_t>(gridDim.x) * kDctWarps) {
+    const int64_t g_begin = run * kDctRun, g_end = min(g_begin + kDctRun, b.total_frames);
+    int clip = find_segment(b.frame_off, b.n_clips, g_begin);
+    int64_t clip_end = __ldg(b.frame_off + clip + 1);
+    double mean = 0.0, acc = 0.0;
+    auto load_mean = [&]() {
+      const double T = static_cast<double>(clip_end - __ldg(b.frame_off + clip));
+      mean = lane < t.n_mfcc ? __ldg(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane) / T : 0.0;
+    };
+    load_mean();
+    for (int64_t g = g_begin; g < g_end; ++g) {
+      if (g >= clip_end) {
+        if (lane < t.n_mfcc) atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + lane, acc);
+        acc = 0.0;
+        while (g >= clip_end) { ++clip; clip_end = __ldg(b.frame_off + clip + 1); }
+        load_mean();
+      }
+      if (lane < t.n_mfcc) {
+        const double d = static_cast<double>(__ldg(mfcc_raw + g * t.n_mfcc + lane)) - mean;
+        acc = fma(d, d, acc);
+      }
+    }
+    if (lane < t.n_mfcc) atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + lane, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: CMVN -> Savitzky-Golay delta / delta-delta (width 9, edges = value at frame 4 / T-5)
+//     -> pair reduction.  Thread per (output row, channel).
+//     extract_features_utils.py:5-8,21-27,33-44; librosa.feature.delta == scipy savgol 'interp'.
+// ------------------------------------------------------------------------------------------------
+struct DeltaOut { float v, d1, d2; };
+
+__device__ __forceinline__ DeltaOut delta_at(const float* __restrict__ col, int in_ld, int64_t T,
+                                             int64_t tf, float mu, float inv_scale_den, bool cmvn,
+                                             bool deltas) {
+  // col points at frame 0 of this clip for this channel
+  auto val = [&](int64_t f) {
+    const float x = __ldg(col + f * in_ld);
+    return cmvn ? __fdiv_rn(x - mu, inv_scale_den) : x;
+  };
+  DeltaOut o;
+  o.v = val(tf);
+  o.d1 = 0.0f;
+  o.d2 = 0.0f;
+  if (deltas) {
+    const int64_t tc = min(max(tf, static_cast<int64_t>(4)), T - 5);
+    float x[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) x[k] = val(tc - 4 + k);
+    // delta: sum k x[k] / 60 ; delta2: [28 7 -8 -17 -20 -17 -8 7 28] / 462
+    const float s1 = 4.0f * (x[8] - x[0]) + 3.0f * (x[7] - x[1]) + 2.0f * (x[6] - x[2]) + (x[5] - x[3]);
+    const float s2 = 28.0f * (x[0] + x[8]) + 7.0f * (x[1] + x[7]) - 8.0f * (x[2] + x[6]) -
+                     17.0f * (x[3] + x[5]) - 20.0f * x[4];
+    o.d1 = s1 * (1.0f / 60.0f);
+    o.d2 = s2 * (1.0f / 462.0f);
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(256) k_delta_reduce(BatchView b, const float* __restrict__ in, int C,
+                                                      int in_ld, const double* __restrict__ sum,
+                                                      const double* __restrict__ sumsq, bool cmvn,
+                                                      bool deltas, bool reduce,
+                                                      float* __restrict__ out, int64_t out_ld,
+                                                      int col0) {
+  const int rows_per_block = blockDim.x / 32;
+  const int lane = threadIdx.x & 31, wr = threadIdx.x >> 5;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * rows_per_block + wr; r < b.total_rows;
+       r += static_cast<int64_t>(gridDim.x) * rows_per_block) {
+    const int clip = find_segment(b.row_off, b.n_clips, r);
+    const int64_t f0 = __ldg(b.frame_off + clip);
+    const int64_t T = __ldg(b.frame_off + clip + 1) - f0;
+    const int64_t lr = r - __ldg(b.row_off + clip);
+    const int64_t ta = reduce ? 2 * lr : lr;
+    const bool pair = reduce && (ta + 1 < T);
+    for (int ch = lane; ch < C; ch += 32) {
+      float mu = 0.0f, den = 1.0f;
+      if (cmvn) {
+        const double Td = static_cast<double>(T);
+        const double m = __ldg(sum + static_cast<int64_t>(clip) * C + ch) / Td;
+        const double var = __ldg(sumsq + static_cast<int64_t>(clip) * C + ch) / Td;
+        mu = static_cast<float>(m);
+        den = static_cast<float>(sqrt(var)) + 1e-10f;  // float32 std + 1e-10 (NEP 50: stays float32)
+      }
+      const float* col = in + f0 * in_ld + ch;
+      DeltaOut a = delta_at(col, in_ld, T, ta, mu, den, cmvn, deltas);
+      if (pair) {
+        const DeltaOut c2 = delta_at(col, in_ld, T, ta + 1, mu, den, cmvn, deltas);
+        a.v = 0.5f * (a.v + c2.v);
+        a.d1 = 0.5f * (a.d1 + c2.d1);
+        a.d2 = 0.5f * (a.d2 + c2.d2);
+      }
+      float* o = out + r * out_ld + col0;
+      o[ch] = a.v;
+      if (deltas) {
+        o[C + ch] = a.d1;
+        o[2 * C + ch] = a.d2;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: autocorrelation.  One warp per output row (frame pair).  The mean-removed, Hann-windowed
+// frame lives in shared memory; lane (g, q) accumulates 12 lags [12q, 12q+12) over half of the
+// frame (g) with a sliding register window: 48 FMAs per two 128-bit shared loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAcWarps = 8;
+constexpr int kAcLagsPerLane = 12;
+constexpr int kAcTail = 16 * kAcLagsPerLane + 16;  // zero tail so x[n + lag] never leaves the row
+
+struct AcGeom { int half; int row_floats; };  // half = samples per n-group (multiple of 16)
+__host__ __device__ inline AcGeom ac_geom(int F) {
+  AcGeom g;
+  g.half = (((F + 1) / 2) + 15) / 16 * 16;
+  g.row_floats = 2 * g.half + kAcTail;
+  return g;
+}
+
+// Computes normalised lags of hop-frame tf into acc[0..11] of lanes with g == 0 (lag = 12 q + j);
+// returns r[0]-normalised values; lane (0,0)'s acc[0] is lag 0 (== 1 or 0).
+__device__ __forceinline__ void autocorr_frame(const DeviceTables& t, const float* __restrict__ y,
+                                               int64_t base, int64_t len, int64_t tf, float* xs,
+                                               const AcGeom& geo, int lane, float (&acc)[kAcLagsPerLane]) {
+  const int F = t.F;
+  const int64_t first = tf * t.H - t.pad;
+  // pass 1: load with np.pad(..., mode='reflect') indexing, accumulate the mean
+  float part = 0.0f;
+  for (int n = lane; n < F; n += 32) {
+    int64_t i = first + n;
+    if (i < 0) i = -i;
+    if (i >= len) i = 2 * (len - 1) - i;
+    const float v = __ldg(y + base + i);
+    xs[n] = v;
+    part += v;
+  }
+  const float mean = warp_sum(part) / static_cast<float>(F);
+  __syncwarp();
+  for (int n = lane; n < F; n += 32) xs[n] = (xs[n] - mean) * __ldg(t.hann_sym + n);
+  for (int n = F + lane; n < geo.row_floats; n += 32) xs[n] = 0.0f;
+  __syncwarp();
+
+  const int g = lane >> 4, q = lane & 15;
+#pragma unroll
+  for (int j = 0; j < kAcLagsPerLane; ++j) acc[j] = 0.0f;
+  const float* xa = xs + g * geo.half;                 // x[n]
+  const float* xw = xa + q * kAcLagsPerLane;           // x[n + lag0 + ...], 16-byte aligned
+  float4 w[4];
+  w[0] = *reinterpret_cast<const float4*>(xw);
+  w[1] = *reinterpret_cast<const float4*>(xw + 4);
+  w[2] = *reinterpret_cast<const float4*>(xw + 8);
+  for (int n = 0; n < geo.half; n += 16) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(xa + n + 4 * s);
+      w[(s + 3) & 3] = *reinterpret_cast<const float4*>(xw + n + 4 * s + 12);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      float wv[16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 ww = w[(s + k) & 3];
+        wv[4 * k + 0] = ww.x; wv[4 * k + 1] = ww.y; wv[4 * k + 2] = ww.z; wv[4 * k + 3] = ww.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < kAcLagsPerLane; ++j) acc[j] = fmaf(av[i], wv[i + j], acc[j]);
+    }
+  }
+  // combine the two n-groups, normalise by lag 0 when it is non-zero
+#pragma unroll
+  for (int j = 0; j < kAcLagsPerLane; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+  const float r0 = __shfl_sync(0xffffffffu, acc[0], 0);
+  if (r0 != 0.0f) {
+#pragma unroll
+    for (int j = 0; j < kAcLagsPerLane; ++j) acc[j] = __fdiv_rn(acc[j], r0);
+  }
+  __syncwarp();
+}
+
+// true when every kept coefficient (lags 1..n_lags) is below the 1e-7 threshold
+__device__ __forceinline__ bool ac_all_small(const float (&acc)[kAcLagsPerLane], int lane, int n_lags) {
+  const int q = lane & 15;
+  bool small = true;
+#pragma unroll
+  for (int j = 0; j < kAcLagsPerLane; ++j) {
+    const int lag = q * kAcLagsPerLane + j;
+    if (lag >= 1 && lag <= n_lags && !(fabsf(acc[j]) < 1e-7f)) small = false;
+  }
+  return __all_sync(0xffffffffu, small);
+}
+
+__global__ void __launch_bounds__(kAcWarps * 32) k_autocorr(DeviceTables t, BatchView b,
+                                                            const float* __restrict__ y, bool reduce,
+                                                            float* __restrict__ out, int64_t out_ld,
+                                                            int col0) {
+  extern __shared__ __align__(16) float s_ac[];
+  const AcGeom geo = ac_geom(t.F);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* xs = s_ac + static_cast<size_t>(warp) * geo.row_floats;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kAcWarps + warp; r < b.total_rows;
+       r += static_cast<int64_t>(gridDim.x) * kAcWarps) {
+    const int clip = find_segment(b.row_off, b.n_clips, r);
+    const int64_t base = __ldg(b.clip_off + clip);
+    const int64_t len = __ldg(b.clip_off + clip + 1) - base;
+    const int64_t T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
+    const int64_t lr = r - __ldg(b.row_off + clip);
+    float va[kAcLagsPerLane], vb[kAcLagsPerLane];
+    if (reduce) {
+      const int64_t ta = 2 * lr;
+      const bool pair = ta + 1 < T;
+      autocorr_frame(t, y, base, len, ta, xs, geo, lane, va);
+      if (pair) {
+        autocorr_frame(t, y, base, len, ta + 1, xs, geo, lane, vb);
+        // fix_edge_frames_autocorr: first frame copies frame 1, last frame copies frame T-2
+        if (ta == 0 && ac_all_small(va, lane, t.n_lags)) {
+#pragma unroll
+          for (int j = 0; j < kAcLagsPerLane; ++j) va[j] = vb[j];
+        }
+        if (ta + 1 == T - 1 && ac_all_small(vb, lane, t.n_lags)) {
+#pragma unroll
+          for (int j = 0; j < kAcLagsPerLane; ++j) vb[j] = va[j];
+        }
+#pragma unroll
+        for (int j = 0; j < kAcLagsPerLane; ++j) va[j] = 0.5f * (va[j] + vb[j]);
+      } else if (ta == T - 1 && ac_all_small(va, lane, t.n_lags)) {
+        autocorr_frame(t, y, base, len, T - 2, xs, geo, lane, va);  // odd T: last row passes through
+      }
+    } else {
+      autocorr_frame(t, y, base, len, lr, xs, geo, lane, va);
+      if (lr == 0 && ac_all_small(va, lane, t.n_lags)) {
+        autocorr_frame(t, y, base, len, 1, xs, geo, lane, va);
+      } else if (lr == T - 1 && ac_all_small(va, lane, t.n_lags)) {
+        autocorr_frame(t, y, base, len, T - 2, xs, geo, lane, va);
+      }
+    }
+    if (lane < 16) {
+      float* o = out + r * out_ld + col0;
+#pragma unroll
+      for (int j = 0; j < kAcLagsPerLane; ++j) {
+        const int lag = lane * kAcLagsPerLane + j;
+        if (lag >= 1 && lag <= t.n_lags) o[lag - 1] = va[j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// smooth_features: row i <- (row i-1 + row i) / 2 inside each clip (from the original rows)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_smooth(BatchView b, const float* __restrict__ in,
+                                                int64_t in_ld, int cols, float* __restrict__ out,
+                                                int64_t out_ld) {
+  for (int64_t r = blockIdx.x; r < b.total_rows; r += gridDim.x) {
+    const int clip = find_segment(b.row_off, b.n_clips, r);
+    const bool first = (r == __ldg(b.row_off + clip));
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const float cur = in[r * in_ld + c];
+      out[r * out_ld + c] = first ? cur : (in[(r - 1) * in_ld + c] + cur) * 0.5f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// collect_features augmentation.  One block per output row; the row's provenance (which version,
+// blend weights) is resolved once, then threads stream the 256 + 61 columns.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Arith;
+template <> struct Arith<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+};
+template <> struct Arith<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+};
+
+// np.linspace(start, stop, n)[i] exactly as numpy evaluates it (arange * step + start, endpoint set)
+__device__ __forceinline__ double linspace_at(double start, double stop, int64_t n, int64_t i) {
+  if (n == 1) return start;
+  if (i == n - 1) return stop;
+  const double step = (stop - start) / static_cast<double>(n - 1);
+  return __dadd_rn(__dmul_rn(static_cast<double>(i), step), start);
+}
+
+// value of version `ver` at its row j, column c, for source matrix `src` (rows [s0, s0+n))
+// ver 0: original, 1: fast rows[::2], 2: slow = interpolate_slower (+ smoothing when smooth_slow)
+template <typename T>
+__device__ __forceinline__ T version_value(const T* __restrict__ src, int64_t ld, int ver, int64_t j,
+                                           int c, bool smooth_slow) {
+  using A = Arith<T>;
+  auto at = [&](int64_t row) { return src[row * ld + c]; };
+  auto slow = [&](int64_t k) -> T {
+    if ((k & 1) == 0) return at(k >> 1);
+    return A::mul(A::add(at(k >> 1), at((k >> 1) + 1)), static_cast<T>(0.5));
+  };
+  if (ver == 0) return at(j);
+  if (ver == 1) return at(2 * j);
+  if (!smooth_slow || j == 0) return slow(j);
+  return A::mul(A::add(slow(j - 1), slow(j)), static_cast<T>(0.5));  // smooth_facial_data
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_collect(CollectView v, const T* __restrict__ audio,
+                                                 int a_cols, const T* __restrict__ facial, int f_cols,
+                                                 T* __restrict__ out_audio, T* __restrict__ out_facial) {
+  using A = Arith<T>;
+  for (int64_t r = blockIdx.x; r < v.total_out_rows; r += gridDim.x) {
+    const int clip = find_segment(v.o_off, v.n_clips, r);
+    const int64_t p = r - __ldg(v.o_off + clip);
+    int64_t a0 = __ldg(v.a_off + clip), na = __ldg(v.a_off + clip + 1) - a0;
+    int64_t f0 = __ldg(v.f_off + clip), nf = __ldg(v.f_off + clip + 1) - f0;
+    // centre-trim the longer stream (data_processing.py:126-145)
+    if (na > nf) a0 += (na - nf) / 2; else if (nf > na) f0 += (nf - na) / 2;
+    const int64_t n = min(na, nf);
+    // version lengths and blend zones (stack_with_blend, data_processing.py:179-197)
+    int ver[3]; int64_t vlen[3]; int nv = 0;
+    ver[nv] = 0; vlen[nv++] = n;
+    if (v.flags & NSF_COLLECT_FAST) { ver[nv] = 1; vlen[nv++] = (n + 1) / 2; }
+    if (v.flags & NSF_COLLECT_SLOW) { ver[nv] = 2; vlen[nv++] = n > 0 ? 2 * n - 1 : 0; }
+    const bool blend = (v.flags & NSF_COLLECT_BLEND) != 0;
+    int64_t len_before[3], nb[3];  // result length before stacking version i, blend rows used
+    int64_t total = vlen[0];
+    len_before[0] = 0; nb[0] = 0;
+    for (int i = 1; i < nv; ++i) {
+      int64_t k = blend ? min(min(static_cast<int64_t>(v.blend_frames), total), vlen[i]) : 0;
+      if (k < 0) k = 0;
+      len_before[i] = total; nb[i] = k;
+      total += vlen[i] - k;
+    }
+    // Resolve row p by walking from the last stacked version down.  Level i of the stack is
+    //   [ result_{i-1}[: L-k] | w1*result_{i-1}[L-k+q] + w2*V_i[q], q < k | V_i[k:] ],  L = len(result_{i-1})
+    // so a row is one "terminal" version row plus at most two enclosing cross-fades.
+    int term_ver = ver[0];
+    int64_t term_row = p;
+    int n_blend = 0, blend_level[2];
+    int64_t blend_q[2];
+    for (int level = nv - 1; level >= 1; --level) {
+      const int64_t L = len_before[level], k = nb[level];
+      if (p >= L) { term_ver = ver[level]; term_row = p - L + k; break; }
+      if (p >= L - k) { blend_level[n_blend] = level; blend_q[n_blend] = p - (L - k); ++n_blend; }
+    }
+    // evaluate per column, innermost first
+    const int cols_total = a_cols + f_cols;
+    for (int c = threadIdx.x; c < cols_total; c += blockDim.x) {
+      const bool is_a = c < a_cols;
+      const T* src = is_a ? audio + a0 * a_cols : facial + f0 * f_cols;
+      const int64_t ld = is_a ? a_cols : f_cols;
+      const int cc = is_a ? c : c - a_cols;
+      const bool smooth_slow = !is_a;
+      T val = version_value<T>(src, ld, term_ver, term_row, cc, smooth_slow);
+      for (int bi = n_blend - 1; bi >= 0; --bi) {
+        const int lv = blend_level[bi];
+        const int64_t q = blend_q[bi], k = nb[lv];
+        const T w1 = static_cast<T>(linspace_at(1.0, 0.0, k, q));
+        const T w2 = static_cast<T>(linspace_at(0.0, 1.0, k, q));
+        const T nv_val = version_value<T>(src, ld, ver[lv], q, cc, smooth_slow);
+        val = A::add(A::mul(w1, val), A::mul(w2, nv_val));
+      }
+      if (is_a) out_audio[r * a_cols + cc] = val; else out_facial[r * f_cols + cc] = val;
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone row helpers with the reference's rounding order (templated float / double).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_rows_op(int op, const T* __restrict__ a, int64_t na,
+                                                 const T* __restrict__ b, int64_t nb, int cols,
+                                                 int64_t k, T* __restrict__ out, int64_t out_rows) {
+  using A = Arith<T>;
+  const int64_t total = out_rows * cols;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e / cols;
+    const int c = static_cast<int>(e - r * cols);
+    T v;
+    if (op == NSF_ROWS_INTERP_SLOWER) {
+      v = (r & 1) ? A::mul(A::add(a[(r >> 1) * cols + c], a[((r >> 1) + 1) * cols + c]), static_cast<T>(0.5))
+                  : a[(r >> 1) * cols + c];
+    } else if (op == NSF_ROWS_SMOOTH) {
+      v = r == 0 ? a[c] : A::mul(A::add(a[(r - 1) * cols + c], a[r * cols + c]), static_cast<T>(0.5));
+    } else {  // NSF_ROWS_BLEND_STACK
+      if (r < na - k) v = a[r * cols + c];
+      else if (r < na) {
+        const int64_t q = r - (na - k);
+        const T w1 = static_cast<T>(linspace_at(1.0, 0.0, k, q));
+        const T w2 = static_cast<T>(linspace_at(0.0, 1.0, k, q));
+        v = A::add(A::mul(w1, a[r * cols + c]), A::mul(w2, b[q * cols + c]));
+      } else v = b[(r - na + k) * cols + c];
+    }
+    out[e] = v;
+  }
+}
+
+// one block per channel: sum, then sum of squared deviations from the mean (two-pass, float64)
+__global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ in, int64_t T, int C,
+                                                   double* __restrict__ sum, double* __restrict__ sumsq) {
+  __shared__ double s_red[8];
+  __shared__ double s_mean;
+  const int c = blockIdx.x;
+  auto block_sum = [&](double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < 8; ++w) r += s_red[w];
+    __syncthreads();
+    return r;
+  };
+  double acc = 0.0;
+  for (int64_t t = threadIdx.x; t < T; t += blockDim.x) acc += static_cast<double>(in[t * C + c]);
+  const double tot = block_sum(acc);
+  if (threadIdx.x == 0) { sum[c] = tot; s_mean = tot / static_cast<double>(T); }
+  __syncthreads();
+  const double mean = s_mean;
+  acc = 0.0;
+  for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
+    const double d = static_cast<double>(in[t * C + c]) - mean;
+    acc = fma(d, d, acc);
+  }
+  const double sq = block_sum(acc);
+  if (threadIdx.x == 0) sumsq[c] = sq;
+}
+
+// fix_edge_frames_autocorr on a frame-major [T][C] matrix, single block
+__global__ void __launch_bounds__(256) k_edge_fix(float* __restrict__ d, int64_t T, int C) {
+  __shared__ int s_big[2];
+  if (threadIdx.x < 2) s_big[threadIdx.x] = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (!(fabsf(d[c]) < 1e-7f)) s_big[0] = 1;
+    if (!(fabsf(d[(T - 1) * C + c]) < 1e-7f)) s_big[1] = 1;
+  }
+  __syncthreads();
+  const bool fix_first = s_big[0] == 0, fix_last = s_big[1] == 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (fix_first) d[c] = d[C + c];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (fix_last) d[(T - 1) * C + c] = d[(T - 2) * C + c];
+  }
+}
+
+int grid_for(int64_t items, int per_block, int max_blocks) {
+  int64_t g = (items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers (return number of kernels launched, or -1 on launch error)
+// ------------------------------------------------------------------------------------------------
+#define NSF_CHECK_LAUNCH() \
+  do { if (cudaGetLastError() != cudaSuccess) return -1; } while (0)
+
+int launch_absmax(cudaStream_t s, const void* pcm, int fmt, const BatchView& b, uint32_t* peak_bits) {
+  if (b.total_samples == 0) return 0;
+  const int grid = static_cast<int>((b.total_samples + kChunk - 1) / kChunk);
+  if (fmt == NSF_PCM_I16)
+    k_absmax<int16_t><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(pcm), b, peak_bits);
+  else
+    k_absmax<float><<<grid, 256, 0, s>>>(static_cast<const float*>(pcm), b, peak_bits);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_normalize(cudaStream_t s, const void* pcm, int fmt, const BatchView& b,
+                     const uint32_t* peak_bits, bool use_peak, float* y) {
+  if (b.total_samples == 0) return 0;
+  const int grid = static_cast<int>((b.total_samples + kChunk - 1) / kChunk);
+  if (fmt == NSF_PCM_I16)
+    k_normalize<int16_t><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(pcm), b, peak_bits, use_peak, y);
+  else
+    k_normalize<float><<<grid, 256, 0, s>>>(static_cast<const float*>(pcm), b, peak_bits, use_peak, y);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_fold32(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y, float* a32) {
+  const int grid = grid_for(b.total_frames, 1, kSmCount * 8);
+  k_fold32<<<grid, 256, t.F * sizeof(float), s>>>(t, b, y, a32);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_dft_simt(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* a32,
+                    float* power) {
+  const int np_max = t.np[0] > t.np[1] ? t.np[0] : t.np[1];
+  dim3 grid(static_cast<unsigned>((b.total_frames + 63) / 64), (np_max + 63) / 64, t.chains);
+  k_dft_simt<<<grid, 256, 0, s>>>(t, b, a32, power);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_mel_db(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* power,
+                  float* db, uint32_t* dbmax_key) {
+  const int grid = grid_for(b.total_frames, kMelWarps, kSmCount * 8);
+  k_mel_db<<<grid, kMelWarps * 32, kMelWarps * t.bins_ld * sizeof(float), s>>>(t, b, power, db, dbmax_key);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* db,
+                   const uint32_t* dbmax_key, float* mfcc_raw, double* sum) {
+  const int grid = grid_for((b.total_frames + kDctRun - 1) / kDctRun, kDctWarps, kSmCount * 6);
+  k_dct_sum<<<grid, kDctWarps * 32, 0, s>>>(t, b, db, dbmax_key, mfcc_raw, sum);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_dev_sq(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* mfcc_raw,
+                  const double* sum, double* sumsq) {
+  const int grid = grid_for((b.total_frames + kDctRun - 1) / kDctRun, kDctWarps, kSmCount * 8);
+  k_dev_sq<<<grid, kDctWarps * 32, 0, s>>>(t, b, mfcc_raw, sum, sumsq);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_delta_reduce(cudaStream_t s, const BatchView& b, const float* in, int C, int in_ld,
+                        const double* sum, const double* sumsq, bool cmvn, bool deltas, bool reduce,
+                        float* out, int64_t out_ld, int col0) {
+  const int grid = grid_for(b.total_rows, 8, kSmCount * 16);
+  k_delta_reduce<<<grid, 256, 0, s>>>(b, in, C, in_ld, sum, sumsq, cmvn, deltas, reduce, out, out_ld, col0);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_autocorr(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
+                    bool reduce, float* out, int64_t out_ld, int col0) {
+  const AcGeom geo = ac_geom(t.F);
+  const size_t smem = static_cast<size_t>(kAcWarps) * geo.row_floats * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) return -1;
+  int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  const int grid = grid_for(b.total_rows, kAcWarps, kSmCount * per_sm);
+  k_autocorr<<<grid, kAcWarps * 32, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_smooth(cudaStream_t s, const BatchView& b, const float* in, int64_t in_ld, int cols,
+                  float* out, int64_t out_ld) {
+  const int grid = grid_for(b.total_rows, 1, kSmCount * 16);
+  k_smooth<<<grid, 256, 0, s>>>(b, in, in_ld, cols, out, out_ld);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_collect(cudaStream_t s, int dtype, const CollectView& v, const void* audio, int a_cols,
+                   const void* facial, int f_cols, void* out_audio, void* out_facial) {
+  if (v.total_out_rows == 0) return 0;
+  const int grid = grid_for(v.total_out_rows, 1, kSmCount * 32);
+  if (dtype == NSF_F64)
+    k_collect<double><<<grid, 128, 0, s>>>(v, static_cast<const double*>(audio), a_cols,
+                                          static_cast<const double*>(facial), f_cols,
+                                          static_cast<double*>(out_audio), static_cast<double*>(out_facial));
+  else
+    k_collect<float><<<grid, 128, 0, s>>>(v, static_cast<const float*>(audio), a_cols,
+                                         static_cast<const float*>(facial), f_cols,
+                                         static_cast<float*>(out_audio), static_cast<float*>(out_facial));
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_rows_op(cudaStream_t s, int op, int dtype, const void* a, int64_t na, const void* b, int64_t nb,
+                   int cols, int64_t k_blend, void* out, int64_t out_rows) {
+  if (out_rows <= 0) return 0;
+  const int grid = grid_for(out_rows * cols, 256 * 4, kSmCount * 16);
+  if (dtype == NSF_F64)
+    k_rows_op<double><<<grid, 256, 0, s>>>(op, static_cast<const double*>(a), na, static_cast<const double*>(b),
+                                          nb, cols, k_blend, static_cast<double*>(out), out_rows);
+  else
+    k_rows_op<float><<<grid, 256, 0, s>>>(op, static_cast<const float*>(a), na, static_cast<const float*>(b), nb,
+                                         cols, k_blend, static_cast<float*>(out), out_rows);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_col_stats(cudaStream_t s, const float* in, int64_t T, int C, double* sum, double* sumsq) {
+  k_col_stats<<<C, 256, 0, s>>>(in, T, C, sum, sumsq);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_edge_fix(cudaStream_t s, float* data, int64_t T, int C) {
+  k_edge_fix<<<1, 256, 0, s>>>(data, T, C);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+}  // namespace nsf

@@ -1,0 +1,478 @@
+// STFT power spectrum on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA into 128B-swizzled shared memory).  Replaces the rFFT inside
+// librosa.feature.mfcc (reference call site: utils/audio/extraction/extract_features_utils.py:19).
+//
+// Maths (DESIGN.md "STFT as four small GEMMs"): two exact symmetries of the DFT kernel turn the
+// F-point real DFT of a windowed frame into, per fold chain (even bins / odd bins), one GEMM for
+// the real parts and one for the imaginary parts, each [frames x K] . [K x bins/2], K = F/4 + 1.
+// That is 4x fewer FLOPs than the plain [frames x F] . [F x 2 bins] DFT-as-GEMM.
+//
+// Precision: inputs are split x = hi + lo into two fp16 values after an exact power-of-two
+// scaling (per frame for the signal, 2^14 for the DFT matrix), and three products
+// hi*hi + hi*lo + lo*hi are accumulated in fp32 in TMEM.  That carries ~22 mantissa bits through
+// the tensor cores (fp32-class accuracy) at 3x the fp16 rate cost; a single fp16/bf16/tf32 pass
+// would be 1e-2..1e-1 off on the CMVN'd features.
+//
+// Kernels
+//   k_tc_fold : signal -> folded, scaled, split fp16 operands   (HBM bound, elementwise)
+//   k_tc_gemm : warp-specialised TMA -> tcgen05.mma -> TMEM -> |.|^2 epilogue
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstring>
+
+#include <algorithm>
+
+#include "nsf_device_utils.cuh"
+#include "nsf_stft_tc.cuh"
+
+namespace nsf {
+
+namespace {
+
+constexpr int BM = 128;      // frames per tile (UMMA M)
+constexpr int BN = 128;      // bins per tile   (UMMA N); Re and Im tiles sit side by side in TMEM
+constexpr int BK = 64;       // K per pipeline stage: 64 fp16 = one 128-byte swizzle row
+constexpr int UK = 16;       // K per tcgen05.mma for 16-bit inputs
+constexpr int kStages = 3;
+constexpr int kTileBytes = BM * BK * 2;             // 16 KiB, A and B tiles have the same size
+constexpr int kStageBytes = 4 * kTileBytes;         // A_hi, A_lo, B_hi, B_lo
+constexpr int kTmemCols = 2 * BN;                   // Re | Im accumulators, fp32
+constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256;
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int32_t x, int32_t y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, 16-bit inputs, fp32 accumulation
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows are 128 bytes, 8-row groups are 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);   // start address, 16-byte units
+  d |= static_cast<uint64_t>(1) << 16;                       // leading byte offset (unused for SW128 K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // stride byte offset: 8 rows * 128 B
+  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4)                                  // accumulator format: F32
+         | (0u << 7) | (0u << 10)                   // A, B format: F16
+         | (static_cast<uint32_t>(n >> 3) << 17)    // N / 8
+         | (static_cast<uint32_t>(m >> 4) << 24);   // M / 16
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tc_fold: one block per hop-frame (grid-stride).  Gathers the zero-padded frame, forms the
+// folded inputs (<= 4 signed, windowed taps each), picks the power-of-two scale that puts the
+// frame's largest folded value in [2^13, 2^14), and writes fp16 hi / lo planes.
+// Operand layout: plane = (chain*2 + part)*2 + hl ; element [plane][frame][k], k contiguous.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tc_fold(DeviceTables t, BatchView b, const float* __restrict__ y,
+                                                 __half* __restrict__ planes, int64_t plane_rows,
+                                                 int32_t* __restrict__ row_exp) {
+  extern __shared__ float s_fold[];   // [F] frame, then [chains*2*kp] folded values
+  __shared__ float s_red[8];
+  float* s_x = s_fold;
+  float* s_p = s_fold + t.F;
+  const int kp = t.kp[0];
+  const int n_out = t.chains * 2 * kp;
+  for (int64_t g = blockIdx.x; g < b.total_frames; g += gridDim.x) {
+    const int clip = find_segment(b.frame_off, b.n_clips, g);
+    const int64_t tf = g - __ldg(b.frame_off + clip);
+    const int64_t base = __ldg(b.clip_off + clip);
+    const int64_t len = __ldg(b.clip_off + clip + 1) - base;
+    const int64_t first = tf * t.H - t.pad;
+    for (int n = threadIdx.x; n < t.F; n += blockDim.x) {
+      const int64_t i = first + n;
+      s_x[n] = (i >= 0 && i < len) ? __ldg(y + base + i) : 0.0f;
+    }
+    __syncthreads();
+    float vmax = 0.0f;
+    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
+      const int cp = e / kp, j = e - cp * kp;       // cp = chain*2 + part
+      const int c = cp >> 1, part = cp & 1;
+      float acc = 0.0f;
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) {
+        const int o = (part * 4 + tap) * kp + j;
+        acc = fmaf(__ldg(t.tap_coef[c] + o), s_x[__ldg(t.tap_idx[c] + o)], acc);
+      }
+      s_p[e] = acc;
+      vmax = fmaxf(vmax, fabsf(acc));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = vmax;
+    __syncthreads();
+    vmax = s_red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) vmax = fmaxf(vmax, s_red[w]);
+    // scale = 2^e with vmax * 2^e in [2^13, 2^14): exact, and well inside fp16 range
+    int e2 = 0;
+    if (vmax > 0.0f && vmax < INFINITY) {
+      int ex;
+      frexpf(vmax, &ex);       // vmax = m * 2^ex, m in [0.5, 1)
+      e2 = 14 - ex;
+      e2 = max(-100, min(100, e2));
+    }
+    const float scale = ldexpf(1.0f, e2);
+    if (threadIdx.x == 0) row_exp[g] = e2;
+    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
+      const int cp = e / kp, j = e - cp * kp;
+      const float v = s_p[e] * scale;
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      planes[(static_cast<int64_t>(cp * 2 + 0) * plane_rows + g) * kp + j] = hi;
+      planes[(static_cast<int64_t>(cp * 2 + 1) * plane_rows + g) * kp + j] = lo;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tc_gemm: one CTA per (bin tile, chain, frame tile).
+//   warp 0    : TMA producer (one lane)   - A_hi, A_lo, B_hi, B_lo tiles per stage
+//   warp 1    : TMEM allocator + tcgen05.mma issuer (one lane)
+//   warps 2-5 : epilogue - tcgen05.ld Re/Im, |.|^2, undo scaling, store
+// Stage schedule: part 0 (real) over all K blocks into TMEM columns [0, BN), then part 1
+// (imaginary) into [BN, 2 BN).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          int64_t total_frames, int64_t plane_rows, int n_tiles, int n_chains, int kp, int np_ld, int np0,
+          int np1, int col_off1, int bins_ld, const int32_t* __restrict__ row_exp, float* __restrict__ power) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.x = (frame tile, chain, bin tile) with the bin tile fastest, so the CTAs that re-read
+  // one frame tile's operands are co-scheduled and hit in L2
+  const int n_tile = blockIdx.x % n_tiles;
+  const int chain = (blockIdx.x / n_tiles) % n_chains;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x / (n_tiles * n_chains)) * BM;
+  const int np = chain == 0 ? np0 : np1;
+  const int n0 = n_tile * BN;
+  if (n0 >= np) return;  // uniform per CTA: this chain has fewer bin tiles
+  const int kblocks = (kp + BK - 1) / BK;
+  const int iters = 2 * kblocks;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int i = 0; i < kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int stage = it % kStages;
+        const uint32_t phase = (it / kStages) & 1;
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        const int part = it / kblocks, kb = it - part * kblocks;
+        const int cp = chain * 2 + part;
+        uint8_t* st = tiles + stage * kStageBytes;
+        mbar_expect_tx(full_bar + stage, kStageBytes);
+        const int kx = kb * BK;
+        const int64_t a_row = static_cast<int64_t>(cp * 2) * plane_rows + g0;
+        tma_load_2d(st + 0 * kTileBytes, &map_a, full_bar + stage, kx, static_cast<int32_t>(a_row));
+        tma_load_2d(st + 1 * kTileBytes, &map_a, full_bar + stage, kx, static_cast<int32_t>(a_row + plane_rows));
+        const int b_row = (cp * 2) * np_ld + n0;
+        tma_load_2d(st + 2 * kTileBytes, &map_b, full_bar + stage, kx, b_row);
+        tma_load_2d(st + 3 * kTileBytes, &map_b, full_bar + stage, kx, b_row + np_ld);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int it = 0; it < iters; ++it) {
+        const int stage = it % kStages;
+        const uint32_t phase = (it / kStages) & 1;
+        mbar_wait(full_bar + stage, phase);
+        tcgen05_fence_after();
+        const int part = it / kblocks, kb = it - part * kblocks;
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(part * BN);
+        const uint32_t st = smem_u32(tiles + stage * kStageBytes);
+        const int ksteps = min(BK / UK, (kp - kb * BK + UK - 1) / UK);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint32_t koff = static_cast<uint32_t>(k * UK * 2);  // bytes along K inside the swizzle row
+          const uint64_t a_hi = make_smem_desc(st + 0 * kTileBytes + koff);
+          const uint64_t a_lo = make_smem_desc(st + 1 * kTileBytes + koff);
+          const uint64_t b_hi = make_smem_desc(st + 2 * kTileBytes + koff);
+          const uint64_t b_lo = make_smem_desc(st + 3 * kTileBytes + koff);
+          umma_f16(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+          umma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+        }
+        umma_commit(empty_bar + stage);          // smem slot reusable once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);                // accumulators complete
+    }
+  } else {
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int64_t g = g0 + quarter * 32 + lane;
+    const bool row_ok = g < total_frames;
+    const float sc = row_ok ? ldexpf(1.0f, -(__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+    const int col_base = (chain == 0 ? 0 : col_off1) + n0;
+    float* out_row = power + (row_ok ? g : 0) * bins_ld + col_base;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+    for (int j = 0; j < BN; j += 32) {
+      float re[32], im[32];
+      tmem_ld_32x32(lane_addr + static_cast<uint32_t>(j), re);
+      tmem_ld_32x32(lane_addr + static_cast<uint32_t>(BN + j), im);
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          if (n0 + j + q < np) {
+            float4 o;
+            float a, c;
+            a = re[q + 0] * sc; c = im[q + 0] * sc; o.x = fmaf(a, a, c * c);
+            a = re[q + 1] * sc; c = im[q + 1] * sc; o.y = fmaf(a, a, c * c);
+            a = re[q + 2] * sc; c = im[q + 2] * sc; o.z = fmaf(a, a, c * c);
+            a = re[q + 3] * sc; c = im[q + 3] * sc; o.w = fmaf(a, a, c * c);
+            *reinterpret_cast<float4*>(out_row + j + q) = o;
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D fp16 tensor [rows][cols] (cols contiguous), box = BK x box_rows, 128B swizzle, zero OOB fill
+bool encode_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int64_t plane_rows_for(int64_t frames) { return (frames + BM - 1) / BM * BM; }
+
+}  // namespace
+
+void build_stft_tc_blob(const Plan& p, StftTcHostBlob* blob) {
+  const int kp = p.chain[0].kp;
+  int np_ld = 0;
+  for (int c = 0; c < p.chains; ++c) np_ld = std::max(np_ld, p.chain[c].np);
+  blob->kp = kp;
+  blob->np_ld = np_ld;
+  blob->planes = p.chains * 4;
+  std::vector<__half> h(static_cast<size_t>(blob->planes) * np_ld * kp, __float2half(0.0f));
+  const double scale = std::ldexp(1.0, kTcBScaleExp);
+  for (int c = 0; c < p.chains; ++c) {
+    const FoldChain& ch = p.chain[c];
+    for (int part = 0; part < 2; ++part)
+      for (int n = 0; n < ch.nbins; ++n)
+        for (int k = 0; k < ch.k; ++k) {
+          const double v = ch.mat[part][static_cast<size_t>(k) * ch.np + n] * scale;
+          const __half hi = __float2half_rn(static_cast<float>(v));
+          const __half lo = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(hi))));
+          const size_t plane = static_cast<size_t>((c * 2 + part) * 2);
+          h[((plane + 0) * np_ld + n) * kp + k] = hi;
+          h[((plane + 1) * np_ld + n) * kp + k] = lo;
+        }
+  }
+  blob->bytes.resize(h.size() * sizeof(__half));
+  std::memcpy(blob->bytes.data(), h.data(), blob->bytes.size());
+}
+
+nsf_status bind_stft_tc_tables(const Plan& p, const StftTcHostBlob& blob, const void* dev_ptr,
+                               StftTcTables* out) {
+  out->bt = dev_ptr;
+  out->kp = blob.kp;
+  out->np_ld = blob.np_ld;
+  out->chains = p.chains;
+  out->np[0] = p.chain[0].np;
+  out->np[1] = p.chains > 1 ? p.chain[1].np : 0;
+  out->col_off[0] = 0;
+  out->col_off[1] = p.chain[0].np;
+  if (!encode_map(&out->map_b, dev_ptr, static_cast<uint64_t>(blob.planes) * blob.np_ld, blob.kp, BN)) {
+    set_error("cuTensorMapEncodeTiled failed for the DFT matrix");
+    return NSF_ERR_CUDA;
+  }
+  out->ready = true;
+  return NSF_OK;
+}
+
+size_t stft_tc_operand_bytes(const Plan& p, int64_t frames) {
+  const int64_t rows = plane_rows_for(frames);
+  const size_t planes = static_cast<size_t>(p.chains) * 4;
+  // fp16 planes, then one int32 exponent per frame; both 256-byte aligned
+  return (planes * rows * p.chain[0].kp * 2 + 255) / 256 * 256 + (static_cast<size_t>(rows) * 4 + 255) / 256 * 256;
+}
+
+namespace {
+struct OperandView { __half* planes; int32_t* row_exp; int64_t rows; };
+OperandView view_operands(const StftTcTables& tc, int64_t frames, void* operands) {
+  OperandView v;
+  v.rows = plane_rows_for(frames);
+  v.planes = static_cast<__half*>(operands);
+  const size_t plane_bytes = (static_cast<size_t>(tc.chains) * 4 * v.rows * tc.kp * 2 + 255) / 256 * 256;
+  v.row_exp = reinterpret_cast<int32_t*>(static_cast<char*>(operands) + plane_bytes);
+  return v;
+}
+}  // namespace
+
+int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTables& t, const BatchView& b,
+                        const float* y, void* operands) {
+  if (!tc.ready) return -1;
+  const OperandView v = view_operands(tc, b.total_frames, operands);
+  int64_t grid = b.total_frames < 148 * 8 ? b.total_frames : 148 * 8;
+  if (grid < 1) grid = 1;
+  const size_t smem = (static_cast<size_t>(t.F) + static_cast<size_t>(t.chains) * 2 * tc.kp) * sizeof(float);
+  k_tc_fold<<<static_cast<int>(grid), 256, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_stft_tc_gemm(cudaStream_t s, const StftTcTables& tc, const DeviceTables& t, const BatchView& b,
+                        void* operands, float* power) {
+  if (!tc.ready) return -1;
+  const OperandView v = view_operands(tc, b.total_frames, operands);
+  CUtensorMap map_a;
+  if (!encode_map(&map_a, v.planes, static_cast<uint64_t>(tc.chains) * 4 * v.rows, tc.kp, BM)) return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)) !=
+        cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  const int np_max = std::max(tc.np[0], tc.np[1]);
+  const int n_tiles = (np_max + BN - 1) / BN;
+  const int64_t grid = (v.rows / BM) * n_tiles * tc.chains;
+  if (grid <= 0 || grid > 0x7fffffffLL) return -1;
+  k_tc_gemm<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, s>>>(
+      map_a, tc.map_b, b.total_frames, v.rows, n_tiles, tc.chains, tc.kp, tc.np_ld, tc.np[0], tc.np[1],
+      tc.col_off[1], t.bins_ld, v.row_exp, power);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace nsf

@@ -1,0 +1,313 @@
+"""Host-side engine: plans, per-device contexts, pinned buffers and the two ways into the C ABI.
+
+* ``extract_host``   - NumPy in / NumPy out through ``nsf_extract_host`` (what the reference-facing
+  functions use; H2D, kernels and D2H are pipelined inside the library);
+* ``extract_device`` - torch CUDA tensors in / out through ``nsf_extract_batch`` (device-resident,
+  stream-ordered; torch is only the allocator and stream provider).
+
+Nothing here computes features on the CPU.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _native as nv
+
+DEFAULT_N_MFCC, DEFAULT_N_MELS, DEFAULT_N_LAGS = 23, 128, 187  # extract_features_utils.py:11,54
+
+
+def default_device():
+    return int(os.environ.get("NSF_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def frame_params(sr):
+    """(frame_length, hop_length) exactly as extract_features.py:12-13 computes them."""
+    f = nv.lib.nsf_frame_length(int(sr))
+    return f, nv.lib.nsf_hop_length(f)
+
+
+class PinnedBuffer:
+    """Page-locked host array (cudaHostAlloc through the C ABI) exposed as a NumPy array."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        nv.check(nv.lib.nsf_host_alloc(C.byref(p), int(max(nbytes, 1))))
+        self._ptr = p
+        self.nbytes = int(nbytes)
+        self._raw = (C.c_char * max(self.nbytes, 1)).from_address(p.value)
+
+    def view(self, dtype, shape):
+        count = int(np.prod(shape))
+        arr = np.frombuffer(self._raw, dtype=dtype, count=count)
+        return arr.reshape(shape)
+
+    def close(self):
+        if self._ptr is not None and self._ptr.value:
+            self._raw = None
+            nv.lib.nsf_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Plan:
+    """Constant tables for one (sr, F, H) geometry.  Pure host object: usable without a GPU."""
+
+    def __init__(self, sr, frame_length, hop_length, n_mfcc=DEFAULT_N_MFCC, n_mels=DEFAULT_N_MELS,
+                 n_lags=DEFAULT_N_LAGS):
+        h = C.c_void_p()
+        nv.check(nv.lib.nsf_plan_create(int(sr), int(frame_length), int(hop_length), int(n_mfcc),
+                                        int(n_mels), int(n_lags), C.byref(h)))
+        self.handle = h
+        self.sr, self.F, self.H = int(sr), int(frame_length), int(hop_length)
+        self.n_mfcc, self.n_mels, self.n_lags = int(n_mfcc), int(n_mels), int(n_lags)
+        b, c, k, kp = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        nv.lib.nsf_plan_info(h, C.byref(b), C.byref(c), C.byref(k), C.byref(kp))
+        self.bins, self.chains, self.fold_k, self.fold_kp = b.value, c.value, k.value, kp.value
+
+    def table(self, which):
+        n = nv.lib.nsf_plan_table(self.handle, which, None, 0)
+        out = np.empty(n, dtype=np.float32)
+        nv.lib.nsf_plan_table(self.handle, which, out.ctypes.data_as(C.POINTER(C.c_float)), n)
+        return out
+
+    def mel_basis(self):
+        return self.table(nv.TABLE_MEL).reshape(self.n_mels, self.bins)
+
+    def dct_matrix(self):
+        return self.table(nv.TABLE_DCT).reshape(self.n_mfcc, self.n_mels)
+
+    def fold_check(self, frame):
+        """DFT of one frame through the fold tables, float64 on the host (table verification)."""
+        frame = np.ascontiguousarray(frame, dtype=np.float32)
+        assert frame.shape == (self.F,)
+        re = np.empty(self.bins, dtype=np.float64)
+        im = np.empty(self.bins, dtype=np.float64)
+        nv.check(nv.lib.nsf_plan_fold_check(self.handle, frame.ctypes.data_as(C.POINTER(C.c_float)),
+                                            re.ctypes.data_as(C.POINTER(C.c_double)),
+                                            im.ctypes.data_as(C.POINTER(C.c_double))))
+        return re + 1j * im
+
+    def feature_cols(self, flags=0):
+        return nv.lib.nsf_feature_cols(self.handle, flags)
+
+    def hop_frames(self, n):
+        return nv.lib.nsf_hop_frames(int(n), self.F, self.H)
+
+    def feature_rows(self, n):
+        return nv.lib.nsf_feature_rows(int(n), self.F, self.H)
+
+    def guard_frames(self, n):
+        return nv.lib.nsf_guard_frames(int(n), self.F, self.H)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                nv.lib.nsf_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def pack_clips(clips, dtype=None):
+    """Concatenate 1-D clips into one packed array + int64 offsets."""
+    lens = [len(c) for c in clips]
+    offsets = np.zeros(len(clips) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    if dtype is None:
+        dtype = np.int16 if all(np.asarray(c).dtype == np.int16 for c in clips) else np.float32
+    packed = np.empty(int(offsets[-1]), dtype=dtype)
+    for c, o in zip(clips, offsets[:-1]):
+        packed[o:o + len(c)] = c
+    return packed, offsets
+
+
+class Engine:
+    """One CUDA context of the library on one device for one plan."""
+
+    def __init__(self, plan, device=None):
+        self.plan = plan
+        self.device = default_device() if device is None else int(device)
+        h = C.c_void_p()
+        nv.check(nv.lib.nsf_ctx_create(plan.handle, self.device, C.byref(h)))
+        self.handle = h
+        self._lock = threading.Lock()
+
+    # ---- geometry ------------------------------------------------------------------------
+    def row_offsets(self, offsets, flags=0):
+        lens = np.diff(np.asarray(offsets, dtype=np.int64))
+        if flags & nv.NO_REDUCE:
+            rows = [self.plan.hop_frames(n) for n in lens]
+        else:
+            rows = [self.plan.feature_rows(n) for n in lens]
+        out = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(rows, out=out[1:])
+        return out
+
+    @staticmethod
+    def _pcm_format(arr):
+        if arr.dtype == np.float32:
+            return nv.PCM_F32
+        if arr.dtype == np.int16:
+            return nv.PCM_I16
+        raise TypeError(f"PCM must be float32 or int16, got {arr.dtype}")
+
+    # ---- host buffers ----------------------------------------------------------------------
+    def extract_host(self, pcm, offsets, flags=0, out=None, want_y=False):
+        """pcm: packed 1-D float32/int16 host array; returns (rows x cols float32[, y float32])."""
+        pcm = np.ascontiguousarray(pcm)
+        fmt = self._pcm_format(pcm)
+        off, off_p = nv.i64_array(offsets)
+        n = len(off) - 1
+        cols = self.plan.feature_cols(flags)
+        rows = int(self.row_offsets(off, flags)[-1])
+        if out is None:
+            out = np.empty((rows, cols), dtype=np.float32)
+        assert out.dtype == np.float32 and out.shape == (rows, cols) and out.flags["C_CONTIGUOUS"]
+        y = np.empty(int(off[-1] - off[0]), dtype=np.float32) if want_y else None
+        with self._lock:
+            nv.check(nv.lib.nsf_extract_host(self.handle, nv.ptr(pcm), fmt, off_p, n, flags, nv.ptr(out),
+                                             cols, nv.ptr(y) if want_y else None))
+        return (out, y) if want_y else out
+
+    # ---- device buffers (torch used for memory and streams only) -------------------------------
+    def workspace_bytes(self, total_samples, n_clips, flags=0):
+        return nv.lib.nsf_workspace_bytes(self.plan.handle, int(total_samples), int(n_clips), flags)
+
+    def extract_device(self, pcm, offsets, flags=0, out=None, workspace=None, y_norm=None, stream=None):
+        """pcm: 1-D CUDA tensor (float32 or int16) on this engine's device.  Stream-ordered."""
+        import torch
+        assert pcm.is_cuda and pcm.device.index == self.device and pcm.is_contiguous()
+        fmt = {torch.float32: nv.PCM_F32, torch.int16: nv.PCM_I16}[pcm.dtype]
+        off, off_p = nv.i64_array(offsets)
+        n = len(off) - 1
+        cols = self.plan.feature_cols(flags)
+        rows = int(self.row_offsets(off, flags)[-1])
+        if out is None:
+            out = torch.empty((rows, cols), dtype=torch.float32, device=pcm.device)
+        assert out.dtype == torch.float32 and out.shape[0] == rows and out.stride(1) == 1
+        need = self.workspace_bytes(int(off[-1] - off[0]), n, flags)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=pcm.device)
+        s = torch.cuda.current_stream(pcm.device) if stream is None else stream
+        base = pcm.data_ptr() + int(off[0]) * pcm.element_size()
+        with self._lock:
+            nv.check(nv.lib.nsf_extract_batch(
+                self.handle, C.c_void_p(s.cuda_stream), C.c_void_p(base), fmt, off_p, n, flags,
+                C.c_void_p(out.data_ptr()), out.stride(0), None,
+                C.c_void_p(y_norm.data_ptr()) if y_norm is not None else None,
+                C.c_void_p(workspace.data_ptr()), workspace.numel()))
+        return out, workspace
+
+    # ---- collect_features augmentation -----------------------------------------------------
+    @staticmethod
+    def collect_flags(include_fast=True, include_slow=False, blend_boundaries=True):
+        return ((nv.COLLECT_FAST if include_fast else 0) | (nv.COLLECT_SLOW if include_slow else 0) |
+                (nv.COLLECT_BLEND if blend_boundaries else 0))
+
+    def collect_host(self, audio, audio_offsets, facial, facial_offsets, include_fast=True,
+                     include_slow=False, blend_boundaries=True, blend_frames=30):
+        """Packed row-major audio / facial rows (same float dtype) -> augmented (audio, facial, offsets)."""
+        audio = np.ascontiguousarray(audio)
+        facial = np.ascontiguousarray(facial, dtype=audio.dtype)
+        dtype = {np.dtype(np.float32): nv.F32, np.dtype(np.float64): nv.F64}[audio.dtype]
+        a_off, a_p = nv.i64_array(audio_offsets)
+        f_off, f_p = nv.i64_array(facial_offsets)
+        n = len(a_off) - 1
+        flags = self.collect_flags(include_fast, include_slow, blend_boundaries)
+        rows = [nv.lib.nsf_collect_rows(int(a_off[i + 1] - a_off[i]), int(f_off[i + 1] - f_off[i]), flags,
+                                        int(blend_frames)) for i in range(n)]
+        o_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(rows, out=o_off[1:])
+        out_a = np.empty((int(o_off[-1]), audio.shape[1]), dtype=audio.dtype)
+        out_f = np.empty((int(o_off[-1]), facial.shape[1]), dtype=audio.dtype)
+        with self._lock:
+            nv.check(nv.lib.nsf_collect_host(self.handle, dtype, nv.ptr(audio), audio.shape[1], a_p,
+                                             nv.ptr(facial), facial.shape[1], f_p, n, flags,
+                                             int(blend_frames), nv.ptr(out_a), nv.ptr(out_f)))
+        return out_a, out_f, o_off
+
+    def rows_op(self, op, a, b=None, blend_frames=0):
+        a = np.ascontiguousarray(a)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        dtype = nv.F64 if a.dtype == np.float64 else nv.F32
+        na, cols = a.shape
+        nb = 0
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=a.dtype)
+            nb = b.shape[0]
+            assert b.shape[1] == cols
+        if op == nv.ROWS_INTERP_SLOWER:
+            rows = 2 * na - 1
+        elif op == nv.ROWS_SMOOTH:
+            rows = na
+        else:
+            rows = na + nb - max(0, min(int(blend_frames), na, nb))
+        out = np.empty((rows, cols), dtype=a.dtype)
+        with self._lock:
+            nv.check(nv.lib.nsf_rows_host(self.handle, op, dtype, nv.ptr(a), na, nv.ptr(b) if b is not None
+                                          else None, nb, cols, int(blend_frames), nv.ptr(out)))
+        return out
+
+    def post(self, frame_major, post_flags):
+        x = np.ascontiguousarray(frame_major, dtype=np.float32)
+        t, c = x.shape
+        rows = (t + 1) // 2 if post_flags & 0x8 else t
+        out = np.empty((rows, c * (3 if post_flags & 0x4 else 1)), dtype=np.float32)
+        with self._lock:
+            nv.check(nv.lib.nsf_post_host(self.handle, x.ctypes.data_as(C.POINTER(C.c_float)), t, c,
+                                          post_flags, nv.ptr(out)))
+        return out
+
+    # ---- instrumentation ---------------------------------------------------------------------
+    def launch_count(self):
+        return nv.lib.nsf_launch_count(self.handle)
+
+    def set_profiling(self, on):
+        nv.lib.nsf_set_profiling(self.handle, 1 if on else 0)
+
+    def stage_times_ms(self):
+        buf = (C.c_float * 8)()
+        n = nv.lib.nsf_stage_times_ms(self.handle, buf, 8)
+        return {nv.STAGE_NAMES[i]: float(buf[i]) for i in range(n)}
+
+    def close(self):
+        if self.handle:
+            nv.lib.nsf_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_plans = {}
+_engines = {}
+_cache_lock = threading.Lock()
+
+
+def get_plan(sr, frame_length, hop_length, n_mfcc=DEFAULT_N_MFCC, n_lags=DEFAULT_N_LAGS):
+    key = (int(sr), int(frame_length), int(hop_length), int(n_mfcc), DEFAULT_N_MELS, int(n_lags))
+    with _cache_lock:
+        if key not in _plans:
+            _plans[key] = Plan(*key)
+        return _plans[key]
+
+
+def get_engine(sr, frame_length, hop_length, device=None, n_mfcc=DEFAULT_N_MFCC, n_lags=DEFAULT_N_LAGS):
+    device = default_device() if device is None else int(device)
+    key = (int(sr), int(frame_length), int(hop_length), int(n_mfcc), int(n_lags), device)
+    plan = get_plan(sr, frame_length, hop_length, n_mfcc, n_lags)
+    with _cache_lock:
+        if key not in _engines:
+            _engines[key] = Engine(plan, device)
+        return _engines[key]
