@@ -36,7 +36,7 @@ extern "C" {
 typedef enum nsf_status {
   NSF_OK = 0,
   NSF_ERR_BAD_ARG = 1,    /* null pointer, negative size, inconsistent offsets ...            */
-  NSF_ERR_TOO_SHORT = 2,  /* a clip fails the 9-frame guard of extract_features.py:16-20      */
+  NSF_ERR_TOO_SHORT = 2,  /* a clip has fewer hop-frames than delta(width=9) / the edge fix need */
   NSF_ERR_CUDA = 3,       /* a CUDA runtime/driver call failed (see nsf_last_error)            */
   NSF_ERR_WORKSPACE = 4,  /* caller workspace smaller than nsf_workspace_bytes()               */
   NSF_ERR_NO_DEVICE = 5,  /* no CUDA device / not an sm_100 part                               */
@@ -132,8 +132,10 @@ NSF_API void nsf_host_free(void* ptr);
  * rows [row_offsets[i], row_offsets[i+1]) of `out`, row_offsets being the prefix sum of
  * nsf_feature_rows() (or nsf_hop_frames() under NSF_NO_REDUCE); pass out_row_offsets = NULL to get
  * exactly that packing.  `out` is row-major float32 with `out_ld` floats between rows
- * (>= nsf_feature_cols()).  Every clip must pass the 9-frame guard, else NSF_ERR_TOO_SHORT and
- * nothing is launched. */
+ * (>= nsf_feature_cols()).  Every clip must have >= 9 hop-frames when deltas are computed (what
+ * librosa.feature.delta requires; 2 otherwise) and more than F/2 samples (reflect padding), else
+ * NSF_ERR_TOO_SHORT and nothing is launched.  The reference's 9-frame guard on UN-padded frames
+ * (extract_features.py:16-20) is the caller's policy: test it with nsf_guard_frames(). */
 NSF_API int64_t nsf_workspace_bytes(const nsf_plan* plan, int64_t total_samples, int32_t n_clips,
                             uint32_t flags);
 
@@ -149,6 +151,13 @@ NSF_API nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void
 NSF_API nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
                             const int64_t* clip_offsets_host, int32_t n_clips, uint32_t flags,
                             float* out_host, int64_t out_ld, float* y_norm_host /* optional */);
+
+/* Peak normalisation alone, HOST buffers: y = decode(pcm) / max|decode(pcm)| per clip when the peak
+ * is > 0 (utils/audio/load_audio.py:12-14, applied by all four loaders).  y_host is float32 with the
+ * packing of clip_offsets_host (rebased to 0).  peaks_host (optional) receives max|y| per clip. */
+NSF_API nsf_status nsf_normalize_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
+                              const int64_t* clip_offsets_host, int32_t n_clips, float* y_host,
+                              float* peaks_host /* optional */);
 
 /* ---- collect_features augmentation ----------------------------------------------------------
  * Replaces the arithmetic of collect_features (data_processing.py:126-177): centre-trim to equal

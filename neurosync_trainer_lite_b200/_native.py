@@ -72,6 +72,7 @@ _SIGS = {
     "nsf_extract_batch": (_i32, [_vp, _vp, _vp, _i32, _i64p, _i32, _u32, _vp, _i64, _i64p, _vp, _vp,
                                  _i64]),
     "nsf_extract_host": (_i32, [_vp, _vp, _i32, _i64p, _i32, _u32, _vp, _i64, _vp]),
+    "nsf_normalize_host": (_i32, [_vp, _vp, _i32, _i64p, _i32, _vp, _vp]),
     "nsf_collect_batch": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64p, _vp, _i32, _i64p, _i32, _u32, _i32,
                                  _vp, _vp, _i64p]),
     "nsf_collect_host": (_i32, [_vp, _i32, _vp, _i32, _i64p, _vp, _i32, _i64p, _i32, _u32, _i32, _vp,

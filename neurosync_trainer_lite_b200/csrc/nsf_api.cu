@@ -262,14 +262,20 @@ nsf_status build_desc(const Plan& p, const int64_t* clip_offsets, int32_t n_clip
   for (int i = 0; i < n_clips; ++i) {
     const int64_t len = clip_offsets[i + 1] - clip_offsets[i];
     if (len < 0) { set_error("clip_offsets must be non-decreasing"); return NSF_ERR_BAD_ARG; }
-    if (nsf_guard_frames(len, p.F, p.H) < kMinGuardFrames) {
+    const int64_t T = nsf_hop_frames(len, p.F, p.H);
+    // librosa.feature.delta(width=9) raises below 9 frames; the edge fix and reflect padding need
+    // 2 frames and F/2 + 1 samples.  (The 9-frame *guard* of extract_features.py:16 counts
+    // un-padded frames and belongs to the caller: see nsf_guard_frames.)
+    const bool any_delta = (!(flags & NSF_NO_DELTAS) && !(flags & NSF_NO_MFCC)) ||
+                           ((flags & NSF_AC_DELTAS) && !(flags & NSF_NO_AUTOCORR));
+    const int64_t need = any_delta ? kMinGuardFrames : 2;
+    if (T < need || len <= p.F / 2) {
       char buf[160];
-      std::snprintf(buf, sizeof buf, "clip %d is too short: %lld frames, required: %d frames", i,
-                    static_cast<long long>(nsf_guard_frames(len, p.F, p.H)), kMinGuardFrames);
+      std::snprintf(buf, sizeof buf, "clip %d is too short: %lld hop-frames, required: %lld", i,
+                    static_cast<long long>(T), static_cast<long long>(need));
       set_error(buf);
       return NSF_ERR_TOO_SHORT;
     }
-    const int64_t T = nsf_hop_frames(len, p.F, p.H);
     const int64_t R = (flags & NSF_NO_REDUCE) ? T : (T + 1) / 2;
     d->clip_off[i] = clip_offsets[i] - origin;
     d->frame_off[i + 1] = d->frame_off[i] + T;
@@ -609,6 +615,55 @@ nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_form
   }
   for (auto& sl : ctx->slot)
     if (sl.stream) NSF_CUDA(cudaStreamSynchronize(sl.stream));
+  return NSF_OK;
+}
+
+nsf_status nsf_normalize_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
+                              const int64_t* clip_offsets, int32_t n_clips, float* y_host, float* peaks_host) {
+  if (!ctx || !pcm_host || !clip_offsets || !y_host || n_clips <= 0) {
+    set_error("nsf_normalize_host: NULL argument"); return NSF_ERR_BAD_ARG;
+  }
+  if (pcm_format != NSF_PCM_F32 && pcm_format != NSF_PCM_I16) { set_error("unknown pcm_format"); return NSF_ERR_BAD_ARG; }
+  for (int i = 0; i < n_clips; ++i)
+    if (clip_offsets[i + 1] < clip_offsets[i]) { set_error("clip_offsets must be non-decreasing"); return NSF_ERR_BAD_ARG; }
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  Slot* sl = &ctx->slot[0];
+  nsf_status st = ensure_slot(sl);
+  if (st != NSF_OK) return st;
+  NSF_CUDA(cudaStreamSynchronize(sl->stream));
+  const size_t esz = pcm_format == NSF_PCM_I16 ? 2 : 4;
+  const int64_t samples = clip_offsets[n_clips] - clip_offsets[0];
+  if (samples == 0) return NSF_OK;
+  const size_t n1 = static_cast<size_t>(n_clips) + 1;
+  // work arena: [clip_off n1 x int64][peak n x u32]
+  const size_t off_b = align_up(n1 * sizeof(int64_t));
+  if ((st = sl->pcm.reserve(samples * esz)) != NSF_OK) return st;
+  if ((st = sl->ynorm.reserve(samples * sizeof(float))) != NSF_OK) return st;
+  if ((st = sl->work.reserve(off_b + align_up(n_clips * sizeof(uint32_t)))) != NSF_OK) return st;
+  if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
+  if ((st = ctx->desc_host.reserve(n1 * sizeof(int64_t))) != NSF_OK) return st;
+  int64_t* h = static_cast<int64_t*>(ctx->desc_host.ptr);
+  for (size_t i = 0; i < n1; ++i) h[i] = clip_offsets[i] - clip_offsets[0];
+  int64_t* d_off = static_cast<int64_t*>(sl->work.ptr);
+  uint32_t* d_peak = reinterpret_cast<uint32_t*>(static_cast<char*>(sl->work.ptr) + off_b);
+  NSF_CUDA(cudaMemcpyAsync(d_off, h, n1 * sizeof(int64_t), cudaMemcpyHostToDevice, sl->stream));
+  NSF_CUDA(cudaEventRecord(ctx->desc_copied, sl->stream));
+  ctx->desc_pending = true;
+  NSF_CUDA(cudaMemsetAsync(d_peak, 0, n_clips * sizeof(uint32_t), sl->stream));
+  const char* src = static_cast<const char*>(pcm_host) + clip_offsets[0] * esz;
+  NSF_CUDA(cudaMemcpyAsync(sl->pcm.ptr, src, samples * esz, cudaMemcpyHostToDevice, sl->stream));
+  BatchView b{};
+  b.clip_off = d_off; b.frame_off = d_off; b.row_off = d_off;
+  b.n_clips = n_clips; b.total_samples = samples;
+  int n = launch_absmax(sl->stream, sl->pcm.ptr, pcm_format, b, d_peak);
+  if (n < 0) { set_error(cuda_msg("launch_absmax", cudaGetLastError())); return NSF_ERR_CUDA; }
+  int m = launch_normalize(sl->stream, sl->pcm.ptr, pcm_format, b, d_peak, true, static_cast<float*>(sl->ynorm.ptr));
+  if (m < 0) { set_error(cuda_msg("launch_normalize", cudaGetLastError())); return NSF_ERR_CUDA; }
+  ctx->launches += n + m;
+  NSF_CUDA(cudaMemcpyAsync(y_host, sl->ynorm.ptr, samples * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+  if (peaks_host)  // float bits of a non-negative float: copy as-is
+    NSF_CUDA(cudaMemcpyAsync(peaks_host, d_peak, n_clips * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl->stream));
+  NSF_CUDA(cudaStreamSynchronize(sl->stream));
   return NSF_OK;
 }
 

@@ -176,6 +176,21 @@ class Engine:
                                              cols, nv.ptr(y) if want_y else None))
         return (out, y) if want_y else out
 
+    def normalize_host(self, pcm, offsets=None):
+        """Peak-normalise packed clips on the device (load_audio.py:12-14) -> float32 host array."""
+        pcm = np.ascontiguousarray(pcm)
+        fmt = self._pcm_format(pcm)
+        if offsets is None:
+            offsets = [0, len(pcm)]
+        off, off_p = nv.i64_array(offsets)
+        y = np.empty(int(off[-1] - off[0]), dtype=np.float32)
+        if y.size == 0:
+            return y
+        with self._lock:
+            nv.check(nv.lib.nsf_normalize_host(self.handle, nv.ptr(pcm), fmt, off_p, len(off) - 1,
+                                               nv.ptr(y), None))
+        return y
+
     # ---- device buffers (torch used for memory and streams only) -------------------------------
     def workspace_bytes(self, total_samples, n_clips, flags=0):
         return nv.lib.nsf_workspace_bytes(self.plan.handle, int(total_samples), int(n_clips), flags)
