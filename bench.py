@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the audio feature front-end (BASELINE.json metric: audio-seconds per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2|c5]
+
+A *step* is one pass of the hot path over one batch of synthetic input: workload ``c2`` (default,
+BASELINE configs[1]) = a 30-minute single-actor dataset, 60 clips x 30 s @ 88.2 kHz, features only
+(``extract_and_combine_features`` semantics, 1800 audio-seconds, (108060, 256) float32 rows out).
+At N > 1 (torchrun, one rank per GPU) every rank extracts its own 60-clip shard - the path shards by
+clip with no collective - so scaling is *weak* and ``value`` is N x 1800 x K / max-over-ranks time.
+
+One JSON line on rank 0:
+* ``value``   device-resident throughput (PCM already in HBM), CUDA events on the launch stream;
+* ``e2e``     the same metric through ``nsf_extract_host`` (C ABI, HOST buffers: pinned float32 PCM in,
+              pinned float32 rows out, H2D and D2H inside the timed region);
+* ``roofline``/``kernels``  per-kernel achieved vs MEASURED_PEAKS.json (live CUDA-event stage times);
+* ``cpu_baseline``  the CPU oracle ("port" of the reference path; real librosa is not installable) on
+              the box's host cores, bounded sample;
+* ``clocks``  nvidia-smi samples taken during the timed region.
+
+``--impl reference`` times the CPU oracle alone (all host cores, bounded sample per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, F, H = 88200, 1470, 735
+WORKLOADS = {
+    # name: (sr, F, H, clips per rank, seconds per clip, description)
+    "c2": (88200, 1470, 735, 60, 30.0,
+           "C2: 30-min single-actor dataset, 60 clips x 30 s @ 88.2 kHz, features only"),
+    "c5": (16000, 266, 133, 10000, 2.0, "C5: 10000 clips x 2 s @ 16 kHz, batched small clips"),
+}
+# algorithmic work per hop-frame; bytes are float32 in / float32 out
+N_MELS, N_MFCC, N_LAGS = 128, 23, 187
+
+
+def algorithmic(sr, Fr, Hr, kp, bins_ld):
+    bins = Fr // 2 + 1
+    ac_flop = 2 * sum(Fr - l for l in range(N_LAGS + 1))
+    return {
+        # stage: (bound, units per hop-frame, unit)
+        "fold": ("hbm", Hr * 4 + 8 * kp * 2, "B"),                     # signal hop in, fp16 hi/lo planes out
+        "stft_gemm": ("tensor", 2 * Fr * 2 * bins, "FLOP"),            # DFT-as-GEMM, one pass
+        "mel_db": ("hbm", bins_ld * 4 + N_MELS * 4, "B"),              # power in, dB out
+        "dct_stats": ("hbm", N_MELS * 4 + 2 * N_MFCC * 4 + N_MFCC * 4, "B"),
+        "cmvn_delta_reduce": ("hbm", N_MFCC * 4 + 3 * N_MFCC * 4 / 2, "B"),
+        "autocorr": ("fma", ac_flop, "FLOP"),                          # fp32 CUDA-core FMAs
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm": d["hbm_gbs"], "tensor": d["bf16_tflops_sustained"], "tensor_burst": d["bf16_tflops"],
+                "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "measured"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "tensor_burst": 1590.0, "sm_max_mhz": 1965.0,
+            "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU oracle timing ----------------------------------------------------------------------------
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
+    seed, seconds, sr, Fr, Hr = args
+    from neurosync_trainer_lite_b200 import synth
+    from oracle import feature_oracle as fo
+    y = synth.synth_clip(seconds, sr, seed=seed, kind="voiced")
+    t0 = time.perf_counter()
+    out = fo.extract_and_combine_features(y, sr, Fr, Hr)
+    return time.perf_counter() - t0, out.shape[0]
+
+
+class CpuOracle:
+    """The CPU oracle on ``procs`` worker processes (one clip per task); pool reused across steps."""
+
+    def __init__(self, workload, procs=None):
+        import multiprocessing as mp
+        self.sr, self.F, self.H, _, self.seconds, _ = WORKLOADS[workload]
+        self.cores = procs or os.cpu_count() or 1
+        # one 30 s clip costs ~1.5 s of one core, one 2 s @ 16 kHz clip ~16 ms: bound the sample
+        self.clips = self.cores * (2 if workload == "c2" else 100)
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool.map(_cpu_worker, self._jobs(self.cores, 0))          # warm: imports, tables
+
+    def _jobs(self, n, salt):
+        return [(1000 + salt + i, self.seconds, self.sr, self.F, self.H) for i in range(n)]
+
+    def step(self, salt=0):
+        """-> (audio-s/s with every worker busy, wall seconds, summed per-clip compute seconds)"""
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, self._jobs(self.clips, salt), chunksize=1)
+        wall = time.perf_counter() - t0
+        busy = sum(r[0] for r in res)
+        # all workers running the reference loop back to back: excludes the synthetic-signal
+        # generation and pool hand-off that the wall clock of this harness also contains
+        return self.cores * self.clips * self.seconds / busy, wall, busy
+
+    def sample(self):
+        return (f"{self.clips} clips x {self.seconds:g} s per step ({self.clips * self.seconds:g} audio-s), "
+                f"{self.cores} worker processes")
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args, rank, world):
+    """CPU oracle on all host cores; rank 0 only."""
+    if rank != 0:
+        return
+    cpu = CpuOracle(args.workload)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu.step()
+    vals, t0 = [], time.perf_counter()
+    for i in range(args.steps):
+        vals.append(cpu.step(salt=i)[0])
+    total = time.perf_counter() - t0
+    cpu.close()
+    value = float(np.mean(vals))
+    sample = cpu.sample()
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][5], "sample": sample,
+                   "note": "CPU oracle = NumPy restatement of the reference path pinned bit-exact to the "
+                           "reference files (librosa itself is not installable here)"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cpu.cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- native arm -------------------------------------------------------------------------------------
+def make_inputs(workload, rank):
+    from neurosync_trainer_lite_b200 import engine, synth
+    sr, Fr, Hr, n_clips, seconds, _ = WORKLOADS[workload]
+    n_base = 6 if workload == "c2" else 50           # distinct signals; the rest are rotations of them
+    kinds = ("voiced", "voiced", "noise", "voiced", "gated", "voiced")
+    base = [synth.synth_clip(seconds, sr, seed=100 * rank + s, kind=kinds[s % 6]) for s in range(n_base)]
+    clips = []
+    for i in range(n_clips):
+        b = base[i % n_base]
+        clips.append(b if i < n_base else np.roll(b, 997 * (i // n_base)))
+    packed, off = engine.pack_clips(clips, dtype=np.float32)
+    return packed, off, base
+
+
+def run_native(args, rank, world, local_rank):
+    import torch
+    import __graft_entry__ as g
+    g.build_library()
+    from neurosync_trainer_lite_b200 import _native as nv
+    from neurosync_trainer_lite_b200 import engine
+    if nv.lib.nsf_device_count() < 1:
+        raise RuntimeError("bench.py needs an sm_100 GPU: the library has no CPU path")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sr, Fr, Hr, n_clips, seconds, desc = WORKLOADS[args.workload]
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    eng = engine.get_engine(sr, Fr, Hr, device=local_rank)
+    packed, off, base = make_inputs(args.workload, rank)
+    audio_s = n_clips * seconds
+    rows = int(eng.row_offsets(off)[-1])
+    frames = sum(eng.plan.hop_frames(int(n)) for n in np.diff(off))
+
+    # ---- device-resident: PCM already in HBM -----------------------------------------------------
+    pcm = torch.from_numpy(packed).to(dev)
+    out = torch.empty((rows, 256), dtype=torch.float32, device=dev)
+    ws = torch.empty(eng.workspace_bytes(len(packed), n_clips), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(max(args.warmup, 3)):
+        eng.extract_device(pcm, off, 0, out=out, workspace=ws)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        eng.extract_device(pcm, off, 0, out=out, workspace=ws)
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launch_count() - launches0
+
+    # per-kernel stage times (CUDA events recorded by the library on the same stream)
+    eng.set_profiling(True)
+    acc = {}
+    reps = max(3, min(args.steps, 10))
+    for _ in range(reps):
+        eng.extract_device(pcm, off, 0, out=out, workspace=ws)
+        torch.cuda.synchronize(dev)
+        for k, v in eng.stage_times_ms().items():
+            acc[k] = acc.get(k, 0.0) + v / reps
+    eng.set_profiling(False)
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------------
+    pin_in = engine.PinnedBuffer(packed.nbytes)
+    pin_out = engine.PinnedBuffer(rows * 256 * 4)
+    h_in = pin_in.view(np.float32, packed.shape)
+    h_in[:] = packed
+    h_out = pin_out.view(np.float32, (rows, 256))
+    for _ in range(max(args.warmup, 3)):
+        eng.extract_host(h_in, off, 0, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.extract_host(h_in, off, 0, out=h_out)     # synchronous: returns when rows are on the host
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    checksum = float(np.abs(h_out[::997]).sum())
+    clocks = sampler.stop() if sampler else None
+
+    # parity spot check against the oracle (outside every timed region)
+    parity = None
+    if rank == 0:
+        from oracle import feature_oracle as fo
+        want = fo.extract_and_combine_features(base[0], sr, Fr, Hr)
+        got = h_out[: want.shape[0]]
+        d = np.abs(got - want)
+        parity = {"clip": 0, "mfcc_max_abs": float(d[:, :69].max()), "autocorr_max_abs": float(d[:, 69:].max())}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    total_audio = audio_s * world
+    ms_per_step = dev_ms / args.steps
+    value = total_audio / (ms_per_step * 1e-3)
+    alg = algorithmic(sr, Fr, Hr, eng.plan.fold_kp, 2 * eng.plan.fold_kp if eng.plan.chains == 2 else eng.plan.fold_kp)
+    fma_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12     # fp32 FMA TFLOP/s at max clock
+    kernels = []
+    for name, (bound, units, unit) in alg.items():
+        ms = acc.get(name, 0.0)
+        if ms <= 0:
+            continue
+        per_s = units * frames / (ms * 1e-3)
+        if bound == "hbm":
+            ach, peak, u = per_s / 1e9, pk["hbm"], "GB/s"
+        elif bound == "tensor":
+            ach, peak, u = per_s / 1e12, pk["tensor"], "TFLOP/s"
+        else:
+            ach, peak, u = per_s / 1e12, fma_peak, "TFLOP/s"
+        kernels.append({"kernel": name, "ms": round(ms, 4), "bound": bound, "achieved": round(ach, 2),
+                        "peak": round(peak, 1), "unit": u, "frac": round(ach / peak, 4)})
+    kernels.sort(key=lambda k: -k["ms"])
+    top = kernels[0]
+    roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+                "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                "peak_source": pk["source"] + (" (fp32 FMA: 148 SM x 128 lanes x 2 x max SM clock)"
+                                               if top["bound"] == "fma" else " (sustained)"),
+                "ms_per_launch": top["ms"], "stage_ms_sum": round(sum(k["ms"] for k in kernels), 4)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        c = CpuOracle(args.workload)
+        v, wall, cpu_s = c.step()
+        c.close()
+        cpu = {"value": v, "unit": "audio-s/s", "cores": c.cores, "kind": "port",
+               "sample": c.sample() + f", wall {wall:.2f} s",
+               "single_process_value": c.clips * c.seconds / cpu_s}
+
+    line = {
+        "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": desc, "clips_per_gpu": n_clips, "audio_seconds_per_gpu_step": audio_s,
+                   "rows_per_gpu_step": rows, "hop_frames_per_gpu_step": frames, "pcm": "float32",
+                   "sharding": f"by clip, {world} rank(s), no collective",
+                   "l2": f"inputs {packed.nbytes / 1e6:.0f} MB + intermediates exceed the 126 MB L2 every step"},
+        "e2e": {"value": total_audio * args.steps / e2e_s, "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(packed.nbytes), "d2h_bytes_per_step": int(rows * 256 * 4),
+                "ms_per_step": e2e_s / args.steps * 1e3, "api": "nsf_extract_host (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+        "parity": parity, "checksum": checksum,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
