@@ -177,6 +177,7 @@ nsf_status upload_tables(nsf_ctx* ctx) {
     }
   }
   const size_t off_hann = put(p.hann_sym.data(), p.hann_sym.size() * sizeof(float));
+  const size_t off_hann_per = put(p.hann_per.data(), p.hann_per.size() * sizeof(float));
   // sparse mel runs in the chain-major power layout: natural bin k lives at column
   // col_off[chain(k)] + index-within-chain(k); a filter's contiguous bin range becomes one run of
   // consecutive columns per chain
@@ -233,6 +234,7 @@ nsf_status upload_tables(nsf_ctx* ctx) {
     t.mat32[c][1] = reinterpret_cast<const float*>(base + off_mat[c][1]);
   }
   t.hann_sym = reinterpret_cast<const float*>(base + off_hann);
+  t.hann_per = reinterpret_cast<const float*>(base + off_hann_per);
   t.mel_start = reinterpret_cast<const int32_t*>(base + off_ms);
   t.mel_len = reinterpret_cast<const int32_t*>(base + off_ml);
   t.mel_ptr = reinterpret_cast<const int32_t*>(base + off_mp);

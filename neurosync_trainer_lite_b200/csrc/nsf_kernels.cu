@@ -194,42 +194,99 @@ __global__ void __launch_bounds__(256) k_dft_simt(DeviceTables t, BatchView b,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1c: sparse mel projection + dB + per-clip dB max.  One warp per frame; lane handles mels
-// lane, lane+32, ... ; the power row is staged in shared memory.
+// K1c: sparse mel projection + dB + per-clip dB max.  A block owns 32 consecutive hop-frames: the
+// power tile is transposed into shared memory ([column][frame], pitch 33) so that LANES ARE FRAMES:
+// every shared load is conflict-free and every filter weight is a warp-uniform (broadcast) load.
+// Warp w accumulates mels [16 w, 16 w + 16); each filter is one contiguous column run per fold chain.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMelWarps = 8;
+constexpr int kMelFrames = 32;
+constexpr int kMelPitch = kMelFrames + 1;
+constexpr int kMelPerWarp = 16;                    // n_mels <= 128
 __global__ void __launch_bounds__(kMelWarps * 32) k_mel_db(DeviceTables t, BatchView b,
                                                            const float* __restrict__ power,
                                                            float* __restrict__ db,
-                                                           uint32_t* __restrict__ dbmax_key) {
-  extern __shared__ float s_pow[];  // [kMelWarps][bins_ld]
+                                                           uint32_t* __restrict__ dbmax_key, int chain_cols) {
+  extern __shared__ float s_mel[];                 // [chain_cols][33] power^T of one chain, then [32][n_mels + 1] dB
+  __shared__ uint32_t s_max[kMelFrames];
+  float* s_pow = s_mel;
+  float* s_out = s_mel + static_cast<size_t>(chain_cols) * kMelPitch;
+  const int out_pitch = t.n_mels + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* row = s_pow + warp * t.bins_ld;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * kMelWarps;
-  for (int64_t g = static_cast<int64_t>(blockIdx.x) * kMelWarps + warp; g < b.total_frames;
-       g += stride) {
-    const float4* src = reinterpret_cast<const float4*>(power + g * t.bins_ld);
-    for (int i = lane; i < t.bins_ld / 4; i += 32) reinterpret_cast<float4*>(row)[i] = __ldg(src + i);
-    __syncwarp();
-    float vmax = -INFINITY;
-    for (int m = lane; m < t.n_mels; m += 32) {
-      float acc = 0.0f;
-      for (int c = 0; c < t.chains; ++c) {   // the filter's bins, split into per-chain column runs
-        const int e = c * t.n_mels + m;
-        const int st = __ldg(t.mel_start + e), ln = __ldg(t.mel_len + e);
-        const float* w = t.mel_w + __ldg(t.mel_ptr + e);
-        for (int i = 0; i < ln; ++i) acc = fmaf(__ldg(w + i), row[st + i], acc);
+  const int64_t n_tiles = (b.total_frames + kMelFrames - 1) / kMelFrames;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t g0 = tile * kMelFrames;
+    const int nf = static_cast<int>(min(static_cast<int64_t>(kMelFrames), b.total_frames - g0));
+    if (threadIdx.x < kMelFrames) s_max[threadIdx.x] = 0u;
+    float acc[kMelPerWarp];
+#pragma unroll
+    for (int q = 0; q < kMelPerWarp; ++q) acc[q] = 0.0f;
+    for (int c = 0; c < t.chains; ++c) {
+      const int c0 = t.col_off[c], nc = t.np[c];
+      __syncthreads();                              // previous chain / tile fully consumed
+      for (int f = warp; f < kMelFrames; f += kMelWarps) {
+        const float* src = power + (g0 + f) * t.bins_ld + c0;
+        if (f < nf) {
+          // 12 independent 128-byte requests per warp in flight, then the transposing stores
+          for (int k0 = lane; k0 < nc; k0 += 32 * 12) {
+            float v[12];
+#pragma unroll
+            for (int q = 0; q < 12; ++q) v[q] = (k0 + 32 * q < nc) ? __ldg(src + k0 + 32 * q) : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+              if (k0 + 32 * q < nc) s_pow[(k0 + 32 * q) * kMelPitch + f] = v[q];
+          }
+        } else {
+          for (int k = lane; k < nc; k += 32) s_pow[k * kMelPitch + f] = 0.0f;
+        }
       }
-      const float v = 10.0f * log10f(fmaxf(1e-10f, acc));
-      db[g * t.n_mels + m] = v;
-      vmax = fmaxf(vmax, v);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < kMelPerWarp; ++q) {
+        const int m = q * kMelWarps + warp;     // interleaved: long (high) filters spread over warps
+        if (m < t.n_mels) {
+          const int e = c * t.n_mels + m;
+          const int ln = __ldg(t.mel_len + e);
+          const float* w = t.mel_w + __ldg(t.mel_ptr + e);
+          const float* col = s_pow + static_cast<size_t>(__ldg(t.mel_start + e) - c0) * kMelPitch + lane;
+          float a = acc[q];
+#pragma unroll 4
+          for (int i = 0; i < ln; ++i) a = fmaf(__ldg(w + i), col[i * kMelPitch], a);
+          acc[q] = a;
+        }
+      }
     }
-    vmax = warp_max(vmax);
-    if (lane == 0) {
-      const int clip = find_segment(b.frame_off, b.n_clips, g);
-      atomicMax(dbmax_key + clip, float_key(vmax));
+    float vmax = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < kMelPerWarp; ++q) {
+      const int m = q * kMelWarps + warp;
+      if (m < t.n_mels) {
+        const float v = 10.0f * log10f(fmaxf(1e-10f, acc[q]));
+        s_out[lane * out_pitch + m] = v;
+        vmax = fmaxf(vmax, v);
+      }
     }
-    __syncwarp();
+    if (lane < nf && warp < t.n_mels) atomicMax(&s_max[lane], float_key(vmax));
+    __syncthreads();
+    // coalesced dB rows out
+    for (int f = warp; f < nf; f += kMelWarps)
+      for (int m = lane; m < t.n_mels; m += 32) db[(g0 + f) * t.n_mels + m] = s_out[f * out_pitch + m];
+    if (warp == 0) {
+      // one global atomic per run of frames that share a clip (normally one per tile)
+      const int64_t g = g0 + lane;
+      const int clip = lane < nf ? find_segment(b.frame_off, b.n_clips, g) : -1;
+      const uint32_t key = lane < nf ? s_max[lane] : 0u;
+      const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
+      const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
+      if (uniform) {
+        uint32_t k = key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, o));
+        if (lane == 0) atomicMax(dbmax_key + first_clip, k);
+      } else if (clip >= 0) {
+        atomicMax(dbmax_key + clip, key);
+      }
+    }
   }
 }
 
@@ -411,22 +468,36 @@ __host__ __device__ inline AcGeom ac_geom(int F) {
 // returns r[0]-normalised values; lane (0,0)'s acc[0] is lag 0 (== 1 or 0).
 __device__ __forceinline__ void autocorr_frame(const DeviceTables& t, const float* __restrict__ y,
                                                int64_t base, int64_t len, int64_t tf, float* xs,
-                                               const AcGeom& geo, int lane, float (&acc)[kAcLagsPerLane]) {
+                                               const float* __restrict__ hann, const AcGeom& geo, int lane,
+                                               float (&acc)[kAcLagsPerLane]) {
   const int F = t.F;
   const int64_t first = tf * t.H - t.pad;
   // pass 1: load with np.pad(..., mode='reflect') indexing, accumulate the mean
   float part = 0.0f;
-  for (int n = lane; n < F; n += 32) {
-    int64_t i = first + n;
-    if (i < 0) i = -i;
-    if (i >= len) i = 2 * (len - 1) - i;
-    const float v = __ldg(y + base + i);
-    xs[n] = v;
-    part += v;
+  if (first >= 0 && first + F <= len) {          // interior frame: plain coalesced loads, 16 in flight
+    const float* src = y + base + first;
+    for (int n0 = lane; n0 < F; n0 += 32 * 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (n0 + 32 * k < F) ? __ldg(src + n0 + 32 * k) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (n0 + 32 * k < F) { xs[n0 + 32 * k] = v[k]; part += v[k]; }
+    }
+  } else {
+    for (int n = lane; n < F; n += 32) {
+      int64_t i = first + n;
+      if (i < 0) i = -i;
+      if (i >= len) i = 2 * (len - 1) - i;
+      const float v = __ldg(y + base + i);
+      xs[n] = v;
+      part += v;
+    }
   }
   const float mean = warp_sum(part) / static_cast<float>(F);
   __syncwarp();
-  for (int n = lane; n < F; n += 32) xs[n] = (xs[n] - mean) * __ldg(t.hann_sym + n);
+#pragma unroll 4
+  for (int n = lane; n < F; n += 32) xs[n] = (xs[n] - mean) * __ldg(hann + n);
   for (int n = F + lane; n < geo.row_floats; n += 32) xs[n] = 0.0f;
   __syncwarp();
 
@@ -462,8 +533,9 @@ __device__ __forceinline__ void autocorr_frame(const DeviceTables& t, const floa
   for (int j = 0; j < kAcLagsPerLane; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
   const float r0 = __shfl_sync(0xffffffffu, acc[0], 0);
   if (r0 != 0.0f) {
+    const float inv = __fdiv_rn(1.0f, r0);       // one division per frame; the products are within 1 ulp
 #pragma unroll
-    for (int j = 0; j < kAcLagsPerLane; ++j) acc[j] = __fdiv_rn(acc[j], r0);
+    for (int j = 0; j < kAcLagsPerLane; ++j) acc[j] *= inv;
   }
   __syncwarp();
 }
@@ -480,7 +552,7 @@ __device__ __forceinline__ bool ac_all_small(const float (&acc)[kAcLagsPerLane],
   return __all_sync(0xffffffffu, small);
 }
 
-__global__ void __launch_bounds__(kAcWarps * 32) k_autocorr(DeviceTables t, BatchView b,
+__global__ void __launch_bounds__(kAcWarps * 32, 4) k_autocorr(DeviceTables t, BatchView b,
                                                             const float* __restrict__ y, bool reduce,
                                                             float* __restrict__ out, int64_t out_ld,
                                                             int col0) {
@@ -488,6 +560,7 @@ __global__ void __launch_bounds__(kAcWarps * 32) k_autocorr(DeviceTables t, Batc
   const AcGeom geo = ac_geom(t.F);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* xs = s_ac + static_cast<size_t>(warp) * geo.row_floats;
+  const float* hann = t.hann_sym;                                        // L1-resident read-only table
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * kAcWarps + warp; r < b.total_rows;
        r += static_cast<int64_t>(gridDim.x) * kAcWarps) {
     const int clip = find_segment(b.row_off, b.n_clips, r);
@@ -499,9 +572,9 @@ __global__ void __launch_bounds__(kAcWarps * 32) k_autocorr(DeviceTables t, Batc
     if (reduce) {
       const int64_t ta = 2 * lr;
       const bool pair = ta + 1 < T;
-      autocorr_frame(t, y, base, len, ta, xs, geo, lane, va);
+      autocorr_frame(t, y, base, len, ta, xs, hann, geo, lane, va);
       if (pair) {
-        autocorr_frame(t, y, base, len, ta + 1, xs, geo, lane, vb);
+        autocorr_frame(t, y, base, len, ta + 1, xs, hann, geo, lane, vb);
         // fix_edge_frames_autocorr: first frame copies frame 1, last frame copies frame T-2
         if (ta == 0 && ac_all_small(va, lane, t.n_lags)) {
 #pragma unroll
@@ -514,14 +587,14 @@ __global__ void __launch_bounds__(kAcWarps * 32) k_autocorr(DeviceTables t, Batc
 #pragma unroll
         for (int j = 0; j < kAcLagsPerLane; ++j) va[j] = 0.5f * (va[j] + vb[j]);
       } else if (ta == T - 1 && ac_all_small(va, lane, t.n_lags)) {
-        autocorr_frame(t, y, base, len, T - 2, xs, geo, lane, va);  // odd T: last row passes through
+        autocorr_frame(t, y, base, len, T - 2, xs, hann, geo, lane, va);  // odd T: last row passes through
       }
     } else {
-      autocorr_frame(t, y, base, len, lr, xs, geo, lane, va);
+      autocorr_frame(t, y, base, len, lr, xs, hann, geo, lane, va);
       if (lr == 0 && ac_all_small(va, lane, t.n_lags)) {
-        autocorr_frame(t, y, base, len, 1, xs, geo, lane, va);
+        autocorr_frame(t, y, base, len, 1, xs, hann, geo, lane, va);
       } else if (lr == T - 1 && ac_all_small(va, lane, t.n_lags)) {
-        autocorr_frame(t, y, base, len, T - 2, xs, geo, lane, va);
+        autocorr_frame(t, y, base, len, T - 2, xs, hann, geo, lane, va);
       }
     }
     if (lane < 16) {
@@ -792,8 +865,20 @@ int launch_dft_simt(cudaStream_t s, const DeviceTables& t, const BatchView& b, c
 
 int launch_mel_db(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* power,
                   float* db, uint32_t* dbmax_key) {
-  const int grid = grid_for(b.total_frames, kMelWarps, kSmCount * 8);
-  k_mel_db<<<grid, kMelWarps * 32, kMelWarps * t.bins_ld * sizeof(float), s>>>(t, b, power, db, dbmax_key);
+  if (t.n_mels > kMelWarps * kMelPerWarp) return -1;
+  const int chain_cols = t.np[0] > t.np[1] ? t.np[0] : t.np[1];
+  const size_t smem = (static_cast<size_t>(chain_cols) * kMelPitch + kMelFrames * (t.n_mels + 1)) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_mel_db, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) return -1;
+  int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const int grid = grid_for((b.total_frames + kMelFrames - 1) / kMelFrames, 1, kSmCount * per_sm);
+  k_mel_db<<<grid, kMelWarps * 32, smem, s>>>(t, b, power, db, dbmax_key, chain_cols);
   NSF_CHECK_LAUNCH();
   return 1;
 }

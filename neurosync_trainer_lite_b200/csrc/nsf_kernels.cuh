@@ -26,7 +26,8 @@ struct DeviceTables {
   const int32_t* tap_idx[2];  // [part][tap][kp]
   const float* tap_coef[2];
   const float* mat32[2][2];   // [chain][part] row-major [kp][np] float32 (validation GEMM)
-  const float* hann_sym;      // [F]
+  const float* hann_sym;      // [F] np.hanning (autocorr branch)
+  const float* hann_per;      // [F] periodic Hann (STFT branch)
   // sparse mel basis re-indexed to the chain-major power layout: per (chain, mel) one run of
   // consecutive power columns; arrays are [chains][n_mels]
   const int32_t* mel_start;   // first power column of the run

@@ -147,70 +147,112 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_tc_fold: one block per hop-frame (grid-stride).  Gathers the zero-padded frame, forms the
-// folded inputs (<= 4 signed, windowed taps each), picks the power-of-two scale that puts the
-// frame's largest folded value in [2^13, 2^14), and writes fp16 hi / lo planes.
-// Operand layout: plane = (chain*2 + part)*2 + hl ; element [plane][frame][k], k contiguous.
+// k_tc_fold: one WARP per hop-frame (grid-stride).  The warp stages the zero-padded, periodic-Hann
+// windowed frame u[0..F) in shared memory, then forms the folded GEMM inputs in closed form
+// (nsf_plan.cpp build_fold describes the same sums as tap tables; tests check them against an FFT):
+//   even F, Nh = F/2, j = 0..Nh/2:   u0 = u[j], u1 = u[j+Nh], u2 = u[Nh-j], u3 = u[F-j]
+//       even bins  Re: u0+u1+u2+u3   Im: u0+u1-u2-u3      odd bins  Re: u0-u1-u2+u3   Im: u0-u1+u2-u3
+//       (j == 0 or 2j == Nh is its own mirror: u0+u1 resp. u0-u1 for both parts)
+//   odd F, j = 0..(F-1)/2:           Re: u[j]+u[F-j]   Im: u[j]-u[F-j]   (j == 0: u[0])
+// Pass 1 finds the frame's largest folded magnitude, which fixes the power-of-two scale that puts it
+// in [2^13, 2^14); pass 2 recomputes the sums (cheaper than holding them), scales, splits into fp16
+// hi / lo and stores half2 pairs.  Operand layout: plane = (chain*2 + part)*2 + hl;
+// element [plane][frame][k], k contiguous.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tc_fold(DeviceTables t, BatchView b, const float* __restrict__ y,
-                                                 __half* __restrict__ planes, int64_t plane_rows,
-                                                 int32_t* __restrict__ row_exp) {
-  extern __shared__ float s_fold[];   // [F] frame, then [chains*2*kp] folded values
-  __shared__ float s_red[8];
-  float* s_x = s_fold;
-  float* s_p = s_fold + t.F;
-  const int kp = t.kp[0];
-  const int n_out = t.chains * 2 * kp;
-  for (int64_t g = blockIdx.x; g < b.total_frames; g += gridDim.x) {
+constexpr int kFoldWarps = 8;
+
+struct Folded { float v[4]; };  // [chain*2 + part]
+
+__device__ __forceinline__ Folded fold_at(const float* __restrict__ u, int j, int F, int Nh, int K, bool even) {
+  Folded o;
+  if (j >= K) { o.v[0] = o.v[1] = o.v[2] = o.v[3] = 0.0f; return o; }
+  if (even) {
+    const float u0 = u[j], u1 = u[j + Nh];
+    const float s = u0 + u1, d = u0 - u1;
+    if (j == 0 || 2 * j == Nh) {
+      o.v[0] = s; o.v[1] = s; o.v[2] = d; o.v[3] = d;
+    } else {
+      const float u2 = u[Nh - j], u3 = u[F - j];
+      const float s2 = u2 + u3, d2 = u3 - u2;
+      o.v[0] = s + s2; o.v[1] = s - s2; o.v[2] = d + d2; o.v[3] = d - d2;
+    }
+  } else {
+    const float u0 = u[j];
+    if (j == 0) { o.v[0] = u0; o.v[1] = u0; }
+    else { const float u1 = u[F - j]; o.v[0] = u0 + u1; o.v[1] = u0 - u1; }
+    o.v[2] = 0.0f; o.v[3] = 0.0f;
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(kFoldWarps * 32) k_tc_fold(DeviceTables t, BatchView b, const float* __restrict__ y,
+                                                             __half* __restrict__ planes, int64_t plane_rows,
+                                                             int32_t* __restrict__ row_exp) {
+  extern __shared__ float s_fold[];   // [F] window, then kFoldWarps x [F] frames
+  const int F = t.F, kp = t.kp[0], K = t.chains == 2 ? (F / 2) / 2 + 1 : (F + 1) / 2;
+  const int Nh = F / 2;
+  const bool even = t.chains == 2;
+  const int n_cp = 2 * t.chains;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_win = s_fold;
+  float* u = s_fold + F + warp * F;
+  for (int n = threadIdx.x; n < F; n += blockDim.x) s_win[n] = __ldg(t.hann_per + n);
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kFoldWarps;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * kFoldWarps + warp; g < b.total_frames; g += stride) {
     const int clip = find_segment(b.frame_off, b.n_clips, g);
     const int64_t tf = g - __ldg(b.frame_off + clip);
     const int64_t base = __ldg(b.clip_off + clip);
     const int64_t len = __ldg(b.clip_off + clip + 1) - base;
-    const int64_t first = tf * t.H - t.pad;
-    for (int n = threadIdx.x; n < t.F; n += blockDim.x) {
-      const int64_t i = first + n;
-      s_x[n] = (i >= 0 && i < len) ? __ldg(y + base + i) : 0.0f;
-    }
-    __syncthreads();
-    float vmax = 0.0f;
-    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
-      const int cp = e / kp, j = e - cp * kp;       // cp = chain*2 + part
-      const int c = cp >> 1, part = cp & 1;
-      float acc = 0.0f;
+    const int64_t first = tf * t.H - t.pad;      // zero padding (librosa stft center=True, constant)
+    const float* src = y + base + first;
+    if (first >= 0 && first + F <= len) {
+      // 16 independent 128-byte requests per warp in flight before the first use
+      for (int n0 = lane; n0 < F; n0 += 32 * 16) {
+        float v[16];
 #pragma unroll
-      for (int tap = 0; tap < 4; ++tap) {
-        const int o = (part * 4 + tap) * kp + j;
-        acc = fmaf(__ldg(t.tap_coef[c] + o), s_x[__ldg(t.tap_idx[c] + o)], acc);
+        for (int q = 0; q < 16; ++q) v[q] = (n0 + 32 * q < F) ? __ldg(src + n0 + 32 * q) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (n0 + 32 * q < F) u[n0 + 32 * q] = v[q] * s_win[n0 + 32 * q];
       }
-      s_p[e] = acc;
-      vmax = fmaxf(vmax, fabsf(acc));
+    } else {
+      for (int n = lane; n < F; n += 32) {
+        const int64_t i = first + n;
+        u[n] = (i >= 0 && i < len) ? __ldg(src + n) * s_win[n] : 0.0f;
+      }
     }
+    __syncwarp();
+    // pass 1: largest folded magnitude of the frame
+    float vmax = 0.0f;
+    for (int j = 2 * lane; j < kp; j += 64) {
+      const Folded a = fold_at(u, j, F, Nh, K, even), c = fold_at(u, j + 1, F, Nh, K, even);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = vmax;
-    __syncthreads();
-    vmax = s_red[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) vmax = fmaxf(vmax, s_red[w]);
+      for (int q = 0; q < 4; ++q) vmax = fmaxf(vmax, fmaxf(fabsf(a.v[q]), fabsf(c.v[q])));
+    }
+    vmax = warp_max(vmax);
     // scale = 2^e with vmax * 2^e in [2^13, 2^14): exact, and well inside fp16 range
     int e2 = 0;
     if (vmax > 0.0f && vmax < INFINITY) {
-      int ex;
-      frexpf(vmax, &ex);       // vmax = m * 2^ex, m in [0.5, 1)
-      e2 = 14 - ex;
+      e2 = 14 - (static_cast<int>((__float_as_uint(vmax) >> 23) & 0xff) - 126);   // vmax = m * 2^ex, m in [0.5, 1)
       e2 = max(-100, min(100, e2));
     }
-    const float scale = ldexpf(1.0f, e2);
-    if (threadIdx.x == 0) row_exp[g] = e2;
-    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
-      const int cp = e / kp, j = e - cp * kp;
-      const float v = s_p[e] * scale;
-      const __half hi = __float2half_rn(v);
-      const __half lo = __float2half_rn(v - __half2float(hi));
-      planes[(static_cast<int64_t>(cp * 2 + 0) * plane_rows + g) * kp + j] = hi;
-      planes[(static_cast<int64_t>(cp * 2 + 1) * plane_rows + g) * kp + j] = lo;
+    const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
+    if (lane == 0) row_exp[g] = e2;
+    // pass 2: scale, split, store
+    for (int j = 2 * lane; j < kp; j += 64) {
+      const Folded a = fold_at(u, j, F, Nh, K, even), c = fold_at(u, j + 1, F, Nh, K, even);
+      for (int cp = 0; cp < n_cp; ++cp) {
+        const float va = a.v[cp] * scale, vc = c.v[cp] * scale;
+        const __half2 hi = __floats2half2_rn(va, vc);
+        const float2 back = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(va - back.x, vc - back.y);
+        __half* dst = planes + (static_cast<int64_t>(cp * 2) * plane_rows + g) * kp + j;
+        *reinterpret_cast<__half2*>(dst) = hi;
+        *reinterpret_cast<__half2*>(dst + plane_rows * kp) = lo;
+      }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -445,10 +487,19 @@ int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
                         const float* y, void* operands) {
   if (!tc.ready) return -1;
   const OperandView v = view_operands(tc, b.total_frames, operands);
-  int64_t grid = b.total_frames < 148 * 8 ? b.total_frames : 148 * 8;
+  const size_t smem = static_cast<size_t>(1 + kFoldWarps) * t.F * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_tc_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return -1;
+    attr_set = true;
+  }
+  if (smem > 160 * 1024) return -1;
+  int per_sm = static_cast<int>((200 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+  int64_t grid = (b.total_frames + kFoldWarps - 1) / kFoldWarps;
+  if (grid > 148 * per_sm) grid = 148 * per_sm;
   if (grid < 1) grid = 1;
-  const size_t smem = (static_cast<size_t>(t.F) + static_cast<size_t>(t.chains) * 2 * tc.kp) * sizeof(float);
-  k_tc_fold<<<static_cast<int>(grid), 256, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp);
+  k_tc_fold<<<static_cast<int>(grid), kFoldWarps * 32, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

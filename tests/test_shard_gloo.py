@@ -1,0 +1,112 @@
+"""N > 1 host logic on CPU: world_size-2 (and 3) gloo process groups exercise the by-clip sharding,
+the gather to host and the restoration of input order.  No GPU: the extractor is injected, so the
+test drives the real partition / offsets / gather code with the CPU oracle's row counts.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_extract(clips):
+    """Deterministic stand-in for the GPU extractor with the REAL row arithmetic (F=1470, H=735):
+    row r of a clip is [clip checksum, r, mean of the r-th chunk]."""
+    from oracle import feature_oracle as fo
+    counts = [fo.feature_rows(len(c), 1470, 735) for c in clips]
+    off = np.zeros(len(clips) + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    rows = np.zeros((int(off[-1]), 3), dtype=np.float32)
+    for k, c in enumerate(clips):
+        rows[off[k]:off[k + 1], 0] = np.float32(np.sum(c, dtype=np.float64))
+        rows[off[k]:off[k + 1], 1] = np.arange(counts[k])
+        rows[off[k]:off[k + 1], 2] = np.float32(len(c))
+    return rows, off
+
+
+def _clips():
+    rng = np.random.default_rng(7)
+    lens = [30000, 8085, 8085, 120000, 44100, 7351, 90000, 90000, 15000, 61234, 8085]
+    return [rng.standard_normal(n).astype(np.float32) for n in lens]
+
+
+def _worker(rank, world, port, shm_name, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from neurosync_trainer_lite_b200 import shard
+    from oracle import feature_oracle as fo
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        clips = _clips()
+        piece = shard.extract_shard(clips, rank, world, _fake_extract)
+        rows, offsets = shard.gather_rows(len(clips), piece, dst=0)
+        # shared-memory variant: every rank writes its slice of one host array
+        counts = [fo.feature_rows(len(c), 1470, 735) for c in clips]
+        goff, _ = shard.row_layout(counts, shard.lpt_partition([len(c) for c in clips], world))
+        if rank == 0:
+            shared = shard.SharedRows(shm_name, goff[-1], 3, create=True)
+        dist.barrier()
+        if rank != 0:
+            shared = shard.SharedRows(shm_name, goff[-1], 3, create=False)
+        shared.write(piece[0], piece[1], piece[2], goff)
+        dist.barrier()
+        if rank == 0:
+            want, woff = _fake_extract(clips)              # single-process answer, input order
+            ok = (np.array_equal(rows, want) and np.array_equal(offsets, woff)
+                  and np.array_equal(np.asarray(shared.array), want))
+            q.put(("ok" if ok else "mismatch", len(piece[0])))
+        dist.barrier()
+        shared.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_extraction_gathers_in_input_order(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, f"nsf_test_{os.getpid()}_{world}", q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    status, _ = q.get(timeout=10)
+    assert status == "ok"
+
+
+def test_lpt_partition_properties():
+    from neurosync_trainer_lite_b200 import shard
+    lens = [len(c) for c in _clips()]
+    for world in (1, 2, 3, 4, 8):
+        parts = shard.lpt_partition(lens, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(lens)))   # a partition
+        loads = [sum(lens[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(lens)                            # LPT balance bound
+        assert parts == shard.lpt_partition(lens, world)                       # deterministic
+    # equal-length clips -> round robin (BASELINE configs 2-4: 30 s clips)
+    assert shard.lpt_partition([100] * 8, 4) == [[0, 4], [1, 5], [2, 6], [3, 7]]
+    assert shard.lpt_partition([5, 5], 4) == [[0], [1], [], []]
+
+
+def test_assemble_handles_empty_ranks():
+    from neurosync_trainer_lite_b200 import shard
+    clips = _clips()[:2]
+    pieces = [shard.extract_shard(clips, r, 4, _fake_extract) for r in range(4)]
+    rows, off = shard.assemble(len(clips), pieces)
+    want, woff = _fake_extract(clips)
+    np.testing.assert_array_equal(rows, want)
+    np.testing.assert_array_equal(off, woff)
