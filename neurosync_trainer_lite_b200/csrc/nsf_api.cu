@@ -519,8 +519,7 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
   // stage 4: floor + DCT + CMVN statistics
   timer.mark(4);
   if (do_mfcc) {
-    NSF_LAUNCH(launch_dct_sum(s, t, b, L.db, L.dbmax_key, L.mfcc_raw, L.sum));
-    if (!(flags & NSF_NO_CMVN)) NSF_LAUNCH(launch_dev_sq(s, t, b, L.mfcc_raw, L.sum, L.sumsq));
+    NSF_LAUNCH(launch_dct_sum(s, t, b, L.db, L.dbmax_key, L.mfcc_raw, L.sum, L.sumsq));
   }
   // stage 5: CMVN + deltas + pair reduce -> columns [0, mfcc_cols)
   timer.mark(5);

@@ -5,7 +5,7 @@
 //                            is the tcgen05 kernel in nsf_stft_tc.cu
 //   k_mel_db                 mel projection (sparse: 1.5 % of the 128 x 736 basis is non-zero),
 //                            10 log10(max(1e-10, .)), per-clip max       (HBM bound)
-//   k_dct_sum / k_dev_sq     top_db floor, DCT-II to n_mfcc, CMVN statistics
+//   k_dct_sum                top_db floor, DCT-II to n_mfcc, CMVN moments (sum x, sum x^2 in f64)
 //   k_delta_reduce           CMVN, Savitzky-Golay delta / delta-delta, pair reduction
 //   k_autocorr               reflect-pad framing, DC removal, np.hanning, 188 lags, normalise,
 //                            edge fix, pair reduction  (fp32 FMA bound; extract_features_utils.py:54-113)
@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(kDctWarps * 32) k_dct_sum(DeviceTables t, Batc
                                                             const float* __restrict__ db,
                                                             const uint32_t* __restrict__ dbmax_key,
                                                             float* __restrict__ mfcc_raw,
-                                                            double* __restrict__ sum) {
+                                                            double* __restrict__ sum,
+                                                            double* __restrict__ sumsq) {
   __shared__ float s_dct[128 * 32];           // [m][k] (k padded to 32): conflict-free per lane
   __shared__ float s_v[kDctWarps][128];
   for (int i = threadIdx.x; i < t.n_mels * 32; i += blockDim.x) s_dct[i] = __ldg(t.dct_t + i);
@@ -312,11 +313,14 @@ __global__ void __launch_bounds__(kDctWarps * 32) k_dct_sum(DeviceTables t, Batc
     int clip = find_segment(b.frame_off, b.n_clips, g_begin);
     int64_t clip_end = __ldg(b.frame_off + clip + 1);
     float floor_db = key_float(__ldg(dbmax_key + clip)) - 80.0f;
-    double run_sum = 0.0;
+    double run_sum = 0.0, run_sq = 0.0;
     for (int64_t g = g_begin; g < g_end; ++g) {
       if (g >= clip_end) {
-        if (lane < t.n_mfcc) atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sum);
-        run_sum = 0.0;
+        if (lane < t.n_mfcc) {
+          atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sum);
+          atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sq);
+        }
+        run_sum = 0.0; run_sq = 0.0;
         while (g >= clip_end) { ++clip; clip_end = __ldg(b.frame_off + clip + 1); }
         floor_db = key_float(__ldg(dbmax_key + clip)) - 80.0f;
       }
@@ -328,45 +332,16 @@ __global__ void __launch_bounds__(kDctWarps * 32) k_dct_sum(DeviceTables t, Batc
       for (int m = 0; m < t.n_mels; ++m) acc = fmaf(s_dct[m * 32 + lane], s_v[warp][m], acc);
       if (lane < t.n_mfcc) {
         mfcc_raw[g * t.n_mfcc + lane] = acc;
-        run_sum += static_cast<double>(acc);
+        const double ad = static_cast<double>(acc);
+        run_sum += ad;
+        run_sq = fma(ad, ad, run_sq);
       }
       __syncwarp();
     }
-    if (lane < t.n_mfcc) atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sum);
-  }
-}
-
-// K2b: sum of squared deviations from the clip mean (numpy's two-pass std, ddof = 0)
-__global__ void __launch_bounds__(kDctWarps * 32) k_dev_sq(DeviceTables t, BatchView b,
-                                                           const float* __restrict__ mfcc_raw,
-                                                           const double* __restrict__ sum,
-                                                           double* __restrict__ sumsq) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_runs = (b.total_frames + kDctRun - 1) / kDctRun;
-  for (int64_t run = static_cast<int64_t>(blockIdx.x) * kDctWarps + warp; run < n_runs;
-       run += static_cast<int64_t>(gridDim.x) * kDctWarps) {
-    const int64_t g_begin = run * kDctRun, g_end = min(g_begin + kDctRun, b.total_frames);
-    int clip = find_segment(b.frame_off, b.n_clips, g_begin);
-    int64_t clip_end = __ldg(b.frame_off + clip + 1);
-    double mean = 0.0, acc = 0.0;
-    auto load_mean = [&]() {
-      const double T = static_cast<double>(clip_end - __ldg(b.frame_off + clip));
-      mean = lane < t.n_mfcc ? __ldg(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane) / T : 0.0;
-    };
-    load_mean();
-    for (int64_t g = g_begin; g < g_end; ++g) {
-      if (g >= clip_end) {
-        if (lane < t.n_mfcc) atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + lane, acc);
-        acc = 0.0;
-        while (g >= clip_end) { ++clip; clip_end = __ldg(b.frame_off + clip + 1); }
-        load_mean();
-      }
-      if (lane < t.n_mfcc) {
-        const double d = static_cast<double>(__ldg(mfcc_raw + g * t.n_mfcc + lane)) - mean;
-        acc = fma(d, d, acc);
-      }
+    if (lane < t.n_mfcc) {
+      atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sum);
+      atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sq);
     }
-    if (lane < t.n_mfcc) atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + lane, acc);
   }
 }
 
@@ -425,7 +400,8 @@ __global__ void __launch_bounds__(256) k_delta_reduce(BatchView b, const float* 
       if (cmvn) {
         const double Td = static_cast<double>(T);
         const double m = __ldg(sum + static_cast<int64_t>(clip) * C + ch) / Td;
-        const double var = __ldg(sumsq + static_cast<int64_t>(clip) * C + ch) / Td;
+        // population variance from the float64 moments (sum x, sum x^2) of the float32 values
+        const double var = fmax(0.0, __ldg(sumsq + static_cast<int64_t>(clip) * C + ch) / Td - m * m);
         mu = static_cast<float>(m);
         den = static_cast<float>(sqrt(var)) + 1e-10f;  // float32 std + 1e-10 (NEP 50: stays float32)
       }
@@ -758,11 +734,10 @@ __global__ void __launch_bounds__(256) k_rows_op(int op, const T* __restrict__ a
   }
 }
 
-// one block per channel: sum, then sum of squared deviations from the mean (two-pass, float64)
+// one block per channel: float64 moments sum x and sum x^2
 __global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ in, int64_t T, int C,
                                                    double* __restrict__ sum, double* __restrict__ sumsq) {
   __shared__ double s_red[8];
-  __shared__ double s_mean;
   const int c = blockIdx.x;
   auto block_sum = [&](double v) {
 #pragma unroll
@@ -774,19 +749,15 @@ __global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ in,
     __syncthreads();
     return r;
   };
-  double acc = 0.0;
-  for (int64_t t = threadIdx.x; t < T; t += blockDim.x) acc += static_cast<double>(in[t * C + c]);
-  const double tot = block_sum(acc);
-  if (threadIdx.x == 0) { sum[c] = tot; s_mean = tot / static_cast<double>(T); }
-  __syncthreads();
-  const double mean = s_mean;
-  acc = 0.0;
+  double acc = 0.0, acc2 = 0.0;
   for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
-    const double d = static_cast<double>(in[t * C + c]) - mean;
-    acc = fma(d, d, acc);
+    const double v = static_cast<double>(in[t * C + c]);
+    acc += v;
+    acc2 = fma(v, v, acc2);
   }
-  const double sq = block_sum(acc);
-  if (threadIdx.x == 0) sumsq[c] = sq;
+  const double tot = block_sum(acc);
+  const double sq = block_sum(acc2);
+  if (threadIdx.x == 0) { sum[c] = tot; sumsq[c] = sq; }
 }
 
 // fix_edge_frames_autocorr on a frame-major [T][C] matrix, single block
@@ -884,17 +855,9 @@ int launch_mel_db(cudaStream_t s, const DeviceTables& t, const BatchView& b, con
 }
 
 int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* db,
-                   const uint32_t* dbmax_key, float* mfcc_raw, double* sum) {
+                   const uint32_t* dbmax_key, float* mfcc_raw, double* sum, double* sumsq) {
   const int grid = grid_for((b.total_frames + kDctRun - 1) / kDctRun, kDctWarps, kSmCount * 6);
-  k_dct_sum<<<grid, kDctWarps * 32, 0, s>>>(t, b, db, dbmax_key, mfcc_raw, sum);
-  NSF_CHECK_LAUNCH();
-  return 1;
-}
-
-int launch_dev_sq(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* mfcc_raw,
-                  const double* sum, double* sumsq) {
-  const int grid = grid_for((b.total_frames + kDctRun - 1) / kDctRun, kDctWarps, kSmCount * 8);
-  k_dev_sq<<<grid, kDctWarps * 32, 0, s>>>(t, b, mfcc_raw, sum, sumsq);
+  k_dct_sum<<<grid, kDctWarps * 32, 0, s>>>(t, b, db, dbmax_key, mfcc_raw, sum, sumsq);
   NSF_CHECK_LAUNCH();
   return 1;
 }

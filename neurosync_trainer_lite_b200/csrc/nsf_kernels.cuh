@@ -46,7 +46,7 @@ struct ExtractBuffers {
   uint32_t* peak_bits;     // [n] max|y| as float bits
   uint32_t* dbmax_key;     // [n] order-preserving key of the per-clip dB maximum
   double* sum;             // [n][n_mfcc]
-  double* sumsq;           // [n][n_mfcc] sum of squared deviations
+  double* sumsq;           // [n][n_mfcc] sum of squares
   float* ac_raw;           // [total_frames][n_lags] (only with autocorr deltas)
 };
 
@@ -61,9 +61,7 @@ int launch_dft_simt(cudaStream_t s, const DeviceTables& t, const BatchView& b, c
 int launch_mel_db(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* power,
                   float* db, uint32_t* dbmax_key);
 int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* db,
-                   const uint32_t* dbmax_key, float* mfcc_raw, double* sum);
-int launch_dev_sq(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* mfcc_raw,
-                  const double* sum, double* sumsq);
+                   const uint32_t* dbmax_key, float* mfcc_raw, double* sum, double* sumsq);
 // generic normalise + delta + pair-reduce over a [frames][C] matrix
 int launch_delta_reduce(cudaStream_t s, const BatchView& b, const float* in, int C, int in_ld,
                         const double* sum, const double* sumsq, bool cmvn, bool deltas, bool reduce,

@@ -147,17 +147,20 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_tc_fold: one WARP per hop-frame (grid-stride).  The warp stages the zero-padded, periodic-Hann
-// windowed frame u[0..F) in shared memory, then forms the folded GEMM inputs in closed form
+// k_tc_fold: one WARP per hop-frame (grid-stride), input double-buffered per warp with TMA bulk
+// copies (cp.async.bulk + mbarrier): while the warp folds frame i, the raw samples of frame
+// i + stride are already landing in its second buffer, so every warp keeps ~6 KB of HBM reads in
+// flight at all times.  The warp windows the frame in place (periodic Hann; zero padding at clip
+// edges is filled by the lanes), tracks max|u|, then forms the folded GEMM inputs in closed form
 // (nsf_plan.cpp build_fold describes the same sums as tap tables; tests check them against an FFT):
 //   even F, Nh = F/2, j = 0..Nh/2:   u0 = u[j], u1 = u[j+Nh], u2 = u[Nh-j], u3 = u[F-j]
 //       even bins  Re: u0+u1+u2+u3   Im: u0+u1-u2-u3      odd bins  Re: u0-u1-u2+u3   Im: u0-u1+u2-u3
 //       (j == 0 or 2j == Nh is its own mirror: u0+u1 resp. u0-u1 for both parts)
 //   odd F, j = 0..(F-1)/2:           Re: u[j]+u[F-j]   Im: u[j]-u[F-j]   (j == 0: u[0])
-// Pass 1 finds the frame's largest folded magnitude, which fixes the power-of-two scale that puts it
-// in [2^13, 2^14); pass 2 recomputes the sums (cheaper than holding them), scales, splits into fp16
-// hi / lo and stores half2 pairs.  Operand layout: plane = (chain*2 + part)*2 + hl;
-// element [plane][frame][k], k contiguous.
+// Every folded value is bounded by 4 max|u|, which fixes the exact power-of-two scale
+// (max|u| * 2^e in [2^11, 2^12), so |v| < 2^14); the scaled value is split into fp16 hi / lo and
+// stored as half2 pairs.  Operand layout: plane = (chain*2 + part)*2 + hl; element
+// [plane][frame][k], k contiguous.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFoldWarps = 8;
 
@@ -185,61 +188,117 @@ __device__ __forceinline__ Folded fold_at(const float* __restrict__ u, int j, in
   return o;
 }
 
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Where hop-frame g lives: its clip, the index of its first sample relative to the clip (negative /
+// beyond the end = zero padding) and whether a 16-byte aligned superset of it can be bulk-copied.
+struct FrameRef {
+  int64_t base, first, len;
+  const float* aligned;   // 16-byte aligned start of the bulk copy (fast path only)
+  uint32_t bytes;         // multiple of 16
+  int skew;               // floats between `aligned` and the frame's first sample
+  bool fast;
+};
+
+__device__ __forceinline__ FrameRef locate_frame(const DeviceTables& t, const BatchView& b, const float* y, int64_t g) {
+  FrameRef r;
+  const int clip = find_segment(b.frame_off, b.n_clips, g);
+  const int64_t tf = g - __ldg(b.frame_off + clip);
+  r.base = __ldg(b.clip_off + clip);
+  r.len = __ldg(b.clip_off + clip + 1) - r.base;
+  r.first = tf * t.H - t.pad;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(y + r.base + r.first);
+  const uintptr_t lo = addr & ~static_cast<uintptr_t>(15);
+  const uintptr_t hi = (addr + static_cast<uintptr_t>(t.F) * 4 + 15) & ~static_cast<uintptr_t>(15);
+  r.aligned = reinterpret_cast<const float*>(lo);
+  r.bytes = static_cast<uint32_t>(hi - lo);
+  r.skew = static_cast<int>((addr - lo) >> 2);
+  r.fast = r.first >= 0 && r.first + t.F <= r.len && lo >= reinterpret_cast<uintptr_t>(y) &&
+           hi <= reinterpret_cast<uintptr_t>(y + b.total_samples);
+  return r;
+}
+
 __global__ void __launch_bounds__(kFoldWarps * 32) k_tc_fold(DeviceTables t, BatchView b, const float* __restrict__ y,
                                                              __half* __restrict__ planes, int64_t plane_rows,
-                                                             int32_t* __restrict__ row_exp) {
-  extern __shared__ float s_fold[];   // [F] window, then kFoldWarps x [F] frames
+                                                             int32_t* __restrict__ row_exp, int buf_floats) {
+  extern __shared__ __align__(16) float s_fold[];   // [F (+pad)] window, then kFoldWarps x 2 x [buf_floats] frames
+  __shared__ uint64_t s_bar[kFoldWarps][2];
   const int F = t.F, kp = t.kp[0], K = t.chains == 2 ? (F / 2) / 2 + 1 : (F + 1) / 2;
   const int Nh = F / 2;
   const bool even = t.chains == 2;
   const int n_cp = 2 * t.chains;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_win = s_fold;
-  float* u = s_fold + F + warp * F;
+  float* bufs = s_fold + ((F + 3) & ~3) + static_cast<size_t>(warp) * 2 * buf_floats;
   for (int n = threadIdx.x; n < F; n += blockDim.x) s_win[n] = __ldg(t.hann_per + n);
+  if (lane == 0) {
+    mbar_init(&s_bar[warp][0], 1);
+    mbar_init(&s_bar[warp][1], 1);
+    fence_barrier_init();
+  }
   __syncthreads();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kFoldWarps;
-  for (int64_t g = static_cast<int64_t>(blockIdx.x) * kFoldWarps + warp; g < b.total_frames; g += stride) {
-    const int clip = find_segment(b.frame_off, b.n_clips, g);
-    const int64_t tf = g - __ldg(b.frame_off + clip);
-    const int64_t base = __ldg(b.clip_off + clip);
-    const int64_t len = __ldg(b.clip_off + clip + 1) - base;
-    const int64_t first = tf * t.H - t.pad;      // zero padding (librosa stft center=True, constant)
-    const float* src = y + base + first;
-    if (first >= 0 && first + F <= len) {
-      // 16 independent 128-byte requests per warp in flight before the first use
-      for (int n0 = lane; n0 < F; n0 += 32 * 16) {
-        float v[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = (n0 + 32 * q < F) ? __ldg(src + n0 + 32 * q) : 0.0f;
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          if (n0 + 32 * q < F) u[n0 + 32 * q] = v[q] * s_win[n0 + 32 * q];
+  int64_t g = static_cast<int64_t>(blockIdx.x) * kFoldWarps + warp;
+  uint32_t phase_bits = 0u;   // bit s = parity the next wait on buffer s expects
+  FrameRef cur;
+  if (g < b.total_frames) {
+    cur = locate_frame(t, b, y, g);
+    if (cur.fast && lane == 0) {
+      mbar_expect_tx(&s_bar[warp][0], cur.bytes);
+      bulk_load(bufs, cur.aligned, cur.bytes, &s_bar[warp][0]);
+    }
+  }
+  for (int it = 0; g < b.total_frames; g += stride, ++it) {
+    const int slot = it & 1;
+    // prefetch the next frame of this warp into the other buffer
+    const int64_t gn = g + stride;
+    FrameRef nxt;
+    nxt.fast = false;
+    if (gn < b.total_frames) {
+      nxt = locate_frame(t, b, y, gn);
+      if (nxt.fast && lane == 0) {
+        // the other buffer was last touched by this warp's generic-proxy stores two frames ago
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_bar[warp][slot ^ 1], nxt.bytes);
+        bulk_load(bufs + (slot ^ 1) * buf_floats, nxt.aligned, nxt.bytes, &s_bar[warp][slot ^ 1]);
+      }
+    }
+    float* u = bufs + slot * buf_floats;
+    float umax = 0.0f;
+    if (cur.fast) {
+      mbar_wait(&s_bar[warp][slot], (phase_bits >> slot) & 1u);
+      phase_bits ^= 1u << slot;
+      u += cur.skew;
+#pragma unroll 4
+      for (int n = lane; n < F; n += 32) {
+        const float v = u[n] * s_win[n];
+        u[n] = v;
+        umax = fmaxf(umax, fabsf(v));
       }
     } else {
+      const float* src = y + cur.base + cur.first;   // zero padding (librosa stft center=True, constant)
       for (int n = lane; n < F; n += 32) {
-        const int64_t i = first + n;
-        u[n] = (i >= 0 && i < len) ? __ldg(src + n) * s_win[n] : 0.0f;
+        const int64_t i = cur.first + n;
+        const float v = (i >= 0 && i < cur.len) ? __ldg(src + n) * s_win[n] : 0.0f;
+        u[n] = v;
+        umax = fmaxf(umax, fabsf(v));
       }
     }
+    umax = warp_max(umax);     // also orders the in-place stores before the cross-lane reads below
     __syncwarp();
-    // pass 1: largest folded magnitude of the frame
-    float vmax = 0.0f;
-    for (int j = 2 * lane; j < kp; j += 64) {
-      const Folded a = fold_at(u, j, F, Nh, K, even), c = fold_at(u, j + 1, F, Nh, K, even);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) vmax = fmaxf(vmax, fmaxf(fabsf(a.v[q]), fabsf(c.v[q])));
-    }
-    vmax = warp_max(vmax);
-    // scale = 2^e with vmax * 2^e in [2^13, 2^14): exact, and well inside fp16 range
+    // scale = 2^e with umax * 2^e in [2^11, 2^12): exact, and |folded| <= 4 umax stays below 2^14
     int e2 = 0;
-    if (vmax > 0.0f && vmax < INFINITY) {
-      e2 = 14 - (static_cast<int>((__float_as_uint(vmax) >> 23) & 0xff) - 126);   // vmax = m * 2^ex, m in [0.5, 1)
+    if (umax > 0.0f && umax < INFINITY) {
+      e2 = 12 - (static_cast<int>((__float_as_uint(umax) >> 23) & 0xff) - 126);   // umax = m * 2^ex, m in [0.5, 1)
       e2 = max(-100, min(100, e2));
     }
     const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
     if (lane == 0) row_exp[g] = e2;
-    // pass 2: scale, split, store
     for (int j = 2 * lane; j < kp; j += 64) {
       const Folded a = fold_at(u, j, F, Nh, K, even), c = fold_at(u, j + 1, F, Nh, K, even);
       for (int cp = 0; cp < n_cp; ++cp) {
@@ -253,6 +312,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_tc_fold(DeviceTables t, Bat
       }
     }
     __syncwarp();
+    cur = nxt;
   }
 }
 
@@ -487,19 +547,20 @@ int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
                         const float* y, void* operands) {
   if (!tc.ready) return -1;
   const OperandView v = view_operands(tc, b.total_frames, operands);
-  const size_t smem = static_cast<size_t>(1 + kFoldWarps) * t.F * sizeof(float);
+  const int buf_floats = ((t.F + 3) & ~3) + 8;   // frame + up to 3 floats of skew + tail, 16-byte multiple
+  const size_t smem = (static_cast<size_t>((t.F + 3) & ~3) + static_cast<size_t>(kFoldWarps) * 2 * buf_floats) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_tc_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_tc_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
     attr_set = true;
   }
-  if (smem > 160 * 1024) return -1;
-  int per_sm = static_cast<int>((200 * 1024) / (smem + 1024));
+  if (smem > 220 * 1024) return -1;
+  int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
   int64_t grid = (b.total_frames + kFoldWarps - 1) / kFoldWarps;
   if (grid > 148 * per_sm) grid = 148 * per_sm;
   if (grid < 1) grid = 1;
-  k_tc_fold<<<static_cast<int>(grid), kFoldWarps * 32, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp);
+  k_tc_fold<<<static_cast<int>(grid), kFoldWarps * 32, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp, buf_floats);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
