@@ -60,6 +60,9 @@ typedef enum nsf_status {
 #define NSF_DEBUG_SIMT_DFT 0x100u /* validation aid: run the STFT GEMM on CUDA cores in fp32 instead
                                      of tcgen05 (never selected automatically)                      */
 
+#define NSF_DEBUG_FMA_AUTOCORR 0x200u /* validation aid: autocorrelation with fp32 CUDA-core FMAs instead
+                                         of the mma.sync Hankel kernel (never selected automatically) */
+
 /* collect flags */
 #define NSF_COLLECT_FAST 0x1u  /* include_fast      (dataset/data_processing.py:152-158) */
 #define NSF_COLLECT_SLOW 0x2u  /* include_slow      (dataset/data_processing.py:161-167) */

@@ -532,11 +532,13 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
     if (flags & NSF_AC_DELTAS) {
       BatchView bf = b;  // un-reduced: one row per hop-frame
       bf.row_off = L.frame_off; bf.total_rows = hd.total_frames;
-      NSF_LAUNCH(launch_autocorr(s, t, bf, y, false, L.ac_raw, p.n_lags, 0));
+      if (flags & NSF_DEBUG_FMA_AUTOCORR) NSF_LAUNCH(launch_autocorr(s, t, bf, y, false, L.ac_raw, p.n_lags, 0));
+      else NSF_LAUNCH(launch_autocorr_mma(s, t, bf, y, false, L.ac_raw, p.n_lags, 0));
       NSF_LAUNCH(launch_delta_reduce(s, b, L.ac_raw, p.n_lags, p.n_lags, nullptr, nullptr, false, true,
                                      reduce, stage_out, stage_ld, mfcc_cols));
     } else {
-      NSF_LAUNCH(launch_autocorr(s, t, b, y, reduce, stage_out, stage_ld, mfcc_cols));
+      if (flags & NSF_DEBUG_FMA_AUTOCORR) NSF_LAUNCH(launch_autocorr(s, t, b, y, reduce, stage_out, stage_ld, mfcc_cols));
+      else NSF_LAUNCH(launch_autocorr_mma(s, t, b, y, reduce, stage_out, stage_ld, mfcc_cols));
     }
   }
   // stage 7: optional smoothing

@@ -1,0 +1,284 @@
+// K4 on the tensor pipe: normalised autocorrelation lags of every hop-frame as Hankel-structured
+// warp-level MMAs (mma.sync m16n8k16, fp16 split operands, fp32 accumulation).
+// Reference: utils/audio/extraction/extract_features_utils.py:54-113 (np.pad reflect, per-frame mean
+// removal, np.hanning, np.correlate lags 0..187, / lag 0, edge-frame fix) and :33-44 (pair mean).
+//
+// Why mma.sync and not tcgen05: the work per frame is a [188 lags x F] Toeplitz matrix-VECTOR
+// product - every frame has its own matrix, so there is no operand shared between frames to make
+// a large GEMM of.  The 16 x 8 x 16 warp MMA is small enough to be filled by ONE frame:
+//     D[i][j] += sum_k A[i][k] B[k][j],  A[i][k] = X(n0 + k + 8 i),  B[k][j] = X(n0 + k - j)
+// contributes X(s + lag) X(s) with lag = 8 i + j (0..127) and s = n0 + k - j, so summing over the
+// K-blocks n0 = 0, 16, 32, ... yields r[lag] for 128 lags at once; a second accumulator fed with
+// the B fragments of 8 blocks earlier (a register ring) covers lags 128..255.  Both operands are
+// plain reads of the (zero-extended) frame X at shifted offsets, i.e. Hankel matrices that never
+// exist in memory.  A tcgen05 tile (M >= 64, N >= 8) would waste > 60 % of its MACs on lags that
+// are not needed.  Measured on B200 (scripts/ubench_mma.cu): mma.sync m16n8k16 f16 553 TFLOP/s vs
+// 72 TFLOP/s for fp32 FFMA.
+//
+// Precision: X is the mean-removed, windowed frame scaled by an exact power of two and split into
+// fp16 hi + lo; hi.hi + hi.lo + lo.hi carries ~22 mantissa bits (fp32 class).  The scale cancels in
+// r[lag] / r[0].
+#include <cuda_fp16.h>
+
+#include "nsf.h"
+#include "nsf_device_utils.cuh"
+#include "nsf_kernels.cuh"
+
+namespace nsf {
+
+namespace {
+
+constexpr int kSmCount = 148;
+constexpr int kAmWarps = 8;
+constexpr int kFrontMargin = 16;   // halfs of zeros before X(0)  (B reads back to X(-7))
+constexpr int kBackMargin = 128;   // halfs of zeros after the last K-block (A reads up to +73)
+constexpr int kVals = 6;           // lags per thread that can be <= 191
+
+struct AmGeom { int nblk8; int len; };   // K-blocks (multiple of 8), halfs per copy
+__host__ __device__ inline AmGeom am_geom(int F) {
+  AmGeom g;
+  g.nblk8 = ((F + 15) / 16 + 7) / 8 * 8;
+  g.len = kFrontMargin + 16 * g.nblk8 + kBackMargin;
+  return g;
+}
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Lag held in slot v of lane (g, t):  base = 2 t + 8 g;  {base, base+1, base+64, base+65, base+128, base+129}
+__device__ __forceinline__ int lag_of(int lane, int v) {
+  const int base = 2 * (lane & 3) + 8 * (lane >> 2);
+  return base + (v & 1) + 64 * (v >> 1);
+}
+
+// Normalised autocorrelation of hop-frame tf of one clip into val[0..5] (see lag_of).
+// copies: [E_hi | E_lo | O_hi | O_lo], each geo.len halfs; E[kFrontMargin + m] = X(m),
+// O[kFrontMargin + m - 1] = X(m) (the one-sample shifted copy keeps odd offsets 4-byte aligned).
+// kIters = ceil((F/2 + 1) / 32) register-staging iterations: the whole frame is fetched with ONE
+// round trip to memory (2 kIters independent loads per lane in flight) and both passes over it
+// (mean / max, then window + scale + split) run out of registers.
+template <int kIters>
+__device__ __forceinline__ void autocorr_frame_mma(const DeviceTables& t, const float* __restrict__ y,
+                                                   int64_t base, int64_t len, int64_t tf, __half* copies,
+                                                   const AmGeom& geo, int lane, float (&val)[kVals]) {
+  const int F = t.F;
+  const int64_t first = tf * t.H - t.pad;
+  const bool interior = first >= 0 && first + F <= len;
+  const float* src = y + base + first;
+  float v0[kIters], v1[kIters];
+  if (interior) {
+#pragma unroll
+    for (int i = 0; i < kIters; ++i) {
+      const int n = 2 * (lane + 32 * i);
+      v0[i] = n < F ? __ldg(src + n) : 0.0f;
+      v1[i] = n + 1 < F ? __ldg(src + n + 1) : 0.0f;
+    }
+  } else {
+    auto sample = [&](int n) -> float {          // np.pad(..., mode='reflect') indexing
+      int64_t i = first + n;
+      if (i < 0) i = -i;
+      if (i >= len) i = 2 * (len - 1) - i;
+      return __ldg(y + base + i);
+    };
+#pragma unroll
+    for (int i = 0; i < kIters; ++i) {
+      const int n = 2 * (lane + 32 * i);
+      v0[i] = n < F ? sample(n) : 0.0f;
+      v1[i] = n + 1 < F ? sample(n + 1) : 0.0f;
+    }
+  }
+  // pass 1: mean and max |x| (bounds |x - mean| * w, which fixes the fp16 scale)
+  float sum = 0.0f, amax = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kIters; ++i) {
+    sum += v0[i] + v1[i];
+    amax = fmaxf(amax, fmaxf(fabsf(v0[i]), fabsf(v1[i])));
+  }
+  sum = warp_sum(sum);
+  amax = warp_max(amax);
+  const float mean = sum / static_cast<float>(F);
+  const float bound = amax + fabsf(mean);
+  int e2 = 0;
+  if (bound > 0.0f && bound < INFINITY) {
+    e2 = 14 - (static_cast<int>((__float_as_uint(bound) >> 23) & 0xff) - 126);   // bound * 2^e2 in [2^13, 2^14)
+    e2 = max(-100, min(100, e2));
+  }
+  const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
+  // pass 2: window, scale, split, store both copies as half2 pairs.  Pair e holds X(2e), X(2e+1);
+  // the shifted copy needs (X(2e-1), X(2e)): X(2e-1) comes from the previous lane / iteration.
+  __half2* e_hi = reinterpret_cast<__half2*>(copies) + kFrontMargin / 2;
+  __half2* e_lo = e_hi + geo.len / 2;
+  __half2* o_hi = e_lo + geo.len / 2;
+  __half2* o_lo = o_hi + geo.len / 2;
+  const int n_pairs = F / 2 + 1;               // one pair beyond the frame flushes the shifted copy
+  float carry_hi = 0.0f, carry_lo = 0.0f;      // X(2e-1) for lane 0 (hi, lo parts as floats)
+#pragma unroll
+  for (int i = 0; i < kIters; ++i) {
+    const int e = lane + 32 * i;
+    float x0 = 0.0f, x1 = 0.0f;
+    if (2 * e < F) x0 = (v0[i] - mean) * __ldg(t.hann_sym + 2 * e) * scale;
+    if (2 * e + 1 < F) x1 = (v1[i] - mean) * __ldg(t.hann_sym + 2 * e + 1) * scale;
+    const __half2 hi = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hi);
+    const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    const float2 lf = __half22float2(lo);
+    float p_hi = __shfl_up_sync(0xffffffffu, hf.y, 1), p_lo = __shfl_up_sync(0xffffffffu, lf.y, 1);
+    if (lane == 0) { p_hi = carry_hi; p_lo = carry_lo; }
+    carry_hi = __shfl_sync(0xffffffffu, hf.y, 31);
+    carry_lo = __shfl_sync(0xffffffffu, lf.y, 31);
+    if (e < n_pairs) {
+      e_hi[e] = hi;
+      e_lo[e] = lo;
+      // O half2 index e - 1 holds (O[2e-2], O[2e-1]) = (X(2e-1), X(2e)); for e == 0 that is the last
+      // half2 of the front margin: (X(-1) = 0, X(0))
+      o_hi[e - 1] = __floats2half2_rn(p_hi, hf.x);
+      o_lo[e - 1] = __floats2half2_rn(p_lo, lf.x);
+    }
+  }
+  __syncwarp();
+
+  // main loop: 6 MMAs per K-block, all fragment loads conflict-free 32-bit shared reads
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
+  const uint32_t* E_lo = E_hi + geo.len / 2;
+  const uint32_t* O_hi = E_lo + geo.len / 2;
+  const uint32_t* O_lo = O_hi + geo.len / 2;
+  // A: pair at X(n0 + 2 tq + 8 g [+8][+64]) -> even offset, E copy
+  const uint32_t* Ah = E_hi + (kFrontMargin + 2 * tq + 8 * g) / 2;
+  const uint32_t* Al = E_lo + (kFrontMargin + 2 * tq + 8 * g) / 2;
+  // B: pair at X(n0 + 2 tq - g [+8]) -> parity of g picks the copy (O index = X index - 1)
+  const int boff = kFrontMargin + 2 * tq - g - (g & 1);
+  const uint32_t* Bh = ((g & 1) ? O_hi : E_hi) + boff / 2;
+  const uint32_t* Bl = ((g & 1) ? O_lo : E_lo) + boff / 2;
+
+  float d0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  uint32_t ring_h[8][2], ring_l[8][2];        // B fragments of the last 8 K-blocks (lags 128..255)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { ring_h[q][0] = ring_h[q][1] = ring_l[q][0] = ring_l[q][1] = 0u; }
+  // A rows g / g+8 are 64 samples = 4 K-blocks apart: (a1, a3) of block a are (a0, a2) of block a+4
+  uint32_t ar_h[4][2], ar_l[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    ar_h[q][0] = Ah[8 * q]; ar_h[q][1] = Ah[8 * q + 4];
+    ar_l[q][0] = Al[8 * q]; ar_l[q][1] = Al[8 * q + 4];
+  }
+  for (int a0 = 0; a0 < geo.nblk8; a0 += 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int w = 8 * (a0 + q);
+      const uint32_t a1h = Ah[w + 32], a3h = Ah[w + 36], a1l = Al[w + 32], a3l = Al[w + 36];
+      const uint32_t b0h = Bh[w], b1h = Bh[w + 4], b0l = Bl[w], b1l = Bl[w + 4];
+      const uint32_t a0h = ar_h[q & 3][0], a2h = ar_h[q & 3][1], a0l = ar_l[q & 3][0], a2l = ar_l[q & 3][1];
+      mma_16816(d0, a0h, a1h, a2h, a3h, b0h, b1h);
+      mma_16816(d0, a0h, a1h, a2h, a3h, b0l, b1l);
+      mma_16816(d0, a0l, a1l, a2l, a3l, b0h, b1h);
+      mma_16816(d1, a0h, a1h, a2h, a3h, ring_h[q][0], ring_h[q][1]);
+      mma_16816(d1, a0h, a1h, a2h, a3h, ring_l[q][0], ring_l[q][1]);
+      mma_16816(d1, a0l, a1l, a2l, a3l, ring_h[q][0], ring_h[q][1]);
+      ring_h[q][0] = b0h; ring_h[q][1] = b1h; ring_l[q][0] = b0l; ring_l[q][1] = b1l;
+      ar_h[q & 3][0] = a1h; ar_h[q & 3][1] = a3h; ar_l[q & 3][0] = a1l; ar_l[q & 3][1] = a3l;
+    }
+  }
+  // d0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  d1: c0,c1 = base+128, base+129.
+  val[0] = d0[0]; val[1] = d0[1]; val[2] = d0[2]; val[3] = d0[3]; val[4] = d1[0]; val[5] = d1[1];
+  const float r0 = __shfl_sync(0xffffffffu, d0[0], 0);   // lag 0 lives in lane 0
+  if (r0 != 0.0f) {
+    const float inv = __fdiv_rn(1.0f, r0);
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) val[v] *= inv;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane, int n_lags) {
+  bool small = true;
+#pragma unroll
+  for (int v = 0; v < kVals; ++v) {
+    const int lag = lag_of(lane, v);
+    if (lag >= 1 && lag <= n_lags && !(fabsf(val[v]) < 1e-7f)) small = false;
+  }
+  return __all_sync(0xffffffffu, small);
+}
+
+template <int kIters>
+__global__ void __launch_bounds__(kAmWarps * 32, 2) k_autocorr_mma(DeviceTables t, BatchView b,
+                                                                   const float* __restrict__ y, bool reduce,
+                                                                   float* __restrict__ out, int64_t out_ld,
+                                                                   int col0) {
+  extern __shared__ __align__(16) __half s_am[];
+  const AmGeom geo = am_geom(t.F);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* copies = s_am + static_cast<size_t>(warp) * 4 * geo.len;
+  // zero once: the margins are never written again, the frame region is rewritten per frame
+  for (int i = lane; i < 4 * geo.len / 2; i += 32) reinterpret_cast<uint32_t*>(copies)[i] = 0u;
+  __syncwarp();
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kAmWarps + warp; r < b.total_rows;
+       r += static_cast<int64_t>(gridDim.x) * kAmWarps) {
+    const int clip = find_segment(b.row_off, b.n_clips, r);
+    const int64_t base = __ldg(b.clip_off + clip);
+    const int64_t len = __ldg(b.clip_off + clip + 1) - base;
+    const int64_t T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
+    const int64_t lr = r - __ldg(b.row_off + clip);
+    const int64_t tf0 = reduce ? 2 * lr : lr;
+    const int n_frames = (reduce && tf0 + 1 < T) ? 2 : 1;   // odd T: the last row passes through
+    float acc[kVals];
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
+    for (int f = 0; f < n_frames; ++f) {
+      const int64_t tf = tf0 + f;
+      int64_t use = tf;
+      float val[kVals];
+      for (int attempt = 0; attempt < 2; ++attempt) {     // one inlined copy of the frame routine
+        autocorr_frame_mma<kIters>(t, y, base, len, use, copies, geo, lane, val);
+        // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2)
+        if (attempt == 0 && T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags)) {
+          use = tf == 0 ? 1 : T - 2;
+          continue;
+        }
+        break;
+      }
+#pragma unroll
+      for (int v = 0; v < kVals; ++v) acc[v] += val[v];
+    }
+    const float wgt = n_frames == 2 ? 0.5f : 1.0f;
+    float* o = out + r * out_ld + col0;
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) {
+      const int lag = lag_of(lane, v);
+      if (lag >= 1 && lag <= t.n_lags) o[lag - 1] = acc[v] * wgt;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
+                        bool reduce, float* out, int64_t out_ld, int col0) {
+  const AmGeom geo = am_geom(t.F);
+  const size_t smem = static_cast<size_t>(kAmWarps) * 4 * geo.len * sizeof(__half);
+  if (smem > 220 * 1024 || t.n_lags > 191) return -1;
+  int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  int64_t grid = (b.total_rows + kAmWarps - 1) / kAmWarps;
+  if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
+  if (grid < 1) grid = 1;
+  const int iters = (t.F / 2 + 1 + 31) / 32;      // register-staging iterations the frame needs
+  auto go = [&](auto kernel) {
+    // per call: all instantiations share this lambda (same function-pointer type), so no static flag
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
+    kernel<<<static_cast<int>(grid), kAmWarps * 32, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  };
+  if (iters <= 6) return go(k_autocorr_mma<6>);      // F <= 382   (16 kHz: 266, 22.05 kHz: 367)
+  if (iters <= 12) return go(k_autocorr_mma<12>);    // F <= 766   (44.1 kHz: 735)
+  if (iters <= 24) return go(k_autocorr_mma<24>);    // F <= 1534  (48 kHz: 800, 88.2 kHz: 1470)
+  if (iters <= 40) return go(k_autocorr_mma<40>);    // F <= 2558
+  return go(k_autocorr_mma<66>);                     // F <= 4096  (plan limit)
+}
+
+}  // namespace nsf

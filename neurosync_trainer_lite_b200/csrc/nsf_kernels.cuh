@@ -68,6 +68,10 @@ int launch_delta_reduce(cudaStream_t s, const BatchView& b, const float* in, int
                         float* out, int64_t out_ld, int col0);
 int launch_autocorr(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
                     bool reduce, float* out, int64_t out_ld, int col0);
+// tensor-pipe variant (mma.sync m16n8k16, Hankel fragments): the product path; launch_autocorr is
+// the fp32-FMA validation variant (NSF_DEBUG_FMA_AUTOCORR)
+int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
+                        bool reduce, float* out, int64_t out_ld, int col0);
 int launch_smooth(cudaStream_t s, const BatchView& b, const float* in, int64_t in_ld, int cols,
                   float* out, int64_t out_ld);
 

@@ -91,6 +91,20 @@ def test_simt_validation_path_agrees(golden, engine, nv):
     assert np.abs(a[:, :69] - b[:, :69]).max() <= TOL_MFCC
 
 
+def test_fma_autocorr_validation_path_agrees(golden, engine, nv):
+    """The fp32-FMA autocorrelation (debug flag) and the mma.sync Hankel kernel agree with each other
+    and with the reference, including odd frame lengths and the 16 kHz geometry."""
+    for name in ("gated_1s5_88k", "voiced_2s_16k", "voiced_1s_44k1_oddF", "voiced_0s6_22k05_oddF"):
+        g = golden(name)
+        eng = engine.get_engine(int(g["sr"]), int(g["F"]), int(g["H"]))
+        y = g["y"]
+        a = eng.extract_host(y, [0, len(y)], nv.DEBUG_FMA_AUTOCORR | nv.NO_MFCC)
+        b = eng.extract_host(y, [0, len(y)], nv.NO_MFCC)
+        assert np.abs(a - g["features"][:, 69:]).max() <= TOL_AC
+        assert np.abs(b - g["features"][:, 69:]).max() <= TOL_AC
+        assert np.abs(a - b).max() <= TOL_AC
+
+
 def test_switches(golden, ef, efu):
     g = golden("switches_0s5_88k")
     y, sr, F, H = g["y"], int(g["sr"]), int(g["F"]), int(g["H"])
