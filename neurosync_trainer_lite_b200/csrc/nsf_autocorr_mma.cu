@@ -9,7 +9,7 @@
 //     D[i][j] += sum_k A[i][k] B[k][j],  A[i][k] = X(n0 + k + 8 i),  B[k][j] = X(n0 + k - j)
 // contributes X(s + lag) X(s) with lag = 8 i + j (0..127) and s = n0 + k - j, so summing over the
 // K-blocks n0 = 0, 16, 32, ... yields r[lag] for 128 lags at once; a second accumulator fed with
-// the B fragments of 8 blocks earlier (a register ring) covers lags 128..255.  Both operands are
+// the B fragments of 4 blocks earlier (a register ring) covers lags 64..191.  Both operands are
 // plain reads of the (zero-extended) frame X at shifted offsets, i.e. Hankel matrices that never
 // exist in memory.  A tcgen05 tile (M >= 64, N >= 8) would waste > 60 % of its MACs on lags that
 // are not needed.  Measured on B200 (scripts/ubench_mma.cu): mma.sync m16n8k16 f16 553 TFLOP/s vs
@@ -34,11 +34,11 @@ constexpr int kFrontMargin = 16;   // halfs of zeros before X(0)  (B reads back 
 constexpr int kBackMargin = 128;   // halfs of zeros after the last K-block (A reads up to +73)
 constexpr int kVals = 6;           // lags per thread that can be <= 191
 
-struct AmGeom { int nblk8; int len; };   // K-blocks (multiple of 8), halfs per copy
+struct AmGeom { int nblk4; int len; };   // K-blocks (multiple of 4), halfs per copy
 __host__ __device__ inline AmGeom am_geom(int F) {
   AmGeom g;
-  g.nblk8 = ((F + 15) / 16 + 7) / 8 * 8;
-  g.len = kFrontMargin + 16 * g.nblk8 + kBackMargin;
+  g.nblk4 = ((F + 15) / 16 + 3) / 4 * 4;
+  g.len = kFrontMargin + 16 * g.nblk4 + kBackMargin;
   return g;
 }
 
@@ -121,8 +121,13 @@ __device__ __forceinline__ void autocorr_frame_mma(const DeviceTables& t, const 
   for (int i = 0; i < kIters; ++i) {
     const int e = lane + 32 * i;
     float x0 = 0.0f, x1 = 0.0f;
-    if (2 * e < F) x0 = (v0[i] - mean) * __ldg(t.hann_sym + 2 * e) * scale;
-    if (2 * e + 1 < F) x1 = (v1[i] - mean) * __ldg(t.hann_sym + 2 * e + 1) * scale;
+    if (2 * e + 1 < F) {                               // the table is 256-byte aligned: one 8-byte load
+      const float2 w = __ldg(reinterpret_cast<const float2*>(t.hann_sym) + e);
+      x0 = (v0[i] - mean) * w.x * scale;
+      x1 = (v1[i] - mean) * w.y * scale;
+    } else if (2 * e < F) {
+      x0 = (v0[i] - mean) * __ldg(t.hann_sym + 2 * e) * scale;
+    }
     const __half2 hi = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(hi);
     const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
@@ -156,10 +161,14 @@ __device__ __forceinline__ void autocorr_frame_mma(const DeviceTables& t, const 
   const uint32_t* Bh = ((g & 1) ? O_hi : E_hi) + boff / 2;
   const uint32_t* Bl = ((g & 1) ? O_lo : E_lo) + boff / 2;
 
-  float d0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  uint32_t ring_h[8][2], ring_l[8][2];        // B fragments of the last 8 K-blocks (lags 128..255)
+  // accumulators: tile 0 = lags 8 i + j (0..127); tile 1 is fed with the B fragments of FOUR blocks
+  // earlier (64 samples), i.e. lags 64 + 8 i + j - its rows 8..15 are lags 128..191.  The main
+  // (hi.hi) and the two cross products go to separate accumulators: four independent MMA chains.
+  float d0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d0x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float d1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  uint32_t ring_h[4][2], ring_l[4][2];        // B fragments of the last 4 K-blocks
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { ring_h[q][0] = ring_h[q][1] = ring_l[q][0] = ring_l[q][1] = 0u; }
+  for (int q = 0; q < 4; ++q) { ring_h[q][0] = ring_h[q][1] = ring_l[q][0] = ring_l[q][1] = 0u; }
   // A rows g / g+8 are 64 samples = 4 K-blocks apart: (a1, a3) of block a are (a0, a2) of block a+4
   uint32_t ar_h[4][2], ar_l[4][2];
 #pragma unroll
@@ -167,26 +176,27 @@ __device__ __forceinline__ void autocorr_frame_mma(const DeviceTables& t, const 
     ar_h[q][0] = Ah[8 * q]; ar_h[q][1] = Ah[8 * q + 4];
     ar_l[q][0] = Al[8 * q]; ar_l[q][1] = Al[8 * q + 4];
   }
-  for (int a0 = 0; a0 < geo.nblk8; a0 += 8) {
+  for (int a0 = 0; a0 < geo.nblk4; a0 += 4) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 4; ++q) {
       const int w = 8 * (a0 + q);
       const uint32_t a1h = Ah[w + 32], a3h = Ah[w + 36], a1l = Al[w + 32], a3l = Al[w + 36];
       const uint32_t b0h = Bh[w], b1h = Bh[w + 4], b0l = Bl[w], b1l = Bl[w + 4];
-      const uint32_t a0h = ar_h[q & 3][0], a2h = ar_h[q & 3][1], a0l = ar_l[q & 3][0], a2l = ar_l[q & 3][1];
+      const uint32_t a0h = ar_h[q][0], a2h = ar_h[q][1], a0l = ar_l[q][0], a2l = ar_l[q][1];
       mma_16816(d0, a0h, a1h, a2h, a3h, b0h, b1h);
-      mma_16816(d0, a0h, a1h, a2h, a3h, b0l, b1l);
-      mma_16816(d0, a0l, a1l, a2l, a3l, b0h, b1h);
       mma_16816(d1, a0h, a1h, a2h, a3h, ring_h[q][0], ring_h[q][1]);
-      mma_16816(d1, a0h, a1h, a2h, a3h, ring_l[q][0], ring_l[q][1]);
-      mma_16816(d1, a0l, a1l, a2l, a3l, ring_h[q][0], ring_h[q][1]);
+      mma_16816(d0x, a0h, a1h, a2h, a3h, b0l, b1l);
+      mma_16816(d1x, a0h, a1h, a2h, a3h, ring_l[q][0], ring_l[q][1]);
+      mma_16816(d0x, a0l, a1l, a2l, a3l, b0h, b1h);
+      mma_16816(d1x, a0l, a1l, a2l, a3l, ring_h[q][0], ring_h[q][1]);
       ring_h[q][0] = b0h; ring_h[q][1] = b1h; ring_l[q][0] = b0l; ring_l[q][1] = b1l;
-      ar_h[q & 3][0] = a1h; ar_h[q & 3][1] = a3h; ar_l[q & 3][0] = a1l; ar_l[q & 3][1] = a3l;
+      ar_h[q][0] = a1h; ar_h[q][1] = a3h; ar_l[q][0] = a1l; ar_l[q][1] = a3l;
     }
   }
-  // d0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  d1: c0,c1 = base+128, base+129.
-  val[0] = d0[0]; val[1] = d0[1]; val[2] = d0[2]; val[3] = d0[3]; val[4] = d1[0]; val[5] = d1[1];
-  const float r0 = __shfl_sync(0xffffffffu, d0[0], 0);   // lag 0 lives in lane 0
+  // tile 0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  tile 1: c2,c3 = base+128, base+129.
+  val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];
+  val[4] = d1[2] + d1x[2]; val[5] = d1[3] + d1x[3];
+  const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
   if (r0 != 0.0f) {
     const float inv = __fdiv_rn(1.0f, r0);
 #pragma unroll
