@@ -63,6 +63,9 @@ typedef enum nsf_status {
 #define NSF_DEBUG_FMA_AUTOCORR 0x200u /* validation aid: autocorrelation with fp32 CUDA-core FMAs instead
                                          of the mma.sync Hankel kernel (never selected automatically) */
 
+#define NSF_DEBUG_UNFUSED_MEL 0x400u   /* validation aid: separate tcgen05 GEMM (power to HBM) + mel/dB kernel
+                                         instead of the fused persistent kernel */
+
 /* collect flags */
 #define NSF_COLLECT_FAST 0x1u  /* include_fast      (dataset/data_processing.py:152-158) */
 #define NSF_COLLECT_SLOW 0x2u  /* include_slow      (dataset/data_processing.py:161-167) */

@@ -19,6 +19,7 @@ PEAK_NORMALIZE, NO_AUTOCORR, SMOOTH, NO_CMVN, NO_DELTAS, AC_DELTAS, NO_REDUCE = 
 NO_MFCC = 0x080
 DEBUG_SIMT_DFT = 0x100
 DEBUG_FMA_AUTOCORR = 0x200
+DEBUG_UNFUSED_MEL = 0x400
 COLLECT_FAST, COLLECT_SLOW, COLLECT_BLEND = 0x1, 0x2, 0x4
 F32, F64 = 0, 1
 TABLE_MEL, TABLE_DCT, TABLE_HANN_SYM, TABLE_HANN_PER = 0, 1, 2, 3

@@ -208,6 +208,30 @@ nsf_status upload_tables(nsf_ctx* ctx) {
   for (int k = 0; k < p.n_mfcc; ++k)
     for (int m = 0; m < p.n_mels; ++m) dct_t[static_cast<size_t>(m) * 32 + k] = p.dct[static_cast<size_t>(k) * p.n_mels + m];
   const size_t off_dct = put(dct_t.data(), dct_t.size() * sizeof(float));
+  // column -> (first filter, two weights) table for the fused mel epilogue of the tcgen05 kernel
+  size_t off_melcol[2] = {0, 0};
+  int mel_col_ok = 1;
+  for (int c = 0; c < p.chains; ++c) {
+    const int ncols = (p.chain[c].np + 127) / 128 * 128;
+    std::vector<float> tab(static_cast<size_t>(ncols) * 4, 0.0f);
+    for (int idx = 0; idx < p.chain[c].nbins; ++idx) {
+      const int k = p.chain[c].bin[idx];
+      int m0 = -1, count = 0, last = -1;
+      for (int m = 0; m < p.n_mels; ++m)
+        if (p.mel_dense[static_cast<size_t>(m) * p.bins + k] != 0.0f) { if (m0 < 0) m0 = m; last = m; ++count; }
+      if (count > 2 || (count == 2 && last != m0 + 1)) mel_col_ok = 0;
+      if (m0 < 0) m0 = 0;
+      if (m0 > p.n_mels - 2) m0 = p.n_mels - 2 < 0 ? 0 : p.n_mels - 2;
+      int32_t bits = m0;
+      float fb;
+      std::memcpy(&fb, &bits, 4);
+      tab[4 * static_cast<size_t>(idx) + 0] = fb;
+      tab[4 * static_cast<size_t>(idx) + 1] = p.mel_dense[static_cast<size_t>(m0) * p.bins + k];
+      tab[4 * static_cast<size_t>(idx) + 2] = m0 + 1 < p.n_mels ? p.mel_dense[static_cast<size_t>(m0 + 1) * p.bins + k] : 0.0f;
+    }
+    off_melcol[c] = put(tab.data(), tab.size() * sizeof(float));
+  }
+  if (p.n_mels < 2) mel_col_ok = 0;
   StftTcHostBlob tcblob;
   build_stft_tc_blob(p, &tcblob);
   const size_t off_tc = put(tcblob.bytes.data(), tcblob.bytes.size());
@@ -240,6 +264,9 @@ nsf_status upload_tables(nsf_ctx* ctx) {
   t.mel_ptr = reinterpret_cast<const int32_t*>(base + off_mp);
   t.mel_w = reinterpret_cast<const float*>(base + off_mw);
   t.dct_t = reinterpret_cast<const float*>(base + off_dct);
+  t.mel_col[0] = reinterpret_cast<const float4*>(base + off_melcol[0]);
+  t.mel_col[1] = p.chains > 1 ? reinterpret_cast<const float4*>(base + off_melcol[1]) : nullptr;
+  t.mel_col_ok = mel_col_ok;
   return bind_stft_tc_tables(p, tcblob, base + off_tc, &ctx->tc);
 }
 
@@ -501,6 +528,7 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
   if (!do_mfcc && (flags & NSF_NO_AUTOCORR)) { set_error("NSF_NO_MFCC | NSF_NO_AUTOCORR leaves nothing to compute"); return NSF_ERR_BAD_ARG; }
 
   // stages 1-3: STFT power -> mel -> dB (+ per-clip max)
+  bool fused_mel = false;
   if (!do_mfcc) {
     // autocorrelation block only
   } else if (flags & NSF_DEBUG_SIMT_DFT) {
@@ -512,10 +540,16 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
     timer.mark(1);
     NSF_LAUNCH(launch_stft_tc_fold(s, ctx->tc, t, b, y, L.tc_a));
     timer.mark(2);
-    NSF_LAUNCH(launch_stft_tc_gemm(s, ctx->tc, t, b, L.tc_a, L.power));
+    if (t.mel_col_ok && !(flags & NSF_DEBUG_UNFUSED_MEL)) {
+      // product path: STFT GEMM with the power -> mel -> dB epilogue fused (no power round trip)
+      NSF_LAUNCH(launch_stft_tc_mel(s, ctx->tc, t, b, L.tc_a, L.db, L.dbmax_key));
+      fused_mel = true;
+    } else {
+      NSF_LAUNCH(launch_stft_tc_gemm(s, ctx->tc, t, b, L.tc_a, L.power));
+    }
   }
   timer.mark(3);
-  if (do_mfcc) NSF_LAUNCH(launch_mel_db(s, t, b, L.power, L.db, L.dbmax_key));
+  if (do_mfcc && !fused_mel) NSF_LAUNCH(launch_mel_db(s, t, b, L.power, L.db, L.dbmax_key));
   // stage 4: floor + DCT + CMVN statistics
   timer.mark(4);
   if (do_mfcc) {

@@ -28,5 +28,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// order-preserving float -> uint32 key (so atomicMax works for negative dB values); 0 = "-inf"
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 }  // namespace nsf
 #endif  // NSF_DEVICE_UTILS_CUH_

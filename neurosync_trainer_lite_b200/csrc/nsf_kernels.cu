@@ -23,15 +23,6 @@ namespace {
 
 constexpr int kSmCount = 148;
 
-// order-preserving float -> uint32 key (so atomicMax works for negative dB values); 0 = "-inf"
-__device__ __forceinline__ uint32_t float_key(float f) {
-  const uint32_t b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float key_float(uint32_t k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
 template <typename T> __device__ __forceinline__ float decode_pcm(T v);
 template <> __device__ __forceinline__ float decode_pcm<float>(float v) { return v; }
 template <> __device__ __forceinline__ float decode_pcm<int16_t>(int16_t v) {

@@ -52,6 +52,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -446,6 +449,202 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_tc_stft_mel: PERSISTENT fused kernel, one CTA per SM looping over tiles of 128 hop-frames.
+// For every tile it runs the (chain, 128-bin) sub-tiles back to back; TMEM holds two 256-column
+// accumulator buffers (Re | Im), so the tensor pipe works on sub-tile s+1 while the epilogue warps
+// drain sub-tile s.  The epilogue never writes the power spectrum: it squares, undoes the scaling and
+// accumulates the triangular mel filters straight into a [128 frames][n_mels] fp32 tile in shared
+// memory (each thread owns one frame row; a bin feeds at most two adjacent filters), and after the
+// last sub-tile writes 10 log10(max(1e-10, mel)) plus the per-clip dB maximum.
+//   warp 0 : TMA producer      warp 1 : TMEM alloc + tcgen05.mma issuer      warps 2-5 : epilogue
+// ------------------------------------------------------------------------------------------------
+constexpr int kFStages = 2;
+constexpr int kMelPitch = 129;                       // floats per frame row of the mel tile
+constexpr size_t kFusedSmem = 1024 + static_cast<size_t>(kFStages) * kStageBytes +
+                              static_cast<size_t>(BM) * kMelPitch * sizeof(float) + 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              DeviceTables t, BatchView b, int64_t plane_rows, int kp, int np_ld,
+              const int32_t* __restrict__ row_exp, float* __restrict__ db, uint32_t* __restrict__ dbmax_key) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* mel_acc = reinterpret_cast<float*>(smem + kFStages * kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kFStages * kStageBytes + BM * kMelPitch * sizeof(float));
+  uint64_t* empty_bar = full_bar + kFStages;
+  uint64_t* tmem_full = empty_bar + kFStages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (kp + BK - 1) / BK;
+  const int ntile[2] = {(t.np[0] + BN - 1) / BN, t.chains > 1 ? (t.np[1] + BN - 1) / BN : 0};
+  const int n_sub = ntile[0] + ntile[1];
+  const int64_t n_tiles = (b.total_frames + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int i = 0; i < kFStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < BM * kMelPitch; i += blockDim.x) mel_acc[i] = 0.0f;
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t g0 = tile * BM;
+        for (int sub = 0; sub < n_sub; ++sub) {
+          const int chain = sub < ntile[0] ? 0 : 1;
+          const int n0 = (chain == 0 ? sub : sub - ntile[0]) * BN;
+          for (int part = 0; part < 2; ++part) {
+            const int cp = chain * 2 + part;
+            const int64_t a_row = static_cast<int64_t>(cp * 2) * plane_rows + g0;
+            const int b_row = (cp * 2) * np_ld + n0;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+              const int stage = it % kFStages;
+              mbar_wait(empty_bar + stage, ((it / kFStages) & 1) ^ 1);
+              uint8_t* st = tiles + stage * kStageBytes;
+              mbar_expect_tx(full_bar + stage, kStageBytes);
+              const int kx = kb * BK;
+              tma_load_2d(st + 0 * kTileBytes, &map_a, full_bar + stage, kx, static_cast<int32_t>(a_row));
+              tma_load_2d(st + 1 * kTileBytes, &map_a, full_bar + stage, kx, static_cast<int32_t>(a_row + plane_rows));
+              tma_load_2d(st + 2 * kTileBytes, &map_b, full_bar + stage, kx, b_row);
+              tma_load_2d(st + 3 * kTileBytes, &map_b, full_bar + stage, kx, b_row + np_ld);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      uint32_t it = 0, acc_it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
+          const uint32_t buf = acc_it & 1u;
+          mbar_wait(tmem_empty + buf, ((acc_it >> 1) & 1u) ^ 1u);     // epilogue has drained this buffer
+          tcgen05_fence_after();
+          for (int part = 0; part < 2; ++part) {
+            const uint32_t d_tmem = tmem_base + buf * 256u + static_cast<uint32_t>(part * BN);
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+              const int stage = it % kFStages;
+              mbar_wait(full_bar + stage, (it / kFStages) & 1);
+              tcgen05_fence_after();
+              const uint32_t st = smem_u32(tiles + stage * kStageBytes);
+              const int ksteps = min(BK / UK, (kp - kb * BK + UK - 1) / UK);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t koff = static_cast<uint32_t>(k * UK * 2);
+                const uint64_t a_hi = make_smem_desc(st + 0 * kTileBytes + koff);
+                const uint64_t a_lo = make_smem_desc(st + 1 * kTileBytes + koff);
+                const uint64_t b_hi = make_smem_desc(st + 2 * kTileBytes + koff);
+                const uint64_t b_lo = make_smem_desc(st + 3 * kTileBytes + koff);
+                umma_f16(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+                umma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+              }
+              umma_commit(empty_bar + stage);
+            }
+          }
+          umma_commit(tmem_full + buf);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;          // frame row of the tile owned by this thread
+    float* my_acc = mel_acc + row * kMelPitch;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t acc_it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t g = tile * BM + row;
+      const bool row_ok = g < b.total_frames;
+      const float sc = row_ok ? ldexpf(1.0f, -(__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+      for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
+        const int chain = sub < ntile[0] ? 0 : 1;
+        const int n0 = (chain == 0 ? sub : sub - ntile[0]) * BN;
+        const float4* tab = t.mel_col[chain] + n0;
+        const uint32_t buf = acc_it & 1u;
+        mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
+        tcgen05_fence_after();
+        // running partial sums for the current filter pair (m0, m0 + 1); flushed when m0 changes
+        int cur_m = -1;
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 1
+        for (int j = 0; j < BN; j += 32) {
+          float re[32], im[32];
+          tmem_ld_32x32(lane_addr + buf * 256u + static_cast<uint32_t>(j), re);
+          tmem_ld_32x32(lane_addr + buf * 256u + static_cast<uint32_t>(BN + j), im);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const float4 e = __ldg(tab + j + q);          // warp-uniform address: one broadcast load
+            const int m0 = __float_as_int(e.x);
+            const float a = re[q] * sc, c = im[q] * sc;
+            const float pw = fmaf(a, a, c * c);
+            if (m0 != cur_m) {                             // uniform branch
+              if (cur_m >= 0) { my_acc[cur_m] += s0; my_acc[cur_m + 1] += s1; }
+              cur_m = m0; s0 = 0.0f; s1 = 0.0f;
+            }
+            s0 = fmaf(pw, e.y, s0);
+            s1 = fmaf(pw, e.z, s1);
+          }
+        }
+        if (cur_m >= 0) { my_acc[cur_m] += s0; my_acc[cur_m + 1] += s1; }
+        // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld_32x32)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+      // tile finished: dB, per-clip maximum, coalesced store, reset of the accumulator rows
+      float vmax = -INFINITY;
+      for (int m = 0; m < t.n_mels; ++m) {
+        const float v = 10.0f * log10f(fmaxf(1e-10f, my_acc[m]));
+        my_acc[m] = v;
+        vmax = fmaxf(vmax, v);
+      }
+      __syncwarp();
+      const int64_t gw = tile * BM + quarter * 32;          // first frame of this warp's 32 rows
+      for (int r = 0; r < 32; ++r) {
+        if (gw + r < b.total_frames) {
+          const float* src = mel_acc + (quarter * 32 + r) * kMelPitch;
+          for (int m = lane; m < t.n_mels; m += 32) db[(gw + r) * t.n_mels + m] = src[m];
+        }
+      }
+      __syncwarp();
+      for (int m = 0; m < kMelPitch; ++m) my_acc[m] = 0.0f;
+      {
+        const int clip = row_ok ? find_segment(b.frame_off, b.n_clips, g) : -1;
+        const uint32_t key = row_ok ? float_key(vmax) : 0u;
+        const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
+        const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
+        if (uniform) {
+          uint32_t k = key;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, o));
+          if (lane == 0 && first_clip >= 0) atomicMax(dbmax_key + first_clip, k);
+        } else if (clip >= 0) {
+          atomicMax(dbmax_key + clip, key);
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -561,6 +760,23 @@ int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
   if (grid > 148 * per_sm) grid = 148 * per_sm;
   if (grid < 1) grid = 1;
   k_tc_fold<<<static_cast<int>(grid), kFoldWarps * 32, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp, buf_floats);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTables& t, const BatchView& b,
+                       void* operands, float* db, uint32_t* dbmax_key) {
+  if (!tc.ready || !t.mel_col_ok || t.n_mels > 128) return -1;
+  const OperandView v = view_operands(tc, b.total_frames, operands);
+  CUtensorMap map_a;
+  if (!encode_map(&map_a, v.planes, static_cast<uint64_t>(tc.chains) * 4 * v.rows, tc.kp, BM)) return -1;
+  if (cudaFuncSetAttribute(k_tc_stft_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)) !=
+      cudaSuccess)
+    return -1;
+  int64_t grid = v.rows / BM;
+  if (grid > 148) grid = 148;
+  if (grid < 1) grid = 1;
+  k_tc_stft_mel<<<static_cast<unsigned>(grid), kThreads, kFusedSmem, s>>>(map_a, tc.map_b, t, b, v.rows, tc.kp, tc.np_ld,
+                                                                            v.row_exp, db, dbmax_key);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

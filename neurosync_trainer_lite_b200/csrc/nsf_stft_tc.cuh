@@ -37,6 +37,9 @@ nsf_status bind_stft_tc_tables(const Plan& p, const StftTcHostBlob& blob, const 
 size_t stft_tc_operand_bytes(const Plan& p, int64_t frames);
 int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTables& t,
                         const BatchView& b, const float* y, void* operands);
+// persistent fused kernel: STFT GEMM -> |.|^2 -> mel -> dB (+ per-clip dB max); writes db [T][n_mels]
+int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTables& t, const BatchView& b,
+                       void* operands, float* db, uint32_t* dbmax_key);
 int launch_stft_tc_gemm(cudaStream_t s, const StftTcTables& tc, const DeviceTables& t,
                         const BatchView& b, void* operands, float* power);
 

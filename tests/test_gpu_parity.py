@@ -91,6 +91,27 @@ def test_simt_validation_path_agrees(golden, engine, nv):
     assert np.abs(a[:, :69] - b[:, :69]).max() <= TOL_MFCC
 
 
+def test_fused_mel_epilogue_agrees_with_unfused_path(golden, engine, nv):
+    """Persistent fused tcgen05 kernel (STFT -> power -> mel -> dB in the epilogue) vs the separate
+    GEMM + mel kernels, on even / odd frame lengths, ragged multi-clip batches and tail tiles."""
+    for name in ("gated_1s5_88k", "voiced_2s_16k", "voiced_1s_44k1_oddF", "noise_0s7_88k"):
+        g = golden(name)
+        eng = engine.get_engine(int(g["sr"]), int(g["F"]), int(g["H"]))
+        y = g["y"]
+        a = eng.extract_host(y, [0, len(y)], nv.NO_AUTOCORR)
+        b = eng.extract_host(y, [0, len(y)], nv.NO_AUTOCORR | nv.DEBUG_UNFUSED_MEL)
+        assert np.abs(a - g["features"][:, :69]).max() <= TOL_MFCC
+        assert np.abs(b - g["features"][:, :69]).max() <= TOL_MFCC
+        assert np.abs(a - b).max() <= 2e-4
+    eng = engine.get_engine(88200, 1470, 735)
+    clips = [synth.synth_clip(s, 88200, seed=i, kind=k) for i, (s, k) in
+             enumerate([(0.9, "voiced"), (2.3, "gated"), (0.31, "noise"), (4.1, "voiced")])]
+    packed, off = engine.pack_clips(clips)
+    a = eng.extract_host(packed, off, nv.NO_AUTOCORR)
+    b = eng.extract_host(packed, off, nv.NO_AUTOCORR | nv.DEBUG_UNFUSED_MEL)
+    assert np.isfinite(a).all() and np.abs(a - b).max() <= 2e-4
+
+
 def test_fma_autocorr_validation_path_agrees(golden, engine, nv):
     """The fp32-FMA autocorrelation (debug flag) and the mma.sync Hankel kernel agree with each other
     and with the reference, including odd frame lengths and the 16 kHz geometry."""
