@@ -29,7 +29,6 @@ namespace nsf {
 namespace {
 
 constexpr int kSmCount = 148;
-constexpr int kAmWarps = 8;
 constexpr int kFrontMargin = 16;   // halfs of zeros before X(0)  (B reads back to X(-7))
 constexpr int kBackMargin = 128;   // halfs of zeros after the last K-block (A reads up to +73)
 constexpr int kVals = 6;           // lags per thread that can be <= 191
@@ -63,9 +62,8 @@ __device__ __forceinline__ int lag_of(int lane, int v) {
 // round trip to memory (2 kIters independent loads per lane in flight) and both passes over it
 // (mean / max, then window + scale + split) run out of registers.
 template <int kIters>
-__device__ __forceinline__ void autocorr_frame_mma(const DeviceTables& t, const float* __restrict__ y,
-                                                   int64_t base, int64_t len, int64_t tf, __half* copies,
-                                                   const AmGeom& geo, int lane, float (&val)[kVals]) {
+__device__ __forceinline__ void am_fill(const DeviceTables& t, const float* __restrict__ y, int64_t base,
+                                        int64_t len, int64_t tf, __half* copies, const AmGeom& geo, int lane) {
   const int F = t.F;
   const int64_t first = tf * t.H - t.pad;
   const bool interior = first >= 0 && first + F <= len;
@@ -109,14 +107,13 @@ __device__ __forceinline__ void autocorr_frame_mma(const DeviceTables& t, const 
     e2 = max(-100, min(100, e2));
   }
   const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
-  // pass 2: window, scale, split, store both copies as half2 pairs.  Pair e holds X(2e), X(2e+1);
-  // the shifted copy needs (X(2e-1), X(2e)): X(2e-1) comes from the previous lane / iteration.
-  __half2* e_hi = reinterpret_cast<__half2*>(copies) + kFrontMargin / 2;
-  __half2* e_lo = e_hi + geo.len / 2;
-  __half2* o_hi = e_lo + geo.len / 2;
-  __half2* o_lo = o_hi + geo.len / 2;
+  // pass 2a: window, scale, split; pair e = (X(2e), X(2e+1)) goes to the E copies as one half2 each.
+  // Iterations are independent (no cross-lane traffic), so the compiler can interleave them freely.
+  uint32_t* e_hi = reinterpret_cast<uint32_t*>(copies) + kFrontMargin / 2;
+  uint32_t* e_lo = e_hi + geo.len / 2;
+  uint32_t* o_hi = e_lo + geo.len / 2;
+  uint32_t* o_lo = o_hi + geo.len / 2;
   const int n_pairs = F / 2 + 1;               // one pair beyond the frame flushes the shifted copy
-  float carry_hi = 0.0f, carry_lo = 0.0f;      // X(2e-1) for lane 0 (hi, lo parts as floats)
 #pragma unroll
   for (int i = 0; i < kIters; ++i) {
     const int e = lane + 32 * i;
@@ -131,22 +128,27 @@ __device__ __forceinline__ void autocorr_frame_mma(const DeviceTables& t, const 
     const __half2 hi = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(hi);
     const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-    const float2 lf = __half22float2(lo);
-    float p_hi = __shfl_up_sync(0xffffffffu, hf.y, 1), p_lo = __shfl_up_sync(0xffffffffu, lf.y, 1);
-    if (lane == 0) { p_hi = carry_hi; p_lo = carry_lo; }
-    carry_hi = __shfl_sync(0xffffffffu, hf.y, 31);
-    carry_lo = __shfl_sync(0xffffffffu, lf.y, 31);
     if (e < n_pairs) {
-      e_hi[e] = hi;
-      e_lo[e] = lo;
-      // O half2 index e - 1 holds (O[2e-2], O[2e-1]) = (X(2e-1), X(2e)); for e == 0 that is the last
-      // half2 of the front margin: (X(-1) = 0, X(0))
-      o_hi[e - 1] = __floats2half2_rn(p_hi, hf.x);
-      o_lo[e - 1] = __floats2half2_rn(p_lo, lf.x);
+      e_hi[e] = *reinterpret_cast<const uint32_t*>(&hi);
+      e_lo[e] = *reinterpret_cast<const uint32_t*>(&lo);
     }
   }
   __syncwarp();
+  // pass 2b: the one-sample shifted copies straight from the E words: O word e-1 = (X(2e-1), X(2e))
+  // = high half of E word e-1 | low half of E word e  (E word -1 is the zero margin)
+#pragma unroll
+  for (int i = 0; i < kIters; ++i) {
+    const int e = lane + 32 * i;
+    if (e < n_pairs) {
+      o_hi[e - 1] = __funnelshift_r(e_hi[e - 1], e_hi[e], 16);
+      o_lo[e - 1] = __funnelshift_r(e_lo[e - 1], e_lo[e], 16);
+    }
+  }
+  __syncwarp();
+}
 
+// The MMA half: normalised lags of the frame currently held in `copies` into val[0..5] (see lag_of).
+__device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
   // main loop: 6 MMAs per K-block, all fragment loads conflict-free 32-bit shared reads
   const int g = lane >> 2, tq = lane & 3;
   const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
@@ -215,20 +217,59 @@ __device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane
   return __all_sync(0xffffffffu, small);
 }
 
+// ---- mbarrier helpers (producer / consumer hand-off of the frame buffers) -------------------------
+__device__ __forceinline__ uint32_t am_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void am_bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(am_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void am_bar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(am_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void am_bar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(am_smem_u32(bar)), "r"(parity) : "memory");
+    if (spins > (1u << 26)) __trap();      // a hand-off bug traps instead of hanging the GPU
+  }
+}
+
+// Warp-specialised kernel.  A block is kAmPairs (consumer, producer) warp pairs; each pair owns two
+// frame buffers.  The producer warp fetches, windows, scales and splits frame after frame; the
+// consumer warp runs nothing but the MMA loop (plus the cheap normalise / pair-mean / store), so the
+// tensor pipe is fed continuously while memory latency and the fp32->fp16 conversion hide behind it.
+constexpr int kAmPairs = 4;
+
 template <int kIters>
-__global__ void __launch_bounds__(kAmWarps * 32, 2) k_autocorr_mma(DeviceTables t, BatchView b,
+__global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables t, BatchView b,
                                                                    const float* __restrict__ y, bool reduce,
                                                                    float* __restrict__ out, int64_t out_ld,
                                                                    int col0) {
   extern __shared__ __align__(16) __half s_am[];
+  __shared__ uint64_t s_bar[kAmPairs][4];          // per pair: full[2], empty[2]
   const AmGeom geo = am_geom(t.F);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __half* copies = s_am + static_cast<size_t>(warp) * 4 * geo.len;
-  // zero once: the margins are never written again, the frame region is rewritten per frame
-  for (int i = lane; i < 4 * geo.len / 2; i += 32) reinterpret_cast<uint32_t*>(copies)[i] = 0u;
-  __syncwarp();
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kAmWarps + warp; r < b.total_rows;
-       r += static_cast<int64_t>(gridDim.x) * kAmWarps) {
+  const int pair = warp % kAmPairs;
+  const bool producer = warp >= kAmPairs;
+  __half* bufs = s_am + static_cast<size_t>(pair) * 2 * 4 * geo.len;      // two buffers of 4 copies
+  uint64_t* full = s_bar[pair];
+  uint64_t* empty = s_bar[pair] + 2;
+  if (!producer) {
+    // zero once: the margins are never written again, the frame region is rewritten per frame
+    for (int i = lane; i < 2 * 4 * geo.len / 2; i += 32) reinterpret_cast<uint32_t*>(bufs)[i] = 0u;
+    if (lane == 0) {
+      am_bar_init(full + 0, 1); am_bar_init(full + 1, 1);
+      am_bar_init(empty + 0, 1); am_bar_init(empty + 1, 1);
+    }
+  }
+  __syncthreads();
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kAmPairs + pair;
+  const int64_t row_stride = static_cast<int64_t>(gridDim.x) * kAmPairs;
+  uint32_t it = 0;                                  // frames handed over so far (buffer = it & 1)
+  for (int64_t r = row0; r < b.total_rows; r += row_stride) {
     const int clip = find_segment(b.row_off, b.n_clips, r);
     const int64_t base = __ldg(b.clip_off + clip);
     const int64_t len = __ldg(b.clip_off + clip + 1) - base;
@@ -236,31 +277,42 @@ __global__ void __launch_bounds__(kAmWarps * 32, 2) k_autocorr_mma(DeviceTables 
     const int64_t lr = r - __ldg(b.row_off + clip);
     const int64_t tf0 = reduce ? 2 * lr : lr;
     const int n_frames = (reduce && tf0 + 1 < T) ? 2 : 1;   // odd T: the last row passes through
-    float acc[kVals];
-#pragma unroll
-    for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
-    for (int f = 0; f < n_frames; ++f) {
-      const int64_t tf = tf0 + f;
-      int64_t use = tf;
-      float val[kVals];
-      for (int attempt = 0; attempt < 2; ++attempt) {     // one inlined copy of the frame routine
-        autocorr_frame_mma<kIters>(t, y, base, len, use, copies, geo, lane, val);
-        // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2)
-        if (attempt == 0 && T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags)) {
-          use = tf == 0 ? 1 : T - 2;
-          continue;
-        }
-        break;
+    if (producer) {
+      for (int f = 0; f < n_frames; ++f, ++it) {
+        const uint32_t buf = it & 1u;
+        am_bar_wait(empty + buf, ((it >> 1) & 1u) ^ 1u);
+        am_fill<kIters>(t, y, base, len, tf0 + f, bufs + buf * 4 * geo.len, geo, lane);   // ends with __syncwarp
+        if (lane == 0) am_bar_arrive(full + buf);
       }
+    } else {
+      float acc[kVals];
 #pragma unroll
-      for (int v = 0; v < kVals; ++v) acc[v] += val[v];
-    }
-    const float wgt = n_frames == 2 ? 0.5f : 1.0f;
-    float* o = out + r * out_ld + col0;
+      for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
+      for (int f = 0; f < n_frames; ++f, ++it) {
+        const uint32_t buf = it & 1u;
+        __half* copies = bufs + buf * 4 * geo.len;
+        const int64_t tf = tf0 + f;
+        float val[kVals];
+        am_bar_wait(full + buf, (it >> 1) & 1u);
+        am_mma(copies, geo, lane, val);
+        // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
+        // rare, so the consumer refills the buffer it still owns itself
+        if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags)) {
+          am_fill<kIters>(t, y, base, len, tf == 0 ? 1 : T - 2, copies, geo, lane);
+          am_mma(copies, geo, lane, val);
+        }
+        __syncwarp();
+        if (lane == 0) am_bar_arrive(empty + buf);
 #pragma unroll
-    for (int v = 0; v < kVals; ++v) {
-      const int lag = lag_of(lane, v);
-      if (lag >= 1 && lag <= t.n_lags) o[lag - 1] = acc[v] * wgt;
+        for (int v = 0; v < kVals; ++v) acc[v] += val[v];
+      }
+      const float wgt = n_frames == 2 ? 0.5f : 1.0f;
+      float* o = out + r * out_ld + col0;
+#pragma unroll
+      for (int v = 0; v < kVals; ++v) {
+        const int lag = lag_of(lane, v);
+        if (lag >= 1 && lag <= t.n_lags) o[lag - 1] = acc[v] * wgt;
+      }
     }
   }
 }
@@ -270,18 +322,18 @@ __global__ void __launch_bounds__(kAmWarps * 32, 2) k_autocorr_mma(DeviceTables 
 int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
                         bool reduce, float* out, int64_t out_ld, int col0) {
   const AmGeom geo = am_geom(t.F);
-  const size_t smem = static_cast<size_t>(kAmWarps) * 4 * geo.len * sizeof(__half);
+  const size_t smem = static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len * sizeof(__half);
   if (smem > 220 * 1024 || t.n_lags > 191) return -1;
   int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
-  int64_t grid = (b.total_rows + kAmWarps - 1) / kAmWarps;
+  int64_t grid = (b.total_rows + kAmPairs - 1) / kAmPairs;
   if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
   if (grid < 1) grid = 1;
   const int iters = (t.F / 2 + 1 + 31) / 32;      // register-staging iterations the frame needs
   auto go = [&](auto kernel) {
     // per call: all instantiations share this lambda (same function-pointer type), so no static flag
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
-    kernel<<<static_cast<int>(grid), kAmWarps * 32, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+    kernel<<<static_cast<int>(grid), kAmPairs * 64, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   };
   if (iters <= 6) return go(k_autocorr_mma<6>);      // F <= 382   (16 kHz: 266, 22.05 kHz: 367)

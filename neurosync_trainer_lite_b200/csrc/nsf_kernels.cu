@@ -282,57 +282,115 @@ __global__ void __launch_bounds__(kMelWarps * 32) k_mel_db(DeviceTables t, Batch
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: top_db floor + DCT-II (first n_mfcc) + per-clip sum.  One warp per run of frames; lane = k.
+// K2: top_db floor + DCT-II (first n_mfcc) + per-clip moments.  LANES ARE FRAMES: a warp transposes
+// a tile of 32 dB rows into shared memory (coalesced 128-byte reads, pitch 33), then every lane runs
+// the DCT of its own frame - per mel one conflict-free shared load of the dB value and KP/4 broadcast
+// 128-bit loads of the coefficient row feed KP FFMAs.  MFCC rows leave through shared memory as one
+// contiguous, fully coalesced block; sum x and sum x^2 are warp-reduced per tile and added in f64.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDctWarps = 8;
-constexpr int kDctRun = 16;  // consecutive frames per warp -> 16x fewer atomics
+constexpr int kDctWarps = 4;
+constexpr int kDctPitch = 33;
+
+template <int KP>
 __global__ void __launch_bounds__(kDctWarps * 32) k_dct_sum(DeviceTables t, BatchView b,
                                                             const float* __restrict__ db,
                                                             const uint32_t* __restrict__ dbmax_key,
                                                             float* __restrict__ mfcc_raw,
                                                             double* __restrict__ sum,
                                                             double* __restrict__ sumsq) {
-  __shared__ float s_dct[128 * 32];           // [m][k] (k padded to 32): conflict-free per lane
-  __shared__ float s_v[kDctWarps][128];
-  for (int i = threadIdx.x; i < t.n_mels * 32; i += blockDim.x) s_dct[i] = __ldg(t.dct_t + i);
-  __syncthreads();
+  extern __shared__ __align__(16) float s_dctk[];   // [n_mels][KP] coefficients, then kDctWarps x [n_mels][33]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_runs = (b.total_frames + kDctRun - 1) / kDctRun;
-  for (int64_t run = static_cast<int64_t>(blockIdx.x) * kDctWarps + warp; run < n_runs;
-       run += static_cast<int64_t>(gridDim.x) * kDctWarps) {
-    const int64_t g_begin = run * kDctRun, g_end = min(g_begin + kDctRun, b.total_frames);
-    int clip = find_segment(b.frame_off, b.n_clips, g_begin);
-    int64_t clip_end = __ldg(b.frame_off + clip + 1);
-    float floor_db = key_float(__ldg(dbmax_key + clip)) - 80.0f;
-    double run_sum = 0.0, run_sq = 0.0;
-    for (int64_t g = g_begin; g < g_end; ++g) {
-      if (g >= clip_end) {
-        if (lane < t.n_mfcc) {
-          atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sum);
-          atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sq);
+  float* s_c = s_dctk;
+  float* s_t = s_dctk + t.n_mels * KP + static_cast<size_t>(warp) * t.n_mels * kDctPitch;
+  for (int i = threadIdx.x; i < t.n_mels * KP; i += blockDim.x) {
+    const int m = i / KP, k = i - m * KP;
+    s_c[i] = __ldg(t.dct_t + m * 32 + k);          // dct_t is [m][32], zero padded beyond n_mfcc
+  }
+  __syncthreads();
+  const int64_t n_tiles = (b.total_frames + 31) / 32;
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * kDctWarps + warp; tile < n_tiles;
+       tile += static_cast<int64_t>(gridDim.x) * kDctWarps) {
+    const int64_t g0 = tile * 32;
+    const int nf = static_cast<int>(min(static_cast<int64_t>(32), b.total_frames - g0));
+    const bool valid = lane < nf;
+    const int clip = valid ? find_segment(b.frame_off, b.n_clips, g0 + lane) : -1;
+    const float floor_db = valid ? key_float(__ldg(dbmax_key + clip)) - 80.0f : 0.0f;
+    // transposing load, 8 rows (up to 32 independent 128-byte requests per warp) at a time
+    for (int f0 = 0; f0 < 32; f0 += 8) {
+      float v[8][4];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = lane + 32 * j;
+          v[r][j] = (f0 + r < nf && m < t.n_mels) ? __ldg(db + (g0 + f0 + r) * t.n_mels + m) : 0.0f;
         }
-        run_sum = 0.0; run_sq = 0.0;
-        while (g >= clip_end) { ++clip; clip_end = __ldg(b.frame_off + clip + 1); }
-        floor_db = key_float(__ldg(dbmax_key + clip)) - 80.0f;
-      }
-      for (int m = lane; m < t.n_mels; m += 32)
-        s_v[warp][m] = fmaxf(__ldg(db + g * t.n_mels + m), floor_db);
-      __syncwarp();
-      float acc = 0.0f;
-#pragma unroll 8
-      for (int m = 0; m < t.n_mels; ++m) acc = fmaf(s_dct[m * 32 + lane], s_v[warp][m], acc);
-      if (lane < t.n_mfcc) {
-        mfcc_raw[g * t.n_mfcc + lane] = acc;
-        const double ad = static_cast<double>(acc);
-        run_sum += ad;
-        run_sq = fma(ad, ad, run_sq);
-      }
-      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = lane + 32 * j;
+          if (m < t.n_mels) s_t[m * kDctPitch + f0 + r] = v[r][j];
+        }
     }
-    if (lane < t.n_mfcc) {
-      atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sum);
-      atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + lane, run_sq);
+    __syncwarp();
+    float acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.0f;
+#pragma unroll 2
+    for (int m = 0; m < t.n_mels; ++m) {
+      const float x = fmaxf(s_t[m * kDctPitch + lane], floor_db);
+      const float4* c4 = reinterpret_cast<const float4*>(s_c + m * KP);
+#pragma unroll
+      for (int k4 = 0; k4 < KP / 4; ++k4) {
+        const float4 c = c4[k4];
+        acc[4 * k4 + 0] = fmaf(c.x, x, acc[4 * k4 + 0]);
+        acc[4 * k4 + 1] = fmaf(c.y, x, acc[4 * k4 + 1]);
+        acc[4 * k4 + 2] = fmaf(c.z, x, acc[4 * k4 + 2]);
+        acc[4 * k4 + 3] = fmaf(c.w, x, acc[4 * k4 + 3]);
+      }
     }
+    __syncwarp();
+    // MFCC rows of the tile are one contiguous block of nf * n_mfcc floats
+    float* s_o = s_t;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      if (k < t.n_mfcc) s_o[lane * t.n_mfcc + k] = acc[k];
+    __syncwarp();
+    for (int i = lane; i < nf * t.n_mfcc; i += 32) mfcc_raw[g0 * t.n_mfcc + i] = s_o[i];
+    // moments
+    const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
+    const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
+    if (uniform) {
+      // float64 reductions: the mean of a constant channel must come out exact (silence -> all-zero rows)
+      double my_s = 0.0, my_q = 0.0;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        if (k < t.n_mfcc) {
+          const double a = valid ? static_cast<double>(acc[k]) : 0.0;
+          double ts = a, tq = a * a;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            ts += __shfl_xor_sync(0xffffffffu, ts, o);
+            tq += __shfl_xor_sync(0xffffffffu, tq, o);
+          }
+          if (lane == k) { my_s = ts; my_q = tq; }
+        }
+      }
+      if (lane < t.n_mfcc && first_clip >= 0) {
+        atomicAdd(sum + static_cast<int64_t>(first_clip) * t.n_mfcc + lane, my_s);
+        atomicAdd(sumsq + static_cast<int64_t>(first_clip) * t.n_mfcc + lane, my_q);
+      }
+    } else if (valid) {                              // tile straddles a clip boundary: per-frame adds
+#pragma unroll
+      for (int k = 0; k < KP; ++k)
+        if (k < t.n_mfcc) {
+          const double a = static_cast<double>(acc[k]);
+          atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + k, a);
+          atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + k, a * a);
+        }
+    }
+    __syncwarp();
   }
 }
 
@@ -341,41 +399,25 @@ __global__ void __launch_bounds__(kDctWarps * 32) k_dct_sum(DeviceTables t, Batc
 //     -> pair reduction.  Thread per (output row, channel).
 //     extract_features_utils.py:5-8,21-27,33-44; librosa.feature.delta == scipy savgol 'interp'.
 // ------------------------------------------------------------------------------------------------
-struct DeltaOut { float v, d1, d2; };
-
-__device__ __forceinline__ DeltaOut delta_at(const float* __restrict__ col, int in_ld, int64_t T,
-                                             int64_t tf, float mu, float inv_scale_den, bool cmvn,
-                                             bool deltas) {
-  // col points at frame 0 of this clip for this channel
-  auto val = [&](int64_t f) {
-    const float x = __ldg(col + f * in_ld);
-    return cmvn ? __fdiv_rn(x - mu, inv_scale_den) : x;
-  };
-  DeltaOut o;
-  o.v = val(tf);
-  o.d1 = 0.0f;
-  o.d2 = 0.0f;
-  if (deltas) {
-    const int64_t tc = min(max(tf, static_cast<int64_t>(4)), T - 5);
-    float x[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) x[k] = val(tc - 4 + k);
-    // delta: sum k x[k] / 60 ; delta2: [28 7 -8 -17 -20 -17 -8 7 28] / 462
-    const float s1 = 4.0f * (x[8] - x[0]) + 3.0f * (x[7] - x[1]) + 2.0f * (x[6] - x[2]) + (x[5] - x[3]);
-    const float s2 = 28.0f * (x[0] + x[8]) + 7.0f * (x[1] + x[7]) - 8.0f * (x[2] + x[6]) -
-                     17.0f * (x[3] + x[5]) - 20.0f * x[4];
-    o.d1 = s1 * (1.0f / 60.0f);
-    o.d2 = s2 * (1.0f / 462.0f);
-  }
-  return o;
+// Savitzky-Golay taps on nine consecutive frames x[0..8]:
+//   delta  = sum k x[k] / 60,  delta2 = [28 7 -8 -17 -20 -17 -8 7 28] . x / 462
+__device__ __forceinline__ float sg_d1(const float* x) {
+  return (4.0f * (x[8] - x[0]) + 3.0f * (x[7] - x[1]) + 2.0f * (x[6] - x[2]) + (x[5] - x[3])) * (1.0f / 60.0f);
+}
+__device__ __forceinline__ float sg_d2(const float* x) {
+  return (28.0f * (x[0] + x[8]) + 7.0f * (x[1] + x[7]) - 8.0f * (x[2] + x[6]) - 17.0f * (x[3] + x[5]) -
+          20.0f * x[4]) * (1.0f / 462.0f);
 }
 
-__global__ void __launch_bounds__(256) k_delta_reduce(BatchView b, const float* __restrict__ in, int C,
-                                                      int in_ld, const double* __restrict__ sum,
-                                                      const double* __restrict__ sumsq, bool cmvn,
-                                                      bool deltas, bool reduce,
-                                                      float* __restrict__ out, int64_t out_ld,
-                                                      int col0) {
+// One warp per output row, lanes over channels.  CMVN is affine and the filters are linear, so the
+// deltas are taken on the mean-centred values and scaled by 1 / (sigma + 1e-10) once; the two frames of a row
+// share nine of their ten taps, so an interior row costs ten coalesced loads per lane.
+__global__ void __launch_bounds__(256, 3) k_delta_reduce(BatchView b, const float* __restrict__ in, int C,
+                                                         int in_ld, const double* __restrict__ sum,
+                                                         const double* __restrict__ sumsq, bool cmvn,
+                                                         bool deltas, bool reduce,
+                                                         float* __restrict__ out, int64_t out_ld,
+                                                         int col0) {
   const int rows_per_block = blockDim.x / 32;
   const int lane = threadIdx.x & 31, wr = threadIdx.x >> 5;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * rows_per_block + wr; r < b.total_rows;
@@ -386,29 +428,55 @@ __global__ void __launch_bounds__(256) k_delta_reduce(BatchView b, const float* 
     const int64_t lr = r - __ldg(b.row_off + clip);
     const int64_t ta = reduce ? 2 * lr : lr;
     const bool pair = reduce && (ta + 1 < T);
+    // window centres (edges replicate the value at frame 4 / T-5: savgol mode='interp')
+    const int64_t ca = min(max(ta, static_cast<int64_t>(4)), T - 5);
+    const int64_t cb = min(max(ta + 1, static_cast<int64_t>(4)), T - 5);
+    const bool shared_taps = pair && cb == ca + 1;
+    const double inv_T = cmvn ? 1.0 / static_cast<double>(T) : 0.0;
     for (int ch = lane; ch < C; ch += 32) {
-      float mu = 0.0f, den = 1.0f;
+      float mu = 0.0f, inv = 1.0f;
       if (cmvn) {
-        const double Td = static_cast<double>(T);
-        const double m = __ldg(sum + static_cast<int64_t>(clip) * C + ch) / Td;
+        const double m = __ldg(sum + static_cast<int64_t>(clip) * C + ch) * inv_T;
         // population variance from the float64 moments (sum x, sum x^2) of the float32 values
-        const double var = fmax(0.0, __ldg(sumsq + static_cast<int64_t>(clip) * C + ch) / Td - m * m);
+        const double var = fmax(0.0, fma(__ldg(sumsq + static_cast<int64_t>(clip) * C + ch), inv_T, -m * m));
         mu = static_cast<float>(m);
-        den = static_cast<float>(sqrt(var)) + 1e-10f;  // float32 std + 1e-10 (NEP 50: stays float32)
+        inv = __fdiv_rn(1.0f, sqrtf(static_cast<float>(var)) + 1e-10f);   // float32 std + 1e-10
       }
       const float* col = in + f0 * in_ld + ch;
-      DeltaOut a = delta_at(col, in_ld, T, ta, mu, den, cmvn, deltas);
-      if (pair) {
-        const DeltaOut c2 = delta_at(col, in_ld, T, ta + 1, mu, den, cmvn, deltas);
-        a.v = 0.5f * (a.v + c2.v);
-        a.d1 = 0.5f * (a.d1 + c2.d1);
-        a.d2 = 0.5f * (a.d2 + c2.d2);
+      float va = (__ldg(col + ta * in_ld) - mu) * inv, d1 = 0.0f, d2 = 0.0f;
+      if (pair) va = 0.5f * (va + (__ldg(col + (ta + 1) * in_ld) - mu) * inv);
+      if (deltas) {
+        float xa[9];
+        const float* pa = col + (ca - 4) * in_ld;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xa[k] = __ldg(pa + k * in_ld) - mu;   // centred: constants give exact 0
+        d1 = sg_d1(xa);
+        d2 = sg_d2(xa);
+        if (pair) {
+          float xb[9];
+          if (shared_taps) {                         // interior row: nine of the ten taps are shared
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xb[k] = xa[k + 1];
+            xb[8] = __ldg(pa + 9 * in_ld) - mu;
+          } else if (cb == ca) {                     // both frames clamp to the same edge window
+#pragma unroll
+            for (int k = 0; k < 9; ++k) xb[k] = xa[k];
+          } else {
+            const float* pb = col + (cb - 4) * in_ld;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) xb[k] = __ldg(pb + k * in_ld) - mu;
+          }
+          d1 = 0.5f * (d1 + sg_d1(xb));
+          d2 = 0.5f * (d2 + sg_d2(xb));
+        }
+        d1 *= inv;
+        d2 *= inv;
       }
       float* o = out + r * out_ld + col0;
-      o[ch] = a.v;
+      o[ch] = va;
       if (deltas) {
-        o[C + ch] = a.d1;
-        o[2 * C + ch] = a.d2;
+        o[C + ch] = d1;
+        o[2 * C + ch] = d2;
       }
     }
   }
@@ -847,8 +915,17 @@ int launch_mel_db(cudaStream_t s, const DeviceTables& t, const BatchView& b, con
 
 int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* db,
                    const uint32_t* dbmax_key, float* mfcc_raw, double* sum, double* sumsq) {
-  const int grid = grid_for((b.total_frames + kDctRun - 1) / kDctRun, kDctWarps, kSmCount * 6);
-  k_dct_sum<<<grid, kDctWarps * 32, 0, s>>>(t, b, db, dbmax_key, mfcc_raw, sum, sumsq);
+  if (t.n_mels > 128 || t.n_mfcc > 32) return -1;
+  const int kp = t.n_mfcc <= 24 ? 24 : 32;
+  const size_t smem = (static_cast<size_t>(t.n_mels) * kp + static_cast<size_t>(kDctWarps) * t.n_mels * kDctPitch) * sizeof(float);
+  const int grid = grid_for((b.total_frames + 31) / 32, kDctWarps, kSmCount * 2);
+  if (kp == 24) {
+    if (cudaFuncSetAttribute(k_dct_sum<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return -1;
+    k_dct_sum<24><<<grid, kDctWarps * 32, smem, s>>>(t, b, db, dbmax_key, mfcc_raw, sum, sumsq);
+  } else {
+    if (cudaFuncSetAttribute(k_dct_sum<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return -1;
+    k_dct_sum<32><<<grid, kDctWarps * 32, smem, s>>>(t, b, db, dbmax_key, mfcc_raw, sum, sumsq);
+  }
   NSF_CHECK_LAUNCH();
   return 1;
 }
@@ -856,7 +933,7 @@ int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, co
 int launch_delta_reduce(cudaStream_t s, const BatchView& b, const float* in, int C, int in_ld,
                         const double* sum, const double* sumsq, bool cmvn, bool deltas, bool reduce,
                         float* out, int64_t out_ld, int col0) {
-  const int grid = grid_for(b.total_rows, 8, kSmCount * 16);
+  const int grid = grid_for(b.total_rows, 8, kSmCount * 8);
   k_delta_reduce<<<grid, 256, 0, s>>>(b, in, C, in_ld, sum, sumsq, cmvn, deltas, reduce, out, out_ld, col0);
   NSF_CHECK_LAUNCH();
   return 1;
