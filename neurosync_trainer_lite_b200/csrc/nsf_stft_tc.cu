@@ -302,16 +302,21 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_tc_fold(DeviceTables t, Bat
     }
     const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
     if (lane == 0) row_exp[g] = e2;
-    for (int j = 2 * lane; j < kp; j += 64) {
+    // eight planes, one half2 store each: base pointer and plane stride hoisted, the (chain, part)
+    // loop fully unrolled (planes of the absent chain of an odd F are simply skipped)
+    __half2* dst0 = reinterpret_cast<__half2*>(planes + g * kp) + lane;
+    const int64_t pstride = plane_rows * kp / 2;           // half2 elements between planes
+    for (int j = 2 * lane; j < kp; j += 64, dst0 += 32) {
       const Folded a = fold_at(u, j, F, Nh, K, even), c = fold_at(u, j + 1, F, Nh, K, even);
-      for (int cp = 0; cp < n_cp; ++cp) {
-        const float va = a.v[cp] * scale, vc = c.v[cp] * scale;
-        const __half2 hi = __floats2half2_rn(va, vc);
-        const float2 back = __half22float2(hi);
-        const __half2 lo = __floats2half2_rn(va - back.x, vc - back.y);
-        __half* dst = planes + (static_cast<int64_t>(cp * 2) * plane_rows + g) * kp + j;
-        *reinterpret_cast<__half2*>(dst) = hi;
-        *reinterpret_cast<__half2*>(dst + plane_rows * kp) = lo;
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        if (cp < n_cp) {
+          const float va = a.v[cp] * scale, vc = c.v[cp] * scale;
+          const __half2 hi = __floats2half2_rn(va, vc);
+          const float2 back = __half22float2(hi);
+          dst0[(2 * cp) * pstride] = hi;
+          dst0[(2 * cp + 1) * pstride] = __floats2half2_rn(va - back.x, vc - back.y);
+        }
       }
     }
     __syncwarp();
