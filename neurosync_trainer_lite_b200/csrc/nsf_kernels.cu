@@ -898,12 +898,9 @@ int launch_mel_db(cudaStream_t s, const DeviceTables& t, const BatchView& b, con
   if (t.n_mels > kMelWarps * kMelPerWarp) return -1;
   const int chain_cols = t.np[0] > t.np[1] ? t.np[0] : t.np[1];
   const size_t smem = (static_cast<size_t>(chain_cols) * kMelPitch + kMelFrames * (t.n_mels + 1)) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_mel_db, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-      return -1;
-    attr_set = true;
-  }
+  // per launch: the attribute is per device, and a process may drive several devices
+  if (cudaFuncSetAttribute(k_mel_db, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    return -1;
   if (smem > 200 * 1024) return -1;
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
@@ -943,12 +940,9 @@ int launch_autocorr(cudaStream_t s, const DeviceTables& t, const BatchView& b, c
                     bool reduce, float* out, int64_t out_ld, int col0) {
   const AcGeom geo = ac_geom(t.F);
   const size_t smem = static_cast<size_t>(kAcWarps) * geo.row_floats * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-      return -1;
-    attr_set = true;
-  }
+  // per launch: the attribute is per device, and a process may drive several devices
+  if (cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    return -1;
   if (smem > 200 * 1024) return -1;
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;

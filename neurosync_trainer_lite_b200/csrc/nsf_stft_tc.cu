@@ -753,11 +753,8 @@ int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
   const OperandView v = view_operands(tc, b.total_frames, operands);
   const int buf_floats = ((t.F + 3) & ~3) + 8;   // frame + up to 3 floats of skew + tail, 16-byte multiple
   const size_t smem = (static_cast<size_t>((t.F + 3) & ~3) + static_cast<size_t>(kFoldWarps) * 2 * buf_floats) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_tc_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
-    attr_set = true;
-  }
+  // per launch: the attribute is per device, and a process may drive several devices
+  if (cudaFuncSetAttribute(k_tc_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
   if (smem > 220 * 1024) return -1;
   int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
@@ -791,13 +788,10 @@ int launch_stft_tc_gemm(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
   const OperandView v = view_operands(tc, b.total_frames, operands);
   CUtensorMap map_a;
   if (!encode_map(&map_a, v.planes, static_cast<uint64_t>(tc.chains) * 4 * v.rows, tc.kp, BM)) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)) !=
-        cudaSuccess)
-      return -1;
-    attr_set = true;
-  }
+  // per launch: the attribute is per device, and a process may drive several devices
+  if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)) !=
+      cudaSuccess)
+    return -1;
   const int np_max = std::max(tc.np[0], tc.np[1]);
   const int n_tiles = (np_max + BN - 1) / BN;
   const int64_t grid = (v.rows / BM) * n_tiles * tc.chains;
