@@ -98,18 +98,39 @@ def collect_arrays(audio_features, facial_data, include_fast=True, include_slow=
     return out_a, out_f
 
 
+def _binary_cache_path(audio_features_csv_path):
+    return os.path.splitext(audio_features_csv_path)[0] + ".npy"
+
+
 def collect_features(audio_path, audio_features_csv_path, facial_csv_path, sr,
-                     include_fast=True, include_slow=False, blend_boundaries=True, blend_frames=30):
-    """reference :108-177 -- same CSV cache side effects, same return shapes and dtypes."""
+                     include_fast=True, include_slow=False, blend_boundaries=True, blend_frames=30,
+                     cache_format=None):
+    """reference :108-177 -- same CSV cache side effects, same return shapes and dtypes.
+
+    ``cache_format`` (extension; default from ``NSF_FEATURE_CACHE`` or "csv"):
+    "csv" = the reference's ``audio_features.csv`` (1.3 s and 9 MB per 30 s clip to write);
+    "npy" = a float32 ``audio_features.npy`` beside it (milliseconds, 1.8 MB); "both" writes both.
+    An existing CSV cache is always honoured first, exactly like the reference."""
+    cache_format = cache_format or os.environ.get("NSF_FEATURE_CACHE", "csv")
+    if cache_format not in ("csv", "npy", "both"):
+        raise ValueError("cache_format must be 'csv', 'npy' or 'both'")
+    npy_path = _binary_cache_path(audio_features_csv_path)
     if os.path.exists(audio_features_csv_path):                           # :112-114
         print(f"Loading audio features from {audio_features_csv_path}")
         audio_features = pd.read_csv(audio_features_csv_path).values
+    elif cache_format != "csv" and os.path.exists(npy_path):
+        print(f"Loading audio features from {npy_path}")
+        audio_features = np.load(npy_path).astype(np.float64)
     else:                                                                 # :115-120
         print(f"Extracting audio features from {audio_path}")
         audio_features, _ = extract_audio_features(audio_path, sr)
         if audio_features is not None:
-            pd.DataFrame(audio_features).to_csv(audio_features_csv_path, index=False)
-            print(f"Audio features saved to {audio_features_csv_path}")
+            if cache_format in ("csv", "both"):
+                pd.DataFrame(audio_features).to_csv(audio_features_csv_path, index=False)
+                print(f"Audio features saved to {audio_features_csv_path}")
+            if cache_format in ("npy", "both"):
+                np.save(npy_path, audio_features.astype(np.float32))
+                print(f"Audio features saved to {npy_path}")
     facial_data = pd.read_csv(facial_csv_path).drop(columns=COLUMNS_TO_DROP).values   # :123
     if audio_features is None:
         # the reference fails here with TypeError: object of type 'NoneType' has no len() (:143)
@@ -176,3 +197,89 @@ def collect_batch(audio_rows, facial_rows, include_fast=True, include_slow=False
     f = np.concatenate([np.asarray(x, dtype=dtype) for x in facial_rows], axis=0)
     return eng.collect_host(a, a_off, f, f_off, include_fast, include_slow, blend_boundaries,
                             blend_frames)
+
+
+def load_data_batched(root_dir, sr, processed_folders, include_fast=True, include_slow=False,
+                      blend_boundaries=True, blend_frames=30, rank=0, world=1, cache_format=None,
+                      device=None):
+    """``load_data`` (reference :10-26) for a whole dataset at once - the B200-first builder.
+
+    Same folder scan, caches, facial handling and ``(audio_features, facial_data)`` examples in
+    ``os.listdir`` order as ``load_data`` + ``process_folder`` + ``collect_features``, but every take
+    without a cache goes through ONE batched extraction call (int16 PCM up, peak normalisation on the
+    device) and all takes through ONE batched float64 augmentation call.  With ``world > 1`` the
+    takes are split by clip over ranks (``shard.lpt_partition``); each rank returns the examples of
+    its own takes together with their positions in the full list: ``(examples, indices)``.
+    """
+    from .. import shard
+    from ..utils.audio.extraction.extract_features import MIN_FRAMES
+    from ..utils.audio.load_audio import decode_for_path
+
+    cache_format = cache_format or os.environ.get("NSF_FEATURE_CACHE", "csv")
+    takes = []                      # (folder, audio_path | None, csv_cache, facial_csv)
+    for folder in os.listdir(root_dir):
+        folder_path = os.path.join(root_dir, folder)
+        if not os.path.isdir(folder_path) or folder in processed_folders:
+            continue
+        mov, mp4, wav, facial_csv, cache_csv, _ = find_files(folder_path)
+        video = mov or mp4
+        have_cache = os.path.exists(cache_csv) or (cache_format != "csv" and
+                                                   os.path.exists(_binary_cache_path(cache_csv)))
+        if not (facial_csv and (video or wav or have_cache)):
+            continue
+        audio_path = get_audio(video, wav, folder_path) if (video or wav) else None
+        if not (audio_path or have_cache):
+            continue
+        takes.append((folder, audio_path, cache_csv, facial_csv, have_cache))
+    # partition by audio size, independent of which caches exist (ranks must agree while caches appear)
+    weights = [max(1, os.path.getsize(t[1])) if t[1] and os.path.exists(t[1]) else 1 for t in takes]
+    mine = shard.lpt_partition(weights, world)[rank] if world > 1 else list(range(len(takes)))
+
+    f_len, h_len = _engine.frame_params(88200)          # file-path mode always lands at 88.2 kHz
+    eng = _engine.get_engine(88200, f_len, h_len, device=device)
+    audio_rows, todo, pcms = {}, [], []
+    for i in mine:
+        folder, audio_path, cache_csv, facial_csv, have_cache = takes[i]
+        if os.path.exists(cache_csv):
+            audio_rows[i] = pd.read_csv(cache_csv).values
+        elif have_cache:
+            audio_rows[i] = np.load(_binary_cache_path(cache_csv)).astype(np.float64)
+        else:
+            pcm, _ = decode_for_path(audio_path, sr)
+            n = eng.plan.guard_frames(len(pcm))
+            if n < MIN_FRAMES:
+                print(f"Audio file is too short: {n} frames, required: {MIN_FRAMES} frames")
+                continue
+            todo.append(i)
+            pcms.append(pcm)
+    if todo:
+        if not all(p.dtype == pcms[0].dtype for p in pcms):
+            pcms = [p if p.dtype == np.float32 else p.astype(np.float32) / np.float32(32768) for p in pcms]
+        packed, off = _engine.pack_clips(pcms, dtype=pcms[0].dtype)
+        rows = eng.extract_host(packed, off, nv.PEAK_NORMALIZE)
+        roff = eng.row_offsets(off)
+        for k, i in enumerate(todo):
+            feats = rows[roff[k]:roff[k + 1]].astype(np.float64)
+            audio_rows[i] = feats
+            cache_csv = takes[i][2]
+            if cache_format in ("csv", "both"):
+                pd.DataFrame(feats).to_csv(cache_csv, index=False)
+            if cache_format in ("npy", "both"):
+                np.save(_binary_cache_path(cache_csv), feats.astype(np.float32))
+    order = [i for i in mine if i in audio_rows]
+    if not order:
+        return ([], []) if world > 1 else []
+    facial = [pd.read_csv(takes[i][3]).drop(columns=COLUMNS_TO_DROP).values.astype(np.float64) for i in order]
+    out_a, out_f, o_off = eng.collect_host(
+        np.concatenate([audio_rows[i] for i in order], axis=0),
+        np.concatenate([[0], np.cumsum([len(audio_rows[i]) for i in order])]),
+        np.concatenate(facial, axis=0), np.concatenate([[0], np.cumsum([len(f) for f in facial])]),
+        include_fast, include_slow, blend_boundaries, blend_frames)
+    examples = []
+    for k, i in enumerate(order):
+        a = out_a[o_off[k]:o_off[k + 1]]
+        f = out_f[o_off[k]:o_off[k + 1]].copy()
+        f[:, :61] *= 100                                                   # process_folder :68
+        examples.append((a, f))
+        processed_folders.add(takes[i][0])
+    return (examples, order) if world > 1 else examples

@@ -352,11 +352,54 @@ def test_collect_features_with_csv_plumbing(tmp_path, dp, oracle):
     assert np.abs(a[:, :69] - wa[:, :69]).max() <= TOL_MFCC
     assert np.abs(a[:, 69:] - wa[:, 69:]).max() <= TOL_AC
     np.testing.assert_array_equal(f, wf)
+    # binary cache extension: float32 .npy beside the CSV path, CSV still wins if present
+    take2 = tmp_path / "data2" / "take_002"
+    take2.mkdir(parents=True)
+    (take2 / "audio.wav").write_bytes(synth.wav_bytes(pcm, 88200))
+    a3, _ = dp.collect_features(str(take2 / "audio.wav"), str(take2 / "audio_features.csv"), str(fcsv), 88200,
+                                cache_format="npy")
+    assert (take2 / "audio_features.npy").exists() and not (take2 / "audio_features.csv").exists()
+    a4, _ = dp.collect_features(None, str(take2 / "audio_features.csv"), str(fcsv), 88200, cache_format="npy")
+    np.testing.assert_allclose(a4, a3, rtol=0, atol=1e-6)                   # float32 cache
+    np.testing.assert_allclose(a3, a, rtol=0, atol=1e-12)
     done = set()
     ex = dp.load_data(str(tmp_path / "data"), 88200, done)                  # dataset builder on top
     assert len(ex) == 1 and done == {"take_001"}
     np.testing.assert_allclose(ex[0][0], a, rtol=0, atol=1e-12)
     np.testing.assert_allclose(ex[0][1], wf * 100, rtol=1e-15, atol=0)      # facial[:, :61] *= 100
+
+
+def test_batched_dataset_builder_equals_per_folder_builder(tmp_path, dp):
+    """load_data_batched (one extraction batch + one augmentation batch, optional clip sharding) gives
+    the same examples, in os.listdir order, as the reference-shaped load_data."""
+    import pandas as pd
+    cols = ["Timecode", "BlendshapeCount"] + [f"bs{i}" for i in range(61)]
+    for root in ("a", "b"):
+        for k, (secs, rows) in enumerate([(2.0, 118), (3.1, 190), (1.4, 80)]):
+            take = tmp_path / root / f"take_{k:03d}"
+            take.mkdir(parents=True)
+            y = synth.synth_clip(secs, 88200, seed=40 + k, kind=("voiced", "gated", "noise")[k])
+            (take / "audio.wav").write_bytes(synth.wav_bytes(synth.to_int16_pcm(0.8 * y), 88200))
+            pd.DataFrame(np.hstack([np.zeros((rows, 2)), synth.synth_facial(rows, seed=k)]),
+                         columns=cols).to_csv(take / f"t{k}_iPhone_cal.csv", index=False)
+    ref = dp.load_data(str(tmp_path / "a"), 88200, set())
+    done = set()
+    got = dp.load_data_batched(str(tmp_path / "b"), 88200, done)
+    assert len(ref) == len(got) == 3 and len(done) == 3
+    # os.listdir order is the same for both roots (same names), so examples pair up
+    for (ra, rf), (ga, gf) in zip(ref, got):
+        assert ra.shape == ga.shape and rf.shape == gf.shape
+        np.testing.assert_allclose(ga, ra, rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(gf, rf)
+    # sharded over two "ranks": union of the shards == the full list, positions returned
+    for p in (tmp_path / "b").glob("*/audio_features.csv"):
+        p.unlink()
+    parts = [dp.load_data_batched(str(tmp_path / "b"), 88200, set(), rank=r, world=2) for r in range(2)]
+    seen = sorted(i for _, idx in parts for i in idx)
+    assert seen == [0, 1, 2]
+    for ex, idx in parts:
+        for (ga, gf), i in zip(ex, idx):
+            np.testing.assert_allclose(ga, ref[i][0], rtol=0, atol=1e-12)
 
 
 def test_dataset_windows_match_reference_semantics(golden, nv):
