@@ -369,16 +369,40 @@ def run_native(args, rank, world, local_rank):
             ach, peak, u = per_s / 1e12, fma_peak, "TFLOP/s"
         kernels.append({"kernel": name, "ms": round(ms, 4), "bound": bound, "achieved": round(ach, 2),
                         "peak": round(peak, 1), "unit": u, "frac": round(ach / peak, 4)})
+    # executed (issued) tensor work where it differs from the algorithmic count: the split-fp16 products
+    hmma_peak = 553.0                                   # mma.sync m16n8k16 f16, measured (profiles/ubench_mma_b200.txt)
+    for k in kernels:
+        ms = k["ms"] * 1e-3
+        if k["kernel"] == "autocorr":
+            nblk = (Fr + 15) // 16
+            nblk4 = (nblk + 3) // 4 * 4
+            ex = frames * nblk4 * 6 * 4096 / ms / 1e12
+            k.update(executed_tflops=round(ex, 1), executed_pipe="mma.sync (HMMA), 3 split-fp16 products",
+                     executed_peak=hmma_peak, executed_frac=round(ex / hmma_peak, 4))
+        elif k["kernel"] == "stft_gemm":
+            kp = eng.plan.fold_kp
+            npad = (eng.plan.fold_kp + 127) // 128 * 128          # bins per chain rounded to 128-wide tiles
+            chains = eng.plan.chains
+            ex = -(-frames // 128) * 128 * chains * 2 * 3 * 2.0 * kp * npad / ms / 1e12
+            k.update(executed_tflops=round(ex, 1), executed_pipe="tcgen05 kind::f16, 3 split-fp16 products",
+                     executed_peak=pk["tensor"], executed_frac=round(ex / pk["tensor"], 4))
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh)
     kernels.sort(key=lambda k: -k["ms"])
     top = kernels[0]
     roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-                "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                "unit": top["unit"], "frac": top["frac"],
+                "traffic": traffic.get(top["kernel"]) if traffic.get("workload") == args.workload else None,
+                "executed": {k: top[k] for k in top if k.startswith("executed_")},
                 "peak_source": pk["source"] + (" (fp32 FMA: 148 SM x 128 lanes x 2 x max SM clock)"
                                                if top["bound"] == "fma" else " (sustained)"),
                 "ms_per_launch": top["ms"], "stage_ms_sum": round(sum(k["ms"] for k in kernels), 4)}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # rank 0 at N = 1 only
         c = CpuOracle(args.workload)
         v, wall, cpu_s = c.step()
         c.close()
