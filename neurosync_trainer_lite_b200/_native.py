@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libnsf.so")
+LIB_PATH = os.environ.get("NSF_LIB_PATH") or os.path.join(_HERE, "_lib", "libnsf.so")   # override: experiments only
 
 # status codes / flags (mirror include/nsf.h)
 OK, ERR_BAD_ARG, ERR_TOO_SHORT, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(7)

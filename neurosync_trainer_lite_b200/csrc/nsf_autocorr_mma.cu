@@ -62,8 +62,9 @@ __device__ __forceinline__ int lag_of(int lane, int v) {
 // round trip to memory (2 kIters independent loads per lane in flight) and both passes over it
 // (mean / max, then window + scale + split) run out of registers.
 template <int kIters>
-__device__ __forceinline__ void am_fill(const DeviceTables& t, const float* __restrict__ y, int64_t base,
-                                        int64_t len, int64_t tf, __half* copies, const AmGeom& geo, int lane) {
+__device__ __forceinline__ void am_fill(const DeviceTables& t, const float* hann, const float* __restrict__ y,
+                                        int64_t base, int64_t len, int64_t tf, __half* copies, const AmGeom& geo,
+                                        int lane) {
   const int F = t.F;
   const int64_t first = tf * t.H - t.pad;
   const bool interior = first >= 0 && first + F <= len;
@@ -118,12 +119,12 @@ __device__ __forceinline__ void am_fill(const DeviceTables& t, const float* __re
   for (int i = 0; i < kIters; ++i) {
     const int e = lane + 32 * i;
     float x0 = 0.0f, x1 = 0.0f;
-    if (2 * e + 1 < F) {                               // the table is 256-byte aligned: one 8-byte load
-      const float2 w = __ldg(reinterpret_cast<const float2*>(t.hann_sym) + e);
+    if (2 * e + 1 < F) {                               // window table in shared memory: one 8-byte load
+      const float2 w = reinterpret_cast<const float2*>(hann)[e];
       x0 = (v0[i] - mean) * w.x * scale;
       x1 = (v1[i] - mean) * w.y * scale;
     } else if (2 * e < F) {
-      x0 = (v0[i] - mean) * __ldg(t.hann_sym + 2 * e) * scale;
+      x0 = (v0[i] - mean) * hann[2 * e] * scale;
     }
     const __half2 hi = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(hi);
@@ -255,6 +256,10 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
   const int pair = warp % kAmPairs;
   const bool producer = warp >= kAmPairs;
   __half* bufs = s_am + static_cast<size_t>(pair) * 2 * 4 * geo.len;      // two buffers of 4 copies
+  // np.hanning(F) staged in shared memory: with ~220 KB of the SM carved out for buffers the L1 is too
+  // small to keep the table resident next to the streaming frame loads
+  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len);
+  for (int n = threadIdx.x; n < t.F; n += blockDim.x) hann[n] = __ldg(t.hann_sym + n);
   uint64_t* full = s_bar[pair];
   uint64_t* empty = s_bar[pair] + 2;
   if (!producer) {
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
       for (int f = 0; f < n_frames; ++f, ++it) {
         const uint32_t buf = it & 1u;
         am_bar_wait(empty + buf, ((it >> 1) & 1u) ^ 1u);
-        am_fill<kIters>(t, y, base, len, tf0 + f, bufs + buf * 4 * geo.len, geo, lane);   // ends with __syncwarp
+        am_fill<kIters>(t, hann, y, base, len, tf0 + f, bufs + buf * 4 * geo.len, geo, lane);   // ends with __syncwarp
         if (lane == 0) am_bar_arrive(full + buf);
       }
     } else {
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
         // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
         // rare, so the consumer refills the buffer it still owns itself
         if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags)) {
-          am_fill<kIters>(t, y, base, len, tf == 0 ? 1 : T - 2, copies, geo, lane);
+          am_fill<kIters>(t, hann, y, base, len, tf == 0 ? 1 : T - 2, copies, geo, lane);
           am_mma(copies, geo, lane, val);
         }
         __syncwarp();
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
 int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
                         bool reduce, float* out, int64_t out_ld, int col0) {
   const AmGeom geo = am_geom(t.F);
-  const size_t smem = static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len * sizeof(__half);
+  const size_t smem = static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len * sizeof(__half) + ((t.F + 3) & ~3) * sizeof(float);
   if (smem > 220 * 1024 || t.n_lags > 191) return -1;
   int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
