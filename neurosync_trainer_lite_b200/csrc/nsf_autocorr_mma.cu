@@ -20,6 +20,8 @@
 // r[lag] / r[0].
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "nsf.h"
 #include "nsf_device_utils.cuh"
 #include "nsf_kernels.cuh"
@@ -55,48 +57,65 @@ __device__ __forceinline__ int lag_of(int lane, int v) {
   return base + (v & 1) + 64 * (v >> 1);
 }
 
-// Normalised autocorrelation of hop-frame tf of one clip into val[0..5] (see lag_of).
-// copies: [E_hi | E_lo | O_hi | O_lo], each geo.len halfs; E[kFrontMargin + m] = X(m),
-// O[kFrontMargin + m - 1] = X(m) (the one-sample shifted copy keeps odd offsets 4-byte aligned).
-// kIters = ceil((F/2 + 1) / 32) register-staging iterations: the whole frame is fetched with ONE
-// round trip to memory (2 kIters independent loads per lane in flight) and both passes over it
-// (mean / max, then window + scale + split) run out of registers.
-template <int kIters>
-__device__ __forceinline__ void am_fill(const DeviceTables& t, const float* hann, const float* __restrict__ y,
-                                        int64_t base, int64_t len, int64_t tf, __half* copies, const AmGeom& geo,
-                                        int lane) {
-  const int F = t.F;
-  const int64_t first = tf * t.H - t.pad;
-  const bool interior = first >= 0 && first + F <= len;
-  const float* src = y + base + first;
-  float v0[kIters], v1[kIters];
-  if (interior) {
+// Where the samples of one hop-frame come from.  `fast` frames lie inside their clip AND at least
+// 64 n_it samples before the end of the packed signal, so their 2 x 32 x n_it loads need no bounds
+// checks (what is read beyond sample F is masked: the staged window table is zero there).  All other
+// frames (the two clip-edge frames of np.pad(..., mode='reflect'), the very end of a batch) take the
+// checked path.
+struct AmSrc {
+  const float* clip;      // y + first sample of the clip
+  int64_t first, len;     // index of the frame's first sample relative to the clip, clip length
+  bool fast, valid;
+};
+__device__ __forceinline__ AmSrc am_src(const DeviceTables& t, const BatchView& b, const float* __restrict__ y,
+                                        int64_t base, int64_t len, int64_t tf, int n_it) {
+  AmSrc s;
+  s.clip = y + base;
+  s.first = tf * t.H - t.pad;
+  s.len = len;
+  s.fast = s.first >= 0 && s.first + t.F <= len && base + s.first + 64 * n_it <= b.total_samples;
+  s.valid = true;
+  return s;
+}
+// Element pair e = lane + 32 i of the frame: samples 2 e, 2 e + 1.
+// kExact: the kernel was instantiated for exactly n_it == kIters iterations, so the `i < n_it`
+// guards vanish and the unrolled iterations can be interleaved freely by the compiler.
+template <int kIters, bool kExact>
+__device__ __forceinline__ void am_issue_fast(const float* __restrict__ src, int n_it, int lane, float (&v0)[kIters],
+                                              float (&v1)[kIters]) {
+  const float* p = src + 2 * lane;
 #pragma unroll
-    for (int i = 0; i < kIters; ++i) {
-      const int n = 2 * (lane + 32 * i);
-      v0[i] = n < F ? __ldg(src + n) : 0.0f;
-      v1[i] = n + 1 < F ? __ldg(src + n + 1) : 0.0f;
-    }
-  } else {
-    auto sample = [&](int n) -> float {          // np.pad(..., mode='reflect') indexing
-      int64_t i = first + n;
-      if (i < 0) i = -i;
-      if (i >= len) i = 2 * (len - 1) - i;
-      return __ldg(y + base + i);
-    };
-#pragma unroll
-    for (int i = 0; i < kIters; ++i) {
-      const int n = 2 * (lane + 32 * i);
-      v0[i] = n < F ? sample(n) : 0.0f;
-      v1[i] = n + 1 < F ? sample(n + 1) : 0.0f;
+  for (int i = 0; i < kIters; ++i) {
+    if (kExact || i < n_it) {          // warp-uniform
+      v0[i] = __ldg(p + 64 * i);
+      v1[i] = __ldg(p + 64 * i + 1);
     }
   }
+}
+// Frame held in (v0, v1) -> the four fp16 copies.
+// copies: [E_hi | E_lo | O_hi | O_lo], each geo.len halfs; E[kFrontMargin + m] = X(m),
+// O[kFrontMargin + m - 1] = X(m) (the one-sample shifted copy keeps odd offsets 4-byte aligned).
+// hann: np.hanning(F) staged in shared memory and ZERO from F up to 64 n_it, so elements beyond the
+// frame come out as exact zeros without a branch (they land in the zero margin of the copies).
+// Both passes over the frame (mean / max, then window + scale + split) run out of registers and the
+// hot path has no divergent or data-dependent branches: a producer warp is alone on its latency.
+// When `next` is a fast frame every register pair is refilled with ITS samples as soon as the pair
+// has been consumed, so the next memory round trip overlaps the rest of this frame.
+template <int kIters, bool kExact>
+__device__ __forceinline__ void am_process(const DeviceTables& t, const float* hann, int n_it, float (&v0)[kIters],
+                                           float (&v1)[kIters], __half* copies, const AmGeom& geo, int lane,
+                                           const float* __restrict__ next_fast) {
+  const int F = t.F;
   // pass 1: mean and max |x| (bounds |x - mean| * w, which fixes the fp16 scale)
   float sum = 0.0f, amax = 0.0f;
 #pragma unroll
   for (int i = 0; i < kIters; ++i) {
-    sum += v0[i] + v1[i];
-    amax = fmaxf(amax, fmaxf(fabsf(v0[i]), fabsf(v1[i])));
+    if (kExact || i < n_it) {
+      const int n = 2 * (lane + 32 * i);
+      const float a = n < F ? v0[i] : 0.0f, c = n + 1 < F ? v1[i] : 0.0f;
+      sum += a + c;
+      amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
+    }
   }
   sum = warp_sum(sum);
   amax = warp_max(amax);
@@ -109,29 +128,27 @@ __device__ __forceinline__ void am_fill(const DeviceTables& t, const float* hann
   }
   const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
   // pass 2a: window, scale, split; pair e = (X(2e), X(2e+1)) goes to the E copies as one half2 each.
-  // Iterations are independent (no cross-lane traffic), so the compiler can interleave them freely.
-  uint32_t* e_hi = reinterpret_cast<uint32_t*>(copies) + kFrontMargin / 2;
+  uint32_t* e_hi = reinterpret_cast<uint32_t*>(copies) + kFrontMargin / 2 + lane;
   uint32_t* e_lo = e_hi + geo.len / 2;
   uint32_t* o_hi = e_lo + geo.len / 2;
   uint32_t* o_lo = o_hi + geo.len / 2;
-  const int n_pairs = F / 2 + 1;               // one pair beyond the frame flushes the shifted copy
+  const float2* w2 = reinterpret_cast<const float2*>(hann) + lane;
+  const float* nx = next_fast + 2 * lane;
 #pragma unroll
   for (int i = 0; i < kIters; ++i) {
-    const int e = lane + 32 * i;
-    float x0 = 0.0f, x1 = 0.0f;
-    if (2 * e + 1 < F) {                               // window table in shared memory: one 8-byte load
-      const float2 w = reinterpret_cast<const float2*>(hann)[e];
-      x0 = (v0[i] - mean) * w.x * scale;
-      x1 = (v1[i] - mean) * w.y * scale;
-    } else if (2 * e < F) {
-      x0 = (v0[i] - mean) * hann[2 * e] * scale;
-    }
-    const __half2 hi = __floats2half2_rn(x0, x1);
-    const float2 hf = __half22float2(hi);
-    const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-    if (e < n_pairs) {
-      e_hi[e] = *reinterpret_cast<const uint32_t*>(&hi);
-      e_lo[e] = *reinterpret_cast<const uint32_t*>(&lo);
+    if (kExact || i < n_it) {
+      const float2 w = w2[32 * i];
+      const float x0 = (v0[i] - mean) * (w.x * scale);
+      const float x1 = (v1[i] - mean) * (w.y * scale);
+      if (next_fast != nullptr) {        // warp-uniform
+        v0[i] = __ldg(nx + 64 * i);
+        v1[i] = __ldg(nx + 64 * i + 1);
+      }
+      const __half2 hi = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      e_hi[32 * i] = *reinterpret_cast<const uint32_t*>(&hi);
+      e_lo[32 * i] = *reinterpret_cast<const uint32_t*>(&lo);
     }
   }
   __syncwarp();
@@ -139,11 +156,64 @@ __device__ __forceinline__ void am_fill(const DeviceTables& t, const float* hann
   // = high half of E word e-1 | low half of E word e  (E word -1 is the zero margin)
 #pragma unroll
   for (int i = 0; i < kIters; ++i) {
-    const int e = lane + 32 * i;
-    if (e < n_pairs) {
-      o_hi[e - 1] = __funnelshift_r(e_hi[e - 1], e_hi[e], 16);
-      o_lo[e - 1] = __funnelshift_r(e_lo[e - 1], e_lo[e], 16);
+    if (kExact || i < n_it) {
+      o_hi[32 * i - 1] = __funnelshift_r(e_hi[32 * i - 1], e_hi[32 * i], 16);
+      o_lo[32 * i - 1] = __funnelshift_r(e_lo[32 * i - 1], e_lo[32 * i], 16);
     }
+  }
+  __syncwarp();
+}
+
+// Any frame, start to finish, without register staging: three plain passes (mean / max, window +
+// split, shifted copies).  Cold path - the two clip-edge frames with np.pad(..., mode='reflect')
+// indexing, the tail of a batch, and the consumers' rare edge-fix refill - kept out of line so that it
+// costs the hot paths neither registers nor instruction-cache space.
+__device__ __noinline__ void am_fill_simple(const DeviceTables& t, const float* hann, const AmSrc& s, __half* copies,
+                                            const AmGeom& geo, int lane) {
+  const int F = t.F;
+  auto sample = [&](int n) -> float {
+    int64_t i = s.first + n;
+    if (i < 0) i = -i;
+    if (i >= s.len) i = 2 * (s.len - 1) - i;
+    return __ldg(s.clip + i);
+  };
+  // same association order as am_process (per lane: pairs e = lane, lane + 32, ...), so a frame gives
+  // bit-identical results whichever path stages it (batch == single-clip determinism)
+  const int n_pairs = F / 2 + 1;               // one pair beyond the frame flushes the shifted copy
+  float sum = 0.0f, amax = 0.0f;
+  for (int e = lane; e < n_pairs; e += 32) {
+    const float a = 2 * e < F ? sample(2 * e) : 0.0f, c = 2 * e + 1 < F ? sample(2 * e + 1) : 0.0f;
+    sum += a + c;
+    amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
+  }
+  sum = warp_sum(sum);
+  amax = warp_max(amax);
+  const float mean = sum / static_cast<float>(F);
+  const float bound = amax + fabsf(mean);
+  int e2 = 0;
+  if (bound > 0.0f && bound < INFINITY) {
+    e2 = 14 - (static_cast<int>((__float_as_uint(bound) >> 23) & 0xff) - 126);
+    e2 = max(-100, min(100, e2));
+  }
+  const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
+  uint32_t* e_hi = reinterpret_cast<uint32_t*>(copies) + kFrontMargin / 2;
+  uint32_t* e_lo = e_hi + geo.len / 2;
+  uint32_t* o_hi = e_lo + geo.len / 2;
+  uint32_t* o_lo = o_hi + geo.len / 2;
+  for (int e = lane; e < n_pairs; e += 32) {
+    float x0 = 0.0f, x1 = 0.0f;
+    if (2 * e < F) x0 = (sample(2 * e) - mean) * (hann[2 * e] * scale);
+    if (2 * e + 1 < F) x1 = (sample(2 * e + 1) - mean) * (hann[2 * e + 1] * scale);
+    const __half2 hi = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hi);
+    const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    e_hi[e] = *reinterpret_cast<const uint32_t*>(&hi);
+    e_lo[e] = *reinterpret_cast<const uint32_t*>(&lo);
+  }
+  __syncwarp();
+  for (int e = lane; e < n_pairs; e += 32) {
+    o_hi[e - 1] = __funnelshift_r(e_hi[e - 1], e_hi[e], 16);
+    o_lo[e - 1] = __funnelshift_r(e_lo[e - 1], e_lo[e], 16);
   }
   __syncwarp();
 }
@@ -169,9 +239,11 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   // (hi.hi) and the two cross products go to separate accumulators: four independent MMA chains.
   float d0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d0x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   float d1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  uint32_t ring_h[4][2], ring_l[4][2];        // B fragments of the last 4 K-blocks
+  // B fragments of the last 4 K-blocks: two register sets used alternately (a group of four blocks
+  // loads into one set while tile 1 reads the other), so no fragment is ever copied
+  uint32_t bp[4][4], bq[4][4];                // [slot][b0h, b1h, b0l, b1l]
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { ring_h[q][0] = ring_h[q][1] = ring_l[q][0] = ring_l[q][1] = 0u; }
+  for (int q = 0; q < 4; ++q) { bq[q][0] = bq[q][1] = bq[q][2] = bq[q][3] = 0u; }
   // A rows g / g+8 are 64 samples = 4 K-blocks apart: (a1, a3) of block a are (a0, a2) of block a+4
   uint32_t ar_h[4][2], ar_l[4][2];
 #pragma unroll
@@ -179,23 +251,35 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
     ar_h[q][0] = Ah[8 * q]; ar_h[q][1] = Ah[8 * q + 4];
     ar_l[q][0] = Al[8 * q]; ar_l[q][1] = Al[8 * q + 4];
   }
-  for (int a0 = 0; a0 < geo.nblk4; a0 += 4) {
+  // one group = 4 K-blocks; `cur` receives this group's B fragments, `old` holds the previous group's
+  auto group = [&](const uint32_t* pa_h, const uint32_t* pa_l, const uint32_t* pb_h, const uint32_t* pb_l,
+                   uint32_t (&cur)[4][4], const uint32_t (&old)[4][4]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int w = 8 * (a0 + q);
-      const uint32_t a1h = Ah[w + 32], a3h = Ah[w + 36], a1l = Al[w + 32], a3l = Al[w + 36];
-      const uint32_t b0h = Bh[w], b1h = Bh[w + 4], b0l = Bl[w], b1l = Bl[w + 4];
+      const uint32_t a1h = pa_h[8 * q + 32], a3h = pa_h[8 * q + 36];
+      const uint32_t a1l = pa_l[8 * q + 32], a3l = pa_l[8 * q + 36];
+      cur[q][0] = pb_h[8 * q]; cur[q][1] = pb_h[8 * q + 4];
+      cur[q][2] = pb_l[8 * q]; cur[q][3] = pb_l[8 * q + 4];
       const uint32_t a0h = ar_h[q][0], a2h = ar_h[q][1], a0l = ar_l[q][0], a2l = ar_l[q][1];
-      mma_16816(d0, a0h, a1h, a2h, a3h, b0h, b1h);
-      mma_16816(d1, a0h, a1h, a2h, a3h, ring_h[q][0], ring_h[q][1]);
-      mma_16816(d0x, a0h, a1h, a2h, a3h, b0l, b1l);
-      mma_16816(d1x, a0h, a1h, a2h, a3h, ring_l[q][0], ring_l[q][1]);
-      mma_16816(d0x, a0l, a1l, a2l, a3l, b0h, b1h);
-      mma_16816(d1x, a0l, a1l, a2l, a3l, ring_h[q][0], ring_h[q][1]);
-      ring_h[q][0] = b0h; ring_h[q][1] = b1h; ring_l[q][0] = b0l; ring_l[q][1] = b1l;
+      // the two cross products of a tile are placed four MMAs apart (dependent accumulator)
+      mma_16816(d0x, a0h, a1h, a2h, a3h, cur[q][2], cur[q][3]);
+      mma_16816(d1x, a0h, a1h, a2h, a3h, old[q][2], old[q][3]);
+      mma_16816(d0, a0h, a1h, a2h, a3h, cur[q][0], cur[q][1]);
+      mma_16816(d1, a0h, a1h, a2h, a3h, old[q][0], old[q][1]);
+      mma_16816(d0x, a0l, a1l, a2l, a3l, cur[q][0], cur[q][1]);
+      mma_16816(d1x, a0l, a1l, a2l, a3l, old[q][0], old[q][1]);
       ar_h[q][0] = a1h; ar_h[q][1] = a3h; ar_l[q][0] = a1l; ar_l[q][1] = a3l;
     }
+  };
+  const uint32_t *pa_h = Ah, *pa_l = Al, *pb_h = Bh, *pb_l = Bl;
+  int left = geo.nblk4;
+#pragma unroll 1
+  for (; left >= 8; left -= 8) {
+    group(pa_h, pa_l, pb_h, pb_l, bp, bq);
+    group(pa_h + 32, pa_l + 32, pb_h + 32, pb_l + 32, bq, bp);
+    pa_h += 64; pa_l += 64; pb_h += 64; pb_l += 64;
   }
+  if (left) group(pa_h, pa_l, pb_h, pb_l, bp, bq);   // nblk4 is a multiple of 4
   // tile 0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  tile 1: c2,c3 = base+128, base+129.
   val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];
   val[4] = d1[2] + d1x[2]; val[5] = d1[3] + d1x[3];
@@ -244,7 +328,7 @@ __device__ __forceinline__ void am_bar_wait(uint64_t* bar, uint32_t parity) {
 // tensor pipe is fed continuously while memory latency and the fp32->fp16 conversion hide behind it.
 constexpr int kAmPairs = 4;
 
-template <int kIters>
+template <int kIters, bool kExact>
 __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables t, BatchView b,
                                                                    const float* __restrict__ y, bool reduce,
                                                                    float* __restrict__ out, int64_t out_ld,
@@ -259,7 +343,8 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
   // np.hanning(F) staged in shared memory: with ~220 KB of the SM carved out for buffers the L1 is too
   // small to keep the table resident next to the streaming frame loads
   float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len);
-  for (int n = threadIdx.x; n < t.F; n += blockDim.x) hann[n] = __ldg(t.hann_sym + n);
+  const int n_it = (t.F / 2 + 1 + 31) / 32;          // register-staging iterations the frame needs
+  for (int n = threadIdx.x; n < 64 * n_it; n += blockDim.x) hann[n] = n < t.F ? __ldg(t.hann_sym + n) : 0.0f;
   uint64_t* full = s_bar[pair];
   uint64_t* empty = s_bar[pair] + 2;
   if (!producer) {
@@ -286,7 +371,14 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
       for (int f = 0; f < n_frames; ++f, ++it) {
         const uint32_t buf = it & 1u;
         am_bar_wait(empty + buf, ((it >> 1) & 1u) ^ 1u);
-        am_fill<kIters>(t, hann, y, base, len, tf0 + f, bufs + buf * 4 * geo.len, geo, lane);   // ends with __syncwarp
+        const AmSrc src = am_src(t, b, y, base, len, tf0 + f, n_it);
+        if (src.fast) {
+          float v0[kIters], v1[kIters];
+          am_issue_fast<kIters, kExact>(src.clip + src.first, n_it, lane, v0, v1);
+          am_process<kIters, kExact>(t, hann, n_it, v0, v1, bufs + buf * 4 * geo.len, geo, lane, nullptr);
+        } else {
+          am_fill_simple(t, hann, src, bufs + buf * 4 * geo.len, geo, lane);
+        }                                                 // both end with __syncwarp
         if (lane == 0) am_bar_arrive(full + buf);
       }
     } else {
@@ -303,7 +395,7 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
         // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
         // rare, so the consumer refills the buffer it still owns itself
         if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags)) {
-          am_fill<kIters>(t, hann, y, base, len, tf == 0 ? 1 : T - 2, copies, geo, lane);
+          am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
           am_mma(copies, geo, lane, val);
         }
         __syncwarp();
@@ -322,30 +414,207 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Trio kernel (the product path when its buffers fit): ONE block of 16 warps per SM, four groups of
+// (3 consumer warps + 1 producer warp) sharing a ring of 4 frame buffers.  The same 16 buffers per SM
+// as four (consumer, producer) pairs x 2 blocks, but 12 instead of 8 warps feed the tensor pipe: three
+// MMA warps per scheduler hide each other's fragment-load and accumulator latencies, and a producer -
+// which needs about a third of a consumer's time per frame - is no longer idle two thirds of the time.
+//
+// Schedule of a group (G = global group index, its j-th row is r = G + j * n_groups): consumer c owns
+// rows j = 3 t + c; hand-off slots are ordered  s = 6 t + 3 f + c  (f = first / second frame of the
+// row), i.e. A.f0 B.f0 C.f0 A.f1 B.f1 C.f1, so three buffers are being consumed while the fourth is
+// being filled.  Slot s lives in buffer s & 3 and is the (s >> 2)-th use of it, which fixes the
+// mbarrier parities on both sides without any shared counters.  A row with a single frame (odd T)
+// still hands over its empty second slot.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTrioGroups = 4;
+constexpr int kTrioWarps = kTrioGroups * 4;
+
+struct AmRow { int64_t base, len, T, tf0; int n_frames; };
+__device__ __forceinline__ AmRow am_locate_row(const BatchView& b, int64_t r, bool reduce) {
+  AmRow w;
+  const int clip = find_segment(b.row_off, b.n_clips, r);
+  w.base = __ldg(b.clip_off + clip);
+  w.len = __ldg(b.clip_off + clip + 1) - w.base;
+  w.T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
+  const int64_t lr = r - __ldg(b.row_off + clip);
+  w.tf0 = reduce ? 2 * lr : lr;
+  w.n_frames = (reduce && w.tf0 + 1 < w.T) ? 2 : 1;   // odd T: the last row passes through
+  return w;
+}
+
+template <int kIters, bool kExact>
+__global__ void __launch_bounds__(kTrioWarps * 32, 1) k_autocorr_trio(DeviceTables t, BatchView b,
+                                                                     const float* __restrict__ y, bool reduce,
+                                                                     float* __restrict__ out, int64_t out_ld,
+                                                                     int col0) {
+  extern __shared__ __align__(16) __half s_am[];
+  __shared__ uint64_t s_bar[kTrioGroups][8];       // per group: full[4], empty[4]
+  const AmGeom geo = am_geom(t.F);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp & 3;                         // a group lives on one scheduler (warp % 4)
+  const int role = warp >> 2;                       // 0..2 consumers, 3 producer
+  const bool producer = role == 3;
+  const size_t buf_halfs = static_cast<size_t>(4) * geo.len;
+  __half* bufs = s_am + static_cast<size_t>(grp) * 4 * buf_halfs;
+  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(kTrioGroups) * 4 * buf_halfs);
+  const int n_it = (t.F / 2 + 1 + 31) / 32;          // register-staging iterations the frame needs
+  for (int n = threadIdx.x; n < 64 * n_it; n += blockDim.x) hann[n] = n < t.F ? __ldg(t.hann_sym + n) : 0.0f;
+  uint64_t* full = s_bar[grp];
+  uint64_t* empty = s_bar[grp] + 4;
+  if (!producer) {
+    // zero once: the margins are never written again, the frame region is rewritten per frame
+    const int words = static_cast<int>(4 * buf_halfs / 2);
+    for (int i = role * 32 + lane; i < words; i += 96) reinterpret_cast<uint32_t*>(bufs)[i] = 0u;
+  } else if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { am_bar_init(full + q, 1); am_bar_init(empty + q, 1); }
+  }
+  __syncthreads();
+  const int64_t G = static_cast<int64_t>(blockIdx.x) * kTrioGroups + grp;
+  const int64_t n_groups = static_cast<int64_t>(gridDim.x) * kTrioGroups;
+  if (producer) {
+    // software pipeline: the samples of slot n+1 are requested while slot n is being converted
+    auto row_of = [&](uint32_t tt_, int fc_) { return G + static_cast<int64_t>(3 * tt_ + (fc_ % 3)) * n_groups; };
+    auto src_of = [&](uint32_t tt_, int fc_) {
+      const AmRow w = am_locate_row(b, row_of(tt_, fc_), reduce);
+      AmSrc sc;
+      sc.valid = false;
+      if (fc_ / 3 < w.n_frames) sc = am_src(t, b, y, w.base, w.len, w.tf0 + fc_ / 3, n_it);
+      return sc;
+    };
+    uint32_t tt = 0;
+    int fc = 0;
+    bool have = G < b.total_rows;
+    float v0[kIters], v1[kIters];
+    AmSrc cur;
+    cur.valid = false;
+    if (have) {
+      cur = src_of(0, 0);
+      if (cur.valid && cur.fast) am_issue_fast<kIters, kExact>(cur.clip + cur.first, n_it, lane, v0, v1);
+    }
+    while (have) {
+      const uint32_t slot = 6u * tt + static_cast<uint32_t>(fc);
+      const uint32_t buf = slot & 3u;
+      // next slot whose row exists (rows run out only at the very end of the group's list)
+      uint32_t ntt = tt;
+      int nfc = fc;
+      bool nhave = false;
+      for (;;) {
+        if (++nfc == 6) {
+          nfc = 0;
+          ++ntt;
+          if (G + static_cast<int64_t>(3 * ntt) * n_groups >= b.total_rows) break;
+        }
+        if (row_of(ntt, nfc) < b.total_rows) { nhave = true; break; }
+      }
+      AmSrc nxt;
+      nxt.valid = false;
+      if (nhave) nxt = src_of(ntt, nfc);
+      am_bar_wait(empty + buf, ((slot >> 2) & 1u) ^ 1u);
+      const bool nxt_fast = nxt.valid && nxt.fast;
+      const float* nxt_ptr = nxt_fast ? nxt.clip + nxt.first : nullptr;
+      if (cur.valid && cur.fast) {
+        am_process<kIters, kExact>(t, hann, n_it, v0, v1, bufs + buf * buf_halfs, geo, lane, nxt_ptr);   // ends with __syncwarp
+      } else {
+        if (cur.valid) am_fill_simple(t, hann, cur, bufs + buf * buf_halfs, geo, lane);
+        if (nxt_fast) am_issue_fast<kIters, kExact>(nxt_ptr, n_it, lane, v0, v1);
+      }
+      __syncwarp();
+      if (lane == 0) am_bar_arrive(full + buf);
+      tt = ntt; fc = nfc; have = nhave; cur = nxt;
+    }
+  } else {
+    const int c = role;
+    for (uint32_t tt = 0;; ++tt) {
+      const int64_t r = G + static_cast<int64_t>(3 * tt + c) * n_groups;
+      if (r >= b.total_rows) break;
+      const AmRow w = am_locate_row(b, r, reduce);
+      float acc[kVals];
+#pragma unroll
+      for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
+#pragma unroll 1
+      for (int f = 0; f < 2; ++f) {
+        const uint32_t slot = 6u * tt + 3u * static_cast<uint32_t>(f) + static_cast<uint32_t>(c);
+        const uint32_t buf = slot & 3u;
+        __half* copies = bufs + buf * buf_halfs;
+        am_bar_wait(full + buf, (slot >> 2) & 1u);
+        if (f < w.n_frames) {
+          const int64_t tf = w.tf0 + f;
+          float val[kVals];
+          am_mma(copies, geo, lane, val);
+          // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
+          // rare, so the consumer refills the buffer it still owns itself
+          if (w.T > 1 && (tf == 0 || tf == w.T - 1) && am_all_small(val, lane, t.n_lags)) {
+            am_fill_simple(t, hann, am_src(t, b, y, w.base, w.len, tf == 0 ? 1 : w.T - 2, n_it), copies, geo, lane);
+            am_mma(copies, geo, lane, val);
+          }
+#pragma unroll
+          for (int v = 0; v < kVals; ++v) acc[v] += val[v];
+        }
+        __syncwarp();
+        if (lane == 0) am_bar_arrive(empty + buf);
+      }
+      const float wgt = w.n_frames == 2 ? 0.5f : 1.0f;
+      float* o = out + r * out_ld + col0;
+#pragma unroll
+      for (int v = 0; v < kVals; ++v) {
+        const int lag = lag_of(lane, v);
+        if (lag >= 1 && lag <= t.n_lags) o[lag - 1] = acc[v] * wgt;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
                         bool reduce, float* out, int64_t out_ld, int col0) {
   const AmGeom geo = am_geom(t.F);
-  const size_t smem = static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len * sizeof(__half) + ((t.F + 3) & ~3) * sizeof(float);
-  if (smem > 220 * 1024 || t.n_lags > 191) return -1;
+  if (t.n_lags > 191) return -1;
+  const int iters = (t.F / 2 + 1 + 31) / 32;      // register-staging iterations the frame needs
+  const size_t hann_bytes = static_cast<size_t>(64) * iters * sizeof(float);   // np.hanning(F), zero padded
+  // NSF_AC_PAIRS=1 keeps the (consumer, producer) pair kernel for every F (validation / A-B timing)
+  static const bool force_pairs = std::getenv("NSF_AC_PAIRS") != nullptr;
+  const size_t trio_smem = static_cast<size_t>(kTrioGroups) * 4 * 4 * geo.len * sizeof(__half) + hann_bytes;
+  if (!force_pairs && trio_smem <= 220 * 1024) {
+    int64_t grid = (b.total_rows + kTrioGroups * 3 - 1) / (kTrioGroups * 3);
+    if (grid > kSmCount) grid = kSmCount;
+    if (grid < 1) grid = 1;
+    auto go = [&](auto kernel) {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
+      kernel<<<static_cast<int>(grid), kTrioWarps * 32, trio_smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+      return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    };
+    if (iters == 23) return go(k_autocorr_trio<23, true>);    // 88.2 kHz: F = 1470
+    if (iters == 5) return go(k_autocorr_trio<5, true>);      // 16 kHz: F = 266
+    if (iters == 12) return go(k_autocorr_trio<12, true>);    // 44.1 kHz: F = 735
+    if (iters <= 6) return go(k_autocorr_trio<6, false>);     // F <= 382   (22.05 kHz: 367)
+    if (iters <= 12) return go(k_autocorr_trio<12, false>);   // F <= 766
+    if (iters <= 24) return go(k_autocorr_trio<24, false>);   // F <= 1534  (48 kHz: 800)
+    // longer frames: the pair kernel below (its two buffers per pair still fit)
+  }
+  const size_t smem = static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len * sizeof(__half) + hann_bytes;
+  if (smem > 220 * 1024) return -1;
   int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
   int64_t grid = (b.total_rows + kAmPairs - 1) / kAmPairs;
   if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
   if (grid < 1) grid = 1;
-  const int iters = (t.F / 2 + 1 + 31) / 32;      // register-staging iterations the frame needs
   auto go = [&](auto kernel) {
     // per call: all instantiations share this lambda (same function-pointer type), so no static flag
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
     kernel<<<static_cast<int>(grid), kAmPairs * 64, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   };
-  if (iters <= 6) return go(k_autocorr_mma<6>);      // F <= 382   (16 kHz: 266, 22.05 kHz: 367)
-  if (iters <= 12) return go(k_autocorr_mma<12>);    // F <= 766   (44.1 kHz: 735)
-  if (iters <= 24) return go(k_autocorr_mma<24>);    // F <= 1534  (48 kHz: 800, 88.2 kHz: 1470)
-  if (iters <= 40) return go(k_autocorr_mma<40>);    // F <= 2558
-  return go(k_autocorr_mma<66>);                     // F <= 4096  (plan limit)
+  if (iters == 23) return go(k_autocorr_mma<23, true>);   // 88.2 kHz: F = 1470
+  if (iters == 5) return go(k_autocorr_mma<5, true>);     // 16 kHz: F = 266
+  if (iters <= 6) return go(k_autocorr_mma<6, false>);    // F <= 382   (22.05 kHz: 367)
+  if (iters <= 12) return go(k_autocorr_mma<12, false>);  // F <= 766   (44.1 kHz: 735)
+  if (iters <= 24) return go(k_autocorr_mma<24, false>);  // F <= 1534  (48 kHz: 800)
+  if (iters <= 40) return go(k_autocorr_mma<40, false>);  // F <= 2558
+  return go(k_autocorr_mma<66, false>);                   // F <= 4096  (plan limit)
 }
 
 }  // namespace nsf

@@ -7,9 +7,24 @@
 
 namespace nsf {
 
-// Largest c in [0, n) with off[c] <= g (off is a non-decreasing prefix sum, off[0] == 0).
+// Largest c in [0, n) with off[c] <= g (off is a non-decreasing prefix sum, off[0] == 0, g < off[n]).
+// Batches are usually clips of (nearly) equal length, so the proportional guess c = g n / off[n] is
+// probed first - two independent loads instead of log2(n) dependent ones (14 for the 10 000-clip
+// batches) - and only a miss falls back to the bisection, on the side of the guess that holds g.
 __device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int n, int64_t g) {
   int lo = 0, hi = n;  // invariant: off[lo] <= g < off[hi]
+  if (n > 2) {
+    const int64_t total = __ldg(off + n);
+    int c = total > 0 ? static_cast<int>(static_cast<double>(g) * static_cast<double>(n) / static_cast<double>(total)) : 0;
+    c = c < 0 ? 0 : (c > n - 1 ? n - 1 : c);
+    const int64_t a = __ldg(off + c), e = __ldg(off + c + 1);
+    if (a <= g) {
+      if (g < e) return c;
+      lo = c + 1;          // off[c + 1] <= g
+    } else {
+      hi = c;              // g < off[c]
+    }
+  }
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (__ldg(off + mid) <= g) lo = mid; else hi = mid;

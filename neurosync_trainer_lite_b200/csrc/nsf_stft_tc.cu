@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include <algorithm>
@@ -316,6 +317,148 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_tc_fold(DeviceTables t, Bat
           const float2 back = __half22float2(hi);
           dst0[(2 * cp) * pstride] = hi;
           dst0[(2 * cp + 1) * pstride] = __floats2half2_rn(va - back.x, vc - back.y);
+        }
+      }
+    }
+    __syncwarp();
+    cur = nxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tc_fold_r: register-resident variant of k_tc_fold for kp <= 64 * kIt (kIt <= 8), the product path
+// for every supported rate up to F = 2044.  k_tc_fold spends most of its time in the shared-memory
+// pipe (window pass in place, then the fold pass re-reads everything: ~420 wavefronts per frame);
+// here the frame is read from shared memory ONCE: each lane windows and folds its 2 kIt columns
+// straight into registers (the periodic Hann window satisfies w[F-j] = w[j] and w[Nh-j] = w[Nh+j], so
+// one float2 table entry (w[j], w[j+Nh]) windows all four taps), the warp reduces max|folded| - which
+// fixes the exact power-of-two scale directly (|v| 2^e in [2^13, 2^14)) - and the scaled values are
+// split and stored.  ~210 wavefronts per frame, which leaves the kernel to the HBM pipe.
+// ------------------------------------------------------------------------------------------------
+template <int kIt>
+__global__ void __launch_bounds__(kFoldWarps * 32) k_tc_fold_r(DeviceTables t, BatchView b, const float* __restrict__ y,
+                                                               __half* __restrict__ planes, int64_t plane_rows,
+                                                               int32_t* __restrict__ row_exp, int buf_floats, int wp_pairs) {
+  extern __shared__ __align__(16) float s_fold[];   // [wp_pairs] float2 window pairs, then kFoldWarps x 2 x [buf_floats]
+  __shared__ uint64_t s_bar[kFoldWarps][2];
+  const int F = t.F, kp = t.kp[0], K = t.chains == 2 ? (F / 2) / 2 + 1 : (F + 1) / 2;
+  const int Nh = F / 2;
+  const bool even = t.chains == 2;
+  const int n_cp = 2 * t.chains;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* s_wp = reinterpret_cast<float2*>(s_fold);
+  float* bufs = s_fold + 2 * wp_pairs + static_cast<size_t>(warp) * 2 * buf_floats;
+  for (int j = threadIdx.x; j < wp_pairs; j += blockDim.x) {
+    float2 w = make_float2(0.0f, 0.0f);
+    if (j < K) {
+      w.x = __ldg(t.hann_per + j);
+      w.y = even ? __ldg(t.hann_per + j + Nh) : 0.0f;
+    }
+    s_wp[j] = w;
+  }
+  if (lane == 0) {
+    mbar_init(&s_bar[warp][0], 1);
+    mbar_init(&s_bar[warp][1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kFoldWarps;
+  int64_t g = static_cast<int64_t>(blockIdx.x) * kFoldWarps + warp;
+  uint32_t phase_bits = 0u;
+  FrameRef cur;
+  if (g < b.total_frames) {
+    cur = locate_frame(t, b, y, g);
+    if (cur.fast && lane == 0) {
+      mbar_expect_tx(&s_bar[warp][0], cur.bytes);
+      bulk_load(bufs, cur.aligned, cur.bytes, &s_bar[warp][0]);
+    }
+  }
+  const int64_t pstride = plane_rows * kp / 2;           // half2 elements between planes
+  for (int it = 0; g < b.total_frames; g += stride, ++it) {
+    const int slot = it & 1;
+    const int64_t gn = g + stride;
+    FrameRef nxt;
+    nxt.fast = false;
+    if (gn < b.total_frames) {
+      nxt = locate_frame(t, b, y, gn);
+      if (nxt.fast && lane == 0) {
+        // the other buffer was last read by this warp's generic-proxy loads (and edge-frame stores)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_bar[warp][slot ^ 1], nxt.bytes);
+        bulk_load(bufs + (slot ^ 1) * buf_floats, nxt.aligned, nxt.bytes, &s_bar[warp][slot ^ 1]);
+      }
+    }
+    const float* u = bufs + slot * buf_floats;
+    if (cur.fast) {
+      mbar_wait(&s_bar[warp][slot], (phase_bits >> slot) & 1u);
+      phase_bits ^= 1u << slot;
+      u += cur.skew;
+    } else {
+      // clip edges: raw samples with the zero padding of librosa's centred STFT, staged by the lanes
+      float* ub = bufs + slot * buf_floats;
+      const float* src = y + cur.base + cur.first;
+      for (int n = lane; n < F; n += 32) {
+        const int64_t i = cur.first + n;
+        ub[n] = (i >= 0 && i < cur.len) ? __ldg(src + n) : 0.0f;
+      }
+      __syncwarp();
+    }
+    // pass 1: window + fold into registers, running max of |folded|
+    float v[kIt][2][4];
+    float vmax = 0.0f;
+#pragma unroll
+    for (int q = 0; q < kIt; ++q) {
+      const int j0 = 2 * lane + 64 * q;
+      const float4 w = j0 < wp_pairs ? *reinterpret_cast<const float4*>(s_wp + j0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float wj[2][2] = {{w.x, w.y}, {w.z, w.w}};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = j0 + h;
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+        if (j < K) {
+          if (even) {
+            const float u0 = u[j] * wj[h][0], u1 = u[j + Nh] * wj[h][1];
+            const float s = u0 + u1, d = u0 - u1;
+            if (j == 0 || 2 * j == Nh) {
+              o0 = s; o1 = s; o2 = d; o3 = d;
+            } else {
+              const float u2 = u[Nh - j] * wj[h][1], u3 = u[F - j] * wj[h][0];
+              const float s2 = u2 + u3, d2 = u3 - u2;
+              o0 = s + s2; o1 = s - s2; o2 = d + d2; o3 = d - d2;
+            }
+          } else {
+            const float u0 = u[j] * wj[h][0];
+            if (j == 0) { o0 = u0; o1 = u0; }
+            else { const float u1 = u[F - j] * wj[h][0]; o0 = u0 + u1; o1 = u0 - u1; }
+          }
+        }
+        v[q][h][0] = o0; v[q][h][1] = o1; v[q][h][2] = o2; v[q][h][3] = o3;
+        vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o0), fabsf(o1)), fmaxf(fabsf(o2), fabsf(o3))));
+      }
+    }
+    vmax = warp_max(vmax);
+    // scale = 2^e with vmax * 2^e in [2^13, 2^14): exact
+    int e2 = 0;
+    if (vmax > 0.0f && vmax < INFINITY) {
+      e2 = 14 - (static_cast<int>((__float_as_uint(vmax) >> 23) & 0xff) - 126);   // vmax = m * 2^ex, m in [0.5, 1)
+      e2 = max(-100, min(100, e2));
+    }
+    const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
+    if (lane == 0) row_exp[g] = e2;
+    // pass 2: scale, split, store (eight planes, one half2 store each)
+    __half2* dst0 = reinterpret_cast<__half2*>(planes + g * kp) + lane;
+#pragma unroll
+    for (int q = 0; q < kIt; ++q) {
+      if (2 * lane + 64 * q < kp) {
+#pragma unroll
+        for (int cp = 0; cp < 4; ++cp) {
+          if (cp < n_cp) {
+            const float va = v[q][0][cp] * scale, vc = v[q][1][cp] * scale;
+            const __half2 hi = __floats2half2_rn(va, vc);
+            const float2 back = __half22float2(hi);
+            dst0[(2 * cp) * pstride + 32 * q] = hi;
+            dst0[(2 * cp + 1) * pstride + 32 * q] = __floats2half2_rn(va - back.x, vc - back.y);
+          }
         }
       }
     }
@@ -752,15 +895,34 @@ int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
   if (!tc.ready) return -1;
   const OperandView v = view_operands(tc, b.total_frames, operands);
   const int buf_floats = ((t.F + 3) & ~3) + 8;   // frame + up to 3 floats of skew + tail, 16-byte multiple
-  const size_t smem = (static_cast<size_t>((t.F + 3) & ~3) + static_cast<size_t>(kFoldWarps) * 2 * buf_floats) * sizeof(float);
-  // per launch: the attribute is per device, and a process may drive several devices
-  if (cudaFuncSetAttribute(k_tc_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
+  const int kp = tc.kp;
+  const int iters = (kp + 63) / 64;
+  // NSF_FOLD_LEGACY=1 keeps the two-pass kernel for every F (validation / A-B timing)
+  static const bool fold_legacy = std::getenv("NSF_FOLD_LEGACY") != nullptr;
+  const bool reg_path = iters <= 8 && !fold_legacy;
+  const int wp_pairs = iters * 64;               // float2 window pairs, zero beyond K
+  const size_t head = reg_path ? static_cast<size_t>(2) * wp_pairs : static_cast<size_t>((t.F + 3) & ~3);
+  const size_t smem = (head + static_cast<size_t>(kFoldWarps) * 2 * buf_floats) * sizeof(float);
   if (smem > 220 * 1024) return -1;
   int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
   int64_t grid = (b.total_frames + kFoldWarps - 1) / kFoldWarps;
   if (grid > 148 * per_sm) grid = 148 * per_sm;
   if (grid < 1) grid = 1;
+  auto go = [&](auto kernel) {
+    // per launch: the attribute is per device, and a process may drive several devices
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
+    kernel<<<static_cast<int>(grid), kFoldWarps * 32, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp, buf_floats, wp_pairs);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  };
+  if (reg_path) {
+    if (iters <= 2) return go(k_tc_fold_r<2>);       // F <= 508   (16 kHz: 266, 22.05 kHz: 367 odd -> kp 192: 3)
+    if (iters <= 3) return go(k_tc_fold_r<3>);
+    if (iters <= 4) return go(k_tc_fold_r<4>);       // 48 kHz: F = 800, kp = 208
+    if (iters <= 6) return go(k_tc_fold_r<6>);       // 88.2 kHz: F = 1470, kp = 368; 44.1 kHz: F = 735 (odd), kp = 368
+    return go(k_tc_fold_r<8>);
+  }
+  if (cudaFuncSetAttribute(k_tc_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
   k_tc_fold<<<static_cast<int>(grid), kFoldWarps * 32, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp, buf_floats);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
