@@ -20,8 +20,6 @@
 // r[lag] / r[0].
 #include <cuda_fp16.h>
 
-#include <cstdlib>
-
 #include "nsf.h"
 #include "nsf_device_utils.cuh"
 #include "nsf_kernels.cuh"
@@ -127,38 +125,45 @@ __device__ __forceinline__ void am_process(const DeviceTables& t, const float* h
     e2 = max(-100, min(100, e2));
   }
   const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
-  // pass 2a: window, scale, split; pair e = (X(2e), X(2e+1)) goes to the E copies as one half2 each.
+  // pass 2: window, scale, split.  Pair e = (X(2e), X(2e+1)) goes to the E copies as one half2 each
+  // and, as two 16-bit stores, to the one-sample shifted O copies (O half m - 1 = X(m)): no second pass
+  // over shared memory and no warp barrier inside the frame.
   uint32_t* e_hi = reinterpret_cast<uint32_t*>(copies) + kFrontMargin / 2 + lane;
   uint32_t* e_lo = e_hi + geo.len / 2;
-  uint32_t* o_hi = e_lo + geo.len / 2;
-  uint32_t* o_lo = o_hi + geo.len / 2;
+  uint16_t* o_hi = reinterpret_cast<uint16_t*>(copies) + 2 * geo.len + kFrontMargin - 1 + 2 * lane;
+  uint16_t* o_lo = o_hi + geo.len;
   const float2* w2 = reinterpret_cast<const float2*>(hann) + lane;
   const float* nx = next_fast + 2 * lane;
+  // groups of four iterations: the four window loads of a group are issued back to back, so their
+  // shared-memory latency (long when the consumers keep the pipe busy) is paid once per group
+  constexpr int kGroup = 4;
 #pragma unroll
-  for (int i = 0; i < kIters; ++i) {
-    if (kExact || i < n_it) {
-      const float2 w = w2[32 * i];
-      const float x0 = (v0[i] - mean) * (w.x * scale);
-      const float x1 = (v1[i] - mean) * (w.y * scale);
-      if (next_fast != nullptr) {        // warp-uniform
-        v0[i] = __ldg(nx + 64 * i);
-        v1[i] = __ldg(nx + 64 * i + 1);
+  for (int i0 = 0; i0 < kIters; i0 += kGroup) {
+    float2 w[kGroup];
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j)
+      if (i0 + j < kIters && (kExact || i0 + j < n_it)) w[j] = w2[32 * (i0 + j)];
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+      const int i = i0 + j;
+      if (i < kIters && (kExact || i < n_it)) {
+        const float x0 = (v0[i] - mean) * (w[j].x * scale);
+        const float x1 = (v1[i] - mean) * (w[j].y * scale);
+        if (next_fast != nullptr) {        // warp-uniform
+          v0[i] = __ldg(nx + 64 * i);
+          v1[i] = __ldg(nx + 64 * i + 1);
+        }
+        const __half2 hi = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hi), lw = *reinterpret_cast<const uint32_t*>(&lo);
+        e_hi[32 * i] = hw;
+        e_lo[32 * i] = lw;
+        o_hi[64 * i] = static_cast<uint16_t>(hw);
+        o_hi[64 * i + 1] = static_cast<uint16_t>(hw >> 16);
+        o_lo[64 * i] = static_cast<uint16_t>(lw);
+        o_lo[64 * i + 1] = static_cast<uint16_t>(lw >> 16);
       }
-      const __half2 hi = __floats2half2_rn(x0, x1);
-      const float2 hf = __half22float2(hi);
-      const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-      e_hi[32 * i] = *reinterpret_cast<const uint32_t*>(&hi);
-      e_lo[32 * i] = *reinterpret_cast<const uint32_t*>(&lo);
-    }
-  }
-  __syncwarp();
-  // pass 2b: the one-sample shifted copies straight from the E words: O word e-1 = (X(2e-1), X(2e))
-  // = high half of E word e-1 | low half of E word e  (E word -1 is the zero margin)
-#pragma unroll
-  for (int i = 0; i < kIters; ++i) {
-    if (kExact || i < n_it) {
-      o_hi[32 * i - 1] = __funnelshift_r(e_hi[32 * i - 1], e_hi[32 * i], 16);
-      o_lo[32 * i - 1] = __funnelshift_r(e_lo[32 * i - 1], e_lo[32 * i], 16);
     }
   }
   __syncwarp();
@@ -322,6 +327,9 @@ __device__ __forceinline__ void am_bar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// (A 3-consumer : 1-producer grouping over a ring of four buffers - 12 MMA warps per SM instead of 8 in
+// the same shared memory - was measured too: 1.37 vs 1.39 ms at 88.2 kHz, 6.3 vs 4.3 ms on the 16 kHz
+// small-clip batch; the lone producer becomes the bottleneck, so the pairs stayed.)
 // Warp-specialised kernel.  A block is kAmPairs (consumer, producer) warp pairs; each pair owns two
 // frame buffers.  The producer warp fetches, windows, scales and splits frame after frame; the
 // consumer warp runs nothing but the MMA loop (plus the cheap normalise / pair-mean / store), so the
@@ -414,159 +422,6 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Trio kernel (the product path when its buffers fit): ONE block of 16 warps per SM, four groups of
-// (3 consumer warps + 1 producer warp) sharing a ring of 4 frame buffers.  The same 16 buffers per SM
-// as four (consumer, producer) pairs x 2 blocks, but 12 instead of 8 warps feed the tensor pipe: three
-// MMA warps per scheduler hide each other's fragment-load and accumulator latencies, and a producer -
-// which needs about a third of a consumer's time per frame - is no longer idle two thirds of the time.
-//
-// Schedule of a group (G = global group index, its j-th row is r = G + j * n_groups): consumer c owns
-// rows j = 3 t + c; hand-off slots are ordered  s = 6 t + 3 f + c  (f = first / second frame of the
-// row), i.e. A.f0 B.f0 C.f0 A.f1 B.f1 C.f1, so three buffers are being consumed while the fourth is
-// being filled.  Slot s lives in buffer s & 3 and is the (s >> 2)-th use of it, which fixes the
-// mbarrier parities on both sides without any shared counters.  A row with a single frame (odd T)
-// still hands over its empty second slot.
-// ------------------------------------------------------------------------------------------------
-constexpr int kTrioGroups = 4;
-constexpr int kTrioWarps = kTrioGroups * 4;
-
-struct AmRow { int64_t base, len, T, tf0; int n_frames; };
-__device__ __forceinline__ AmRow am_locate_row(const BatchView& b, int64_t r, bool reduce) {
-  AmRow w;
-  const int clip = find_segment(b.row_off, b.n_clips, r);
-  w.base = __ldg(b.clip_off + clip);
-  w.len = __ldg(b.clip_off + clip + 1) - w.base;
-  w.T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
-  const int64_t lr = r - __ldg(b.row_off + clip);
-  w.tf0 = reduce ? 2 * lr : lr;
-  w.n_frames = (reduce && w.tf0 + 1 < w.T) ? 2 : 1;   // odd T: the last row passes through
-  return w;
-}
-
-template <int kIters, bool kExact>
-__global__ void __launch_bounds__(kTrioWarps * 32, 1) k_autocorr_trio(DeviceTables t, BatchView b,
-                                                                     const float* __restrict__ y, bool reduce,
-                                                                     float* __restrict__ out, int64_t out_ld,
-                                                                     int col0) {
-  extern __shared__ __align__(16) __half s_am[];
-  __shared__ uint64_t s_bar[kTrioGroups][8];       // per group: full[4], empty[4]
-  const AmGeom geo = am_geom(t.F);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = warp & 3;                         // a group lives on one scheduler (warp % 4)
-  const int role = warp >> 2;                       // 0..2 consumers, 3 producer
-  const bool producer = role == 3;
-  const size_t buf_halfs = static_cast<size_t>(4) * geo.len;
-  __half* bufs = s_am + static_cast<size_t>(grp) * 4 * buf_halfs;
-  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(kTrioGroups) * 4 * buf_halfs);
-  const int n_it = (t.F / 2 + 1 + 31) / 32;          // register-staging iterations the frame needs
-  for (int n = threadIdx.x; n < 64 * n_it; n += blockDim.x) hann[n] = n < t.F ? __ldg(t.hann_sym + n) : 0.0f;
-  uint64_t* full = s_bar[grp];
-  uint64_t* empty = s_bar[grp] + 4;
-  if (!producer) {
-    // zero once: the margins are never written again, the frame region is rewritten per frame
-    const int words = static_cast<int>(4 * buf_halfs / 2);
-    for (int i = role * 32 + lane; i < words; i += 96) reinterpret_cast<uint32_t*>(bufs)[i] = 0u;
-  } else if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { am_bar_init(full + q, 1); am_bar_init(empty + q, 1); }
-  }
-  __syncthreads();
-  const int64_t G = static_cast<int64_t>(blockIdx.x) * kTrioGroups + grp;
-  const int64_t n_groups = static_cast<int64_t>(gridDim.x) * kTrioGroups;
-  if (producer) {
-    // software pipeline: the samples of slot n+1 are requested while slot n is being converted
-    auto row_of = [&](uint32_t tt_, int fc_) { return G + static_cast<int64_t>(3 * tt_ + (fc_ % 3)) * n_groups; };
-    auto src_of = [&](uint32_t tt_, int fc_) {
-      const AmRow w = am_locate_row(b, row_of(tt_, fc_), reduce);
-      AmSrc sc;
-      sc.valid = false;
-      if (fc_ / 3 < w.n_frames) sc = am_src(t, b, y, w.base, w.len, w.tf0 + fc_ / 3, n_it);
-      return sc;
-    };
-    uint32_t tt = 0;
-    int fc = 0;
-    bool have = G < b.total_rows;
-    float v0[kIters], v1[kIters];
-    AmSrc cur;
-    cur.valid = false;
-    if (have) {
-      cur = src_of(0, 0);
-      if (cur.valid && cur.fast) am_issue_fast<kIters, kExact>(cur.clip + cur.first, n_it, lane, v0, v1);
-    }
-    while (have) {
-      const uint32_t slot = 6u * tt + static_cast<uint32_t>(fc);
-      const uint32_t buf = slot & 3u;
-      // next slot whose row exists (rows run out only at the very end of the group's list)
-      uint32_t ntt = tt;
-      int nfc = fc;
-      bool nhave = false;
-      for (;;) {
-        if (++nfc == 6) {
-          nfc = 0;
-          ++ntt;
-          if (G + static_cast<int64_t>(3 * ntt) * n_groups >= b.total_rows) break;
-        }
-        if (row_of(ntt, nfc) < b.total_rows) { nhave = true; break; }
-      }
-      AmSrc nxt;
-      nxt.valid = false;
-      if (nhave) nxt = src_of(ntt, nfc);
-      am_bar_wait(empty + buf, ((slot >> 2) & 1u) ^ 1u);
-      const bool nxt_fast = nxt.valid && nxt.fast;
-      const float* nxt_ptr = nxt_fast ? nxt.clip + nxt.first : nullptr;
-      if (cur.valid && cur.fast) {
-        am_process<kIters, kExact>(t, hann, n_it, v0, v1, bufs + buf * buf_halfs, geo, lane, nxt_ptr);   // ends with __syncwarp
-      } else {
-        if (cur.valid) am_fill_simple(t, hann, cur, bufs + buf * buf_halfs, geo, lane);
-        if (nxt_fast) am_issue_fast<kIters, kExact>(nxt_ptr, n_it, lane, v0, v1);
-      }
-      __syncwarp();
-      if (lane == 0) am_bar_arrive(full + buf);
-      tt = ntt; fc = nfc; have = nhave; cur = nxt;
-    }
-  } else {
-    const int c = role;
-    for (uint32_t tt = 0;; ++tt) {
-      const int64_t r = G + static_cast<int64_t>(3 * tt + c) * n_groups;
-      if (r >= b.total_rows) break;
-      const AmRow w = am_locate_row(b, r, reduce);
-      float acc[kVals];
-#pragma unroll
-      for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
-#pragma unroll 1
-      for (int f = 0; f < 2; ++f) {
-        const uint32_t slot = 6u * tt + 3u * static_cast<uint32_t>(f) + static_cast<uint32_t>(c);
-        const uint32_t buf = slot & 3u;
-        __half* copies = bufs + buf * buf_halfs;
-        am_bar_wait(full + buf, (slot >> 2) & 1u);
-        if (f < w.n_frames) {
-          const int64_t tf = w.tf0 + f;
-          float val[kVals];
-          am_mma(copies, geo, lane, val);
-          // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
-          // rare, so the consumer refills the buffer it still owns itself
-          if (w.T > 1 && (tf == 0 || tf == w.T - 1) && am_all_small(val, lane, t.n_lags)) {
-            am_fill_simple(t, hann, am_src(t, b, y, w.base, w.len, tf == 0 ? 1 : w.T - 2, n_it), copies, geo, lane);
-            am_mma(copies, geo, lane, val);
-          }
-#pragma unroll
-          for (int v = 0; v < kVals; ++v) acc[v] += val[v];
-        }
-        __syncwarp();
-        if (lane == 0) am_bar_arrive(empty + buf);
-      }
-      const float wgt = w.n_frames == 2 ? 0.5f : 1.0f;
-      float* o = out + r * out_ld + col0;
-#pragma unroll
-      for (int v = 0; v < kVals; ++v) {
-        const int lag = lag_of(lane, v);
-        if (lag >= 1 && lag <= t.n_lags) o[lag - 1] = acc[v] * wgt;
-      }
-    }
-  }
-}
-
 }  // namespace
 
 int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
@@ -575,26 +430,6 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   if (t.n_lags > 191) return -1;
   const int iters = (t.F / 2 + 1 + 31) / 32;      // register-staging iterations the frame needs
   const size_t hann_bytes = static_cast<size_t>(64) * iters * sizeof(float);   // np.hanning(F), zero padded
-  // NSF_AC_PAIRS=1 keeps the (consumer, producer) pair kernel for every F (validation / A-B timing)
-  static const bool force_pairs = std::getenv("NSF_AC_PAIRS") != nullptr;
-  const size_t trio_smem = static_cast<size_t>(kTrioGroups) * 4 * 4 * geo.len * sizeof(__half) + hann_bytes;
-  if (!force_pairs && trio_smem <= 220 * 1024) {
-    int64_t grid = (b.total_rows + kTrioGroups * 3 - 1) / (kTrioGroups * 3);
-    if (grid > kSmCount) grid = kSmCount;
-    if (grid < 1) grid = 1;
-    auto go = [&](auto kernel) {
-      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
-      kernel<<<static_cast<int>(grid), kTrioWarps * 32, trio_smem, s>>>(t, b, y, reduce, out, out_ld, col0);
-      return cudaGetLastError() == cudaSuccess ? 1 : -1;
-    };
-    if (iters == 23) return go(k_autocorr_trio<23, true>);    // 88.2 kHz: F = 1470
-    if (iters == 5) return go(k_autocorr_trio<5, true>);      // 16 kHz: F = 266
-    if (iters == 12) return go(k_autocorr_trio<12, true>);    // 44.1 kHz: F = 735
-    if (iters <= 6) return go(k_autocorr_trio<6, false>);     // F <= 382   (22.05 kHz: 367)
-    if (iters <= 12) return go(k_autocorr_trio<12, false>);   // F <= 766
-    if (iters <= 24) return go(k_autocorr_trio<24, false>);   // F <= 1534  (48 kHz: 800)
-    // longer frames: the pair kernel below (its two buffers per pair still fit)
-  }
   const size_t smem = static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len * sizeof(__half) + hann_bytes;
   if (smem > 220 * 1024) return -1;
   int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));

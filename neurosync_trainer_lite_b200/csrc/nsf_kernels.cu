@@ -15,6 +15,8 @@
 
 #include "nsf.h"
 #include "nsf_device_utils.cuh"
+#include <cstdlib>
+
 #include "nsf_kernels.cuh"
 
 namespace nsf {
@@ -395,6 +397,106 @@ __global__ void __launch_bounds__(kDctWarps * 32) k_dct_sum(DeviceTables t, Batc
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 (product variant): the same arithmetic with LANES = FRAMES and NO transposition tile.  Each lane
+// reads its own dB row with 128-bit loads (a warp request touches 32 rows; the seven later requests
+// to the same 128-byte lines hit in L1, which is nearly all free here because the kernel needs only
+// 15 KB of shared memory) and feeds KP FFMAs per mel from broadcast 128-bit coefficient loads.  Without
+// the 17 KB tile per warp the SM holds 16 warps instead of 8, which is what hides the memory latency
+// (k_dct_sum: 0.131 ms on C2, long-scoreboard bound).  Accumulation order over the mels is identical
+// to k_dct_sum, so the MFCCs are bit-identical; the per-clip moments are summed over the 32 frames of a
+// tile by lane k (float64, one column each) from the staged output rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDct2Warps = 8;
+
+template <int KP>
+__global__ void __launch_bounds__(kDct2Warps * 32, 2) k_dct_rows(DeviceTables t, BatchView b,
+                                                                 const float* __restrict__ db,
+                                                                 const uint32_t* __restrict__ dbmax_key,
+                                                                 float* __restrict__ mfcc_raw,
+                                                                 double* __restrict__ sum,
+                                                                 double* __restrict__ sumsq) {
+  extern __shared__ __align__(16) float s_dctk[];   // [n_mels][KP] coefficients, then kDct2Warps x [32][n_mfcc]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_c = s_dctk;
+  float* s_o = s_dctk + t.n_mels * KP + static_cast<size_t>(warp) * 32 * t.n_mfcc;
+  for (int i = threadIdx.x; i < t.n_mels * KP; i += blockDim.x) {
+    const int m = i / KP, k = i - m * KP;
+    s_c[i] = __ldg(t.dct_t + m * 32 + k);          // dct_t is [m][32], zero padded beyond n_mfcc
+  }
+  __syncthreads();
+  const int64_t n_tiles = (b.total_frames + 31) / 32;
+  const int nq = t.n_mels >> 2;                     // n_mels is a multiple of 4 (checked by the launcher)
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * kDct2Warps + warp; tile < n_tiles;
+       tile += static_cast<int64_t>(gridDim.x) * kDct2Warps) {
+    const int64_t g0 = tile * 32;
+    const int nf = static_cast<int>(min(static_cast<int64_t>(32), b.total_frames - g0));
+    const bool valid = lane < nf;
+    const int clip = valid ? find_segment(b.frame_off, b.n_clips, g0 + lane) : -1;
+    const float floor_db = valid ? key_float(__ldg(dbmax_key + clip)) - 80.0f : 0.0f;
+    const float4* row = reinterpret_cast<const float4*>(db + (g0 + (valid ? lane : 0)) * t.n_mels);
+    float acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.0f;
+#pragma unroll 1
+    for (int q0 = 0; q0 < nq; q0 += 4) {
+      float4 x4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x4[u] = q0 + u < nq ? __ldg(row + q0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (q0 + u < nq) {
+          const float xs[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = fmaxf(xs[e], floor_db);
+            const float4* c4 = reinterpret_cast<const float4*>(s_c + (4 * (q0 + u) + e) * KP);
+#pragma unroll
+            for (int k4 = 0; k4 < KP / 4; ++k4) {
+              const float4 c = c4[k4];
+              acc[4 * k4 + 0] = fmaf(c.x, x, acc[4 * k4 + 0]);
+              acc[4 * k4 + 1] = fmaf(c.y, x, acc[4 * k4 + 1]);
+              acc[4 * k4 + 2] = fmaf(c.z, x, acc[4 * k4 + 2]);
+              acc[4 * k4 + 3] = fmaf(c.w, x, acc[4 * k4 + 3]);
+            }
+          }
+        }
+      }
+    }
+    // MFCC rows of the tile are one contiguous block of nf * n_mfcc floats: stage, then coalesced stores
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      if (k < t.n_mfcc) s_o[lane * t.n_mfcc + k] = valid ? acc[k] : 0.0f;
+    __syncwarp();
+    for (int i = lane; i < nf * t.n_mfcc; i += 32) mfcc_raw[g0 * t.n_mfcc + i] = s_o[i];
+    // moments
+    const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
+    const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
+    if (uniform) {
+      // float64 sums: the mean of a constant channel must come out exact (silence -> all-zero rows)
+      if (lane < t.n_mfcc && first_clip >= 0) {
+        double ts = 0.0, tq = 0.0;
+        for (int f = 0; f < nf; ++f) {
+          const double a = static_cast<double>(s_o[f * t.n_mfcc + lane]);
+          ts += a;
+          tq = fma(a, a, tq);
+        }
+        atomicAdd(sum + static_cast<int64_t>(first_clip) * t.n_mfcc + lane, ts);
+        atomicAdd(sumsq + static_cast<int64_t>(first_clip) * t.n_mfcc + lane, tq);
+      }
+    } else if (valid) {                              // tile straddles a clip boundary: per-frame adds
+#pragma unroll
+      for (int k = 0; k < KP; ++k)
+        if (k < t.n_mfcc) {
+          const double a = static_cast<double>(acc[k]);
+          atomicAdd(sum + static_cast<int64_t>(clip) * t.n_mfcc + k, a);
+          atomicAdd(sumsq + static_cast<int64_t>(clip) * t.n_mfcc + k, a * a);
+        }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: CMVN -> Savitzky-Golay delta / delta-delta (width 9, edges = value at frame 4 / T-5)
 //     -> pair reduction.  Thread per (output row, channel).
 //     extract_features_utils.py:5-8,21-27,33-44; librosa.feature.delta == scipy savgol 'interp'.
@@ -420,8 +522,16 @@ __global__ void __launch_bounds__(256, 3) k_delta_reduce(BatchView b, const floa
                                                          int col0) {
   const int rows_per_block = blockDim.x / 32;
   const int lane = threadIdx.x & 31, wr = threadIdx.x >> 5;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * rows_per_block + wr; r < b.total_rows;
-       r += static_cast<int64_t>(gridDim.x) * rows_per_block) {
+  // every warp owns a CONTIGUOUS run of rows: consecutive rows share eight of their ten taps (L1 hits)
+  // and almost always the clip, so the float64 CMVN constants of a (clip, channel) are formed once per
+  // run instead of once per row
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * rows_per_block;
+  const int64_t chunk = (b.total_rows + n_warps - 1) / n_warps;
+  const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * rows_per_block + wr) * chunk;
+  const int64_t r_end = min(r_begin + chunk, b.total_rows);
+  int cached_clip = -1;
+  float cached_mu = 0.0f, cached_inv = 1.0f;       // channel `lane` of cached_clip
+  for (int64_t r = r_begin; r < r_end; ++r) {
     const int clip = find_segment(b.row_off, b.n_clips, r);
     const int64_t f0 = __ldg(b.frame_off + clip);
     const int64_t T = __ldg(b.frame_off + clip + 1) - f0;
@@ -436,11 +546,17 @@ __global__ void __launch_bounds__(256, 3) k_delta_reduce(BatchView b, const floa
     for (int ch = lane; ch < C; ch += 32) {
       float mu = 0.0f, inv = 1.0f;
       if (cmvn) {
-        const double m = __ldg(sum + static_cast<int64_t>(clip) * C + ch) * inv_T;
-        // population variance from the float64 moments (sum x, sum x^2) of the float32 values
-        const double var = fmax(0.0, fma(__ldg(sumsq + static_cast<int64_t>(clip) * C + ch), inv_T, -m * m));
-        mu = static_cast<float>(m);
-        inv = __fdiv_rn(1.0f, sqrtf(static_cast<float>(var)) + 1e-10f);   // float32 std + 1e-10
+        if (ch == lane && clip == cached_clip) {
+          mu = cached_mu;
+          inv = cached_inv;
+        } else {
+          const double m = __ldg(sum + static_cast<int64_t>(clip) * C + ch) * inv_T;
+          // population variance from the float64 moments (sum x, sum x^2) of the float32 values
+          const double var = fmax(0.0, fma(__ldg(sumsq + static_cast<int64_t>(clip) * C + ch), inv_T, -m * m));
+          mu = static_cast<float>(m);
+          inv = __fdiv_rn(1.0f, sqrtf(static_cast<float>(var)) + 1e-10f);   // float32 std + 1e-10
+          if (ch == lane) { cached_mu = mu; cached_inv = inv; }
+        }
       }
       const float* col = in + f0 * in_ld + ch;
       float va = (__ldg(col + ta * in_ld) - mu) * inv, d1 = 0.0f, d2 = 0.0f;
@@ -479,6 +595,7 @@ __global__ void __launch_bounds__(256, 3) k_delta_reduce(BatchView b, const floa
         o[2 * C + ch] = d2;
       }
     }
+    cached_clip = clip;
   }
 }
 
@@ -914,6 +1031,17 @@ int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, co
                    const uint32_t* dbmax_key, float* mfcc_raw, double* sum, double* sumsq) {
   if (t.n_mels > 128 || t.n_mfcc > 32) return -1;
   const int kp = t.n_mfcc <= 24 ? 24 : 32;
+  // NSF_DCT_TILE=1 keeps the transposing-tile kernel (validation / A-B timing); it is also the path for
+  // mel counts that are not a multiple of 4 (rows would not be 16-byte aligned)
+  static const bool force_tile = std::getenv("NSF_DCT_TILE") != nullptr;
+  if (!force_tile && (t.n_mels & 3) == 0) {
+    const size_t smem2 = (static_cast<size_t>(t.n_mels) * kp + static_cast<size_t>(kDct2Warps) * 32 * t.n_mfcc) * sizeof(float);
+    const int grid2 = grid_for((b.total_frames + 31) / 32, kDct2Warps, kSmCount * 2);
+    if (kp == 24) k_dct_rows<24><<<grid2, kDct2Warps * 32, smem2, s>>>(t, b, db, dbmax_key, mfcc_raw, sum, sumsq);
+    else k_dct_rows<32><<<grid2, kDct2Warps * 32, smem2, s>>>(t, b, db, dbmax_key, mfcc_raw, sum, sumsq);
+    NSF_CHECK_LAUNCH();
+    return 1;
+  }
   const size_t smem = (static_cast<size_t>(t.n_mels) * kp + static_cast<size_t>(kDctWarps) * t.n_mels * kDctPitch) * sizeof(float);
   const int grid = grid_for((b.total_frames + 31) / 32, kDctWarps, kSmCount * 2);
   if (kp == 24) {
