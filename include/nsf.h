@@ -214,6 +214,29 @@ NSF_API nsf_status nsf_rows_host(nsf_ctx* ctx, int32_t op, int32_t dtype, const 
 NSF_API nsf_status nsf_post_host(nsf_ctx* ctx, const float* in_host, int64_t n_frames, int32_t channels,
                                  uint32_t post_flags, float* out_host);
 
+/* ---- sample-rate conversion ------------------------------------------------------------------------
+ * The resampling half of the loaders: `librosa.resample(y, orig_sr=sr, target_sr=88200)` of
+ * load_and_preprocess_audio (utils/audio/load_audio.py:8-10) and the `sr=` conversion inside
+ * `librosa.load` (:19, :25, :36).  The reference resolves both to soxr_hq, a closed-form description of
+ * which is not available here ("parity unpinned"); this entry point is the
+ * rational polyphase resampler  up/down = target_sr/orig_sr (reduced):  a Kaiser(beta = 5) windowed-sinc
+ * low-pass of 20 * max(up, down) + 1 taps, cut-off 1 / max(up, down), unit DC gain, zero-extended
+ * input, centred output of ceil(n_in * up / down) samples - the arithmetic of
+ * scipy.signal.resample_poly, evaluated per output sample in float64 on the device and rounded once
+ * to float32.  Synthetic benchmark configurations never resample.
+ *   nsf_resample_len    output length (0 when a rate is not positive)
+ *   nsf_resample_design filter of the conversion: returns the tap count 20 max(up,down)+1 and copies
+ *                       min(count, capacity) float64 taps (already scaled by `up`) when taps != NULL;
+ *                       up / down / n_pre_pad / n_pre_remove (all optional) describe the polyphase
+ *                       indexing  out[j] = sum_n h[(j + n_pre_remove) down - n_pre_pad - n up] x[n].
+ *                       Runs without a GPU.
+ *   nsf_resample_host   host PCM (float32 or int16) -> host float32 at target_sr, through the device. */
+NSF_API int64_t nsf_resample_len(int64_t n_in, int32_t orig_sr, int32_t target_sr);
+NSF_API int64_t nsf_resample_design(int32_t orig_sr, int32_t target_sr, double* taps, int64_t capacity,
+                                    int32_t* up, int32_t* down, int32_t* n_pre_pad, int32_t* n_pre_remove);
+NSF_API nsf_status nsf_resample_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format, int64_t n_in,
+                                     int32_t orig_sr, int32_t target_sr, float* out_host, int64_t out_capacity);
+
 /* ---- instrumentation -------------------------------------------------------------------------
  * Kernel launches issued by this context since creation (bench.py reports it as gpu_launches). */
 NSF_API int64_t nsf_launch_count(const nsf_ctx* ctx);

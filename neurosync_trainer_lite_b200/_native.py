@@ -81,6 +81,9 @@ _SIGS = {
                                 _vp]),
     "nsf_rows_host": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "nsf_post_host": (_i32, [_vp, _vp, _i64, _i32, _u32, _vp]),
+    "nsf_resample_len": (_i64, [_i64, _i32, _i32]),
+    "nsf_resample_design": (_i64, [_i32, _i32, _f64p, _i64, _i32p, _i32p, _i32p, _i32p]),
+    "nsf_resample_host": (_i32, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i64]),
     "nsf_launch_count": (_i64, [_vp]),
     "nsf_set_profiling": (None, [_vp, _i32]),
     "nsf_stage_times_ms": (_i32, [_vp, _f32p, _i32]),

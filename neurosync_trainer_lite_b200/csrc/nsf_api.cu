@@ -704,6 +704,40 @@ nsf_status nsf_normalize_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_fo
   return NSF_OK;
 }
 
+// ---- sample-rate conversion ------------------------------------------------------------------------
+nsf_status nsf_resample_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format, int64_t n_in, int32_t orig_sr,
+                             int32_t target_sr, float* out_host, int64_t out_capacity) {
+  if (!ctx || !pcm_host || !out_host || n_in <= 0) { set_error("nsf_resample_host: NULL argument or empty input"); return NSF_ERR_BAD_ARG; }
+  if (pcm_format != NSF_PCM_F32 && pcm_format != NSF_PCM_I16) { set_error("unknown pcm_format"); return NSF_ERR_BAD_ARG; }
+  ResampleDesign d;
+  if (!design_resampler(orig_sr, target_sr, &d)) { set_error("nsf_resample_host: rates must be positive"); return NSF_ERR_BAD_ARG; }
+  const int64_t n_out = nsf_resample_len(n_in, orig_sr, target_sr);
+  if (out_capacity < n_out) { set_error("nsf_resample_host: out_capacity < nsf_resample_len()"); return NSF_ERR_BAD_ARG; }
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  Slot* sl = &ctx->slot[0];
+  nsf_status st = ensure_slot(sl);
+  if (st != NSF_OK) return st;
+  NSF_CUDA(cudaStreamSynchronize(sl->stream));
+  // phase-major tap table [up][kmax]: row p holds h[p], h[p + up], h[p + 2 up], ...
+  const int n_taps = static_cast<int>(d.h.size());
+  const int kmax = (n_taps + d.up - 1) / d.up;
+  std::vector<double> pm(static_cast<size_t>(d.up) * kmax, 0.0);
+  for (int i = 0; i < n_taps; ++i) pm[static_cast<size_t>(i % d.up) * kmax + i / d.up] = d.h[i];
+  const size_t esz = pcm_format == NSF_PCM_I16 ? 2 : 4;
+  if ((st = sl->pcm.reserve(static_cast<size_t>(n_in) * esz)) != NSF_OK) return st;
+  if ((st = sl->ynorm.reserve(static_cast<size_t>(n_out) * sizeof(float))) != NSF_OK) return st;
+  if ((st = sl->work.reserve(pm.size() * sizeof(double))) != NSF_OK) return st;
+  NSF_CUDA(cudaMemcpyAsync(sl->work.ptr, pm.data(), pm.size() * sizeof(double), cudaMemcpyHostToDevice, sl->stream));
+  NSF_CUDA(cudaMemcpyAsync(sl->pcm.ptr, pcm_host, static_cast<size_t>(n_in) * esz, cudaMemcpyHostToDevice, sl->stream));
+  const int n = launch_resample(sl->stream, sl->pcm.ptr, pcm_format, n_in, d.up, d.down, d.n_pre_pad, d.n_pre_remove,
+                                static_cast<const double*>(sl->work.ptr), kmax, static_cast<float*>(sl->ynorm.ptr), n_out);
+  if (n < 0) { set_error(cuda_msg("launch_resample", cudaGetLastError())); return NSF_ERR_CUDA; }
+  ctx->launches += n;
+  NSF_CUDA(cudaMemcpyAsync(out_host, sl->ynorm.ptr, static_cast<size_t>(n_out) * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+  NSF_CUDA(cudaStreamSynchronize(sl->stream));     // pm (host vector) must outlive its async copy
+  return NSF_OK;
+}
+
 // ---- collect ---------------------------------------------------------------------------------------
 static nsf_status collect_offsets(const int64_t* a_off, const int64_t* f_off, int32_t n, uint32_t flags,
                                   int32_t blend_frames, const int64_t* o_off_in, std::vector<int64_t>* o_off) {

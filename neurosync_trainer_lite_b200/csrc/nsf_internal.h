@@ -48,6 +48,13 @@ struct Plan {
 };
 
 void set_error(const std::string& msg);
+
+// Polyphase resampler design (scipy.signal.resample_poly arithmetic); see nsf_resample_design in nsf.h.
+struct ResampleDesign {
+  int up = 1, down = 1, half_len = 0, n_pre_pad = 0, n_pre_remove = 0;
+  std::vector<double> h;   // 2 half_len + 1 taps, scaled by `up`
+};
+bool design_resampler(int orig_sr, int target_sr, ResampleDesign* d);
 nsf_status build_plan(int sr, int F, int H, int n_mfcc, int n_mels, int n_lags, Plan* plan);
 
 // Python-style floor division for the guard (extract_features.py:16)

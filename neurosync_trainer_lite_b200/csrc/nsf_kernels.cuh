@@ -95,6 +95,10 @@ int launch_collect(cudaStream_t s, int dtype, const CollectView& v, const void* 
 // stand-alone row helpers (interpolate_slower / smooth / one stack_with_blend step)
 int launch_rows_op(cudaStream_t s, int op, int dtype, const void* a, int64_t na, const void* b,
                    int64_t nb, int cols, int64_t k_blend, void* out, int64_t out_rows);
+// polyphase sample-rate conversion (scipy.signal.resample_poly arithmetic); taps_pm is the filter in
+// phase-major float64 layout [up][kmax] (zero beyond the last tap of a phase)
+int launch_resample(cudaStream_t s, const void* pcm, int pcm_format, int64_t n_in, int up, int down,
+                    int n_pre_pad, int n_pre_remove, const double* taps_pm, int kmax, float* out, int64_t n_out);
 // generic per-channel statistics of one [T][C] matrix and the edge fix
 int launch_col_stats(cudaStream_t s, const float* in, int64_t T, int C, double* sum, double* sumsq);
 int launch_edge_fix(cudaStream_t s, float* data, int64_t T, int C);

@@ -243,6 +243,54 @@ nsf_status build_plan(int sr, int F, int H, int n_mfcc, int n_mels, int n_lags, 
   return NSF_OK;
 }
 
+
+// ---- polyphase resampler design --------------------------------------------------------------------
+namespace {
+int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+// modified Bessel function of the first kind, order 0 (power series; x <= 5 here)
+double bessel_i0(double x) {
+  const double q = 0.25 * x * x;
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < 200; ++k) {
+    term *= q / (static_cast<double>(k) * k);
+    sum += term;
+    if (term < 1e-18 * sum) break;
+  }
+  return sum;
+}
+}  // namespace
+
+// scipy.signal.resample_poly(x, up, down): h = up * firwin(2 half_len + 1, 1/max(up,down), window=('kaiser', 5.0)),
+// half_len = 10 max(up, down); h is front-padded with n_pre_pad = down - half_len % down zeros so that the
+// output sample j is upfirdn output j + n_pre_remove, n_pre_remove = (half_len + n_pre_pad) / down.
+bool design_resampler(int orig_sr, int target_sr, ResampleDesign* d) {
+  if (orig_sr <= 0 || target_sr <= 0) return false;
+  const int g = gcd_int(target_sr, orig_sr);
+  d->up = target_sr / g;
+  d->down = orig_sr / g;
+  const int max_rate = d->up > d->down ? d->up : d->down;
+  d->half_len = 10 * max_rate;
+  const int n = 2 * d->half_len + 1;
+  const double fc = 1.0 / max_rate, alpha = 0.5 * (n - 1), beta = 5.0;
+  const double pi = 3.14159265358979323846264338327950288;
+  d->h.assign(n, 0.0);
+  const double i0b = bessel_i0(beta);
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double m = i - alpha;
+    const double arg = pi * fc * m;
+    const double sinc = m == 0.0 ? 1.0 : std::sin(arg) / arg;                  // np.sinc(fc m)
+    const double r = m / alpha;
+    const double win = bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / i0b;   // np.kaiser(n, 5)
+    d->h[i] = fc * sinc * win;
+    sum += d->h[i];
+  }
+  for (double& v : d->h) v = v / sum * d->up;                                   // unit DC gain, then * up
+  d->n_pre_pad = d->down - d->half_len % d->down;
+  d->n_pre_remove = (d->half_len + d->n_pre_pad) / d->down;
+  return true;
+}
+
 }  // namespace nsf
 
 // ------------------------------------------------------------------------------------------------
@@ -382,6 +430,27 @@ nsf_status nsf_plan_fold_check(const nsf_plan* plan, const float* frame, double*
     }
   }
   return NSF_OK;
+}
+
+
+int64_t nsf_resample_len(int64_t n_in, int32_t orig_sr, int32_t target_sr) {
+  nsf::ResampleDesign d;
+  if (n_in <= 0 || !nsf::design_resampler(orig_sr, target_sr, &d)) return 0;
+  const int64_t n_up = n_in * d.up;
+  return n_up / d.down + (n_up % d.down != 0);
+}
+
+int64_t nsf_resample_design(int32_t orig_sr, int32_t target_sr, double* taps, int64_t capacity, int32_t* up,
+                            int32_t* down, int32_t* n_pre_pad, int32_t* n_pre_remove) {
+  nsf::ResampleDesign d;
+  if (!nsf::design_resampler(orig_sr, target_sr, &d)) { nsf::set_error("nsf_resample_design: rates must be positive"); return 0; }
+  if (up) *up = d.up;
+  if (down) *down = d.down;
+  if (n_pre_pad) *n_pre_pad = d.n_pre_pad;
+  if (n_pre_remove) *n_pre_remove = d.n_pre_remove;
+  const int64_t n = static_cast<int64_t>(d.h.size());
+  if (taps) for (int64_t i = 0; i < n && i < capacity; ++i) taps[i] = d.h[i];
+  return n;
 }
 
 }  // extern "C"

@@ -191,6 +191,21 @@ class Engine:
                                                nv.ptr(y), None))
         return y
 
+    def resample_host(self, pcm, orig_sr, target_sr):
+        """``librosa.resample(y, orig_sr=, target_sr=)`` stand-in on the device (load_audio.py:8-10):
+        rational polyphase filter, scipy.signal.resample_poly arithmetic (see include/nsf.h) ->
+        float32 host array of ``nsf_resample_len`` samples."""
+        pcm = np.ascontiguousarray(pcm)
+        fmt = self._pcm_format(pcm)
+        n_out = int(nv.lib.nsf_resample_len(len(pcm), int(orig_sr), int(target_sr)))
+        out = np.empty(n_out, dtype=np.float32)
+        if n_out == 0:
+            return out
+        with self._lock:
+            nv.check(nv.lib.nsf_resample_host(self.handle, nv.ptr(pcm), fmt, len(pcm), int(orig_sr),
+                                              int(target_sr), nv.ptr(out), n_out))
+        return out
+
     # ---- device buffers (torch used for memory and streams only) -------------------------------
     def workspace_bytes(self, total_samples, n_clips, flags=0):
         return nv.lib.nsf_workspace_bytes(self.plan.handle, int(total_samples), int(n_clips), flags)

@@ -9,9 +9,11 @@ Division of labour
 * **peak normalisation** ``y / max|y|`` (reference ``load_audio.py:12-14``) runs on the GPU through
   ``nsf_normalize_host`` - or, on the feature path, fused into ``nsf_extract_host`` via
   ``NSF_PEAK_NORMALIZE`` so the PCM crosses PCIe once, as int16 when the file is int16.
-* **resampling** (only when the file's rate differs from the requested one) is a host polyphase
-  filter.  The reference uses ``soxr_hq``, which is not available here, so this step is *not*
-  parity-pinned; the synthetic benchmark configurations never resample.
+* **resampling** (only when the file's rate differs from the requested one) runs on the GPU through
+  ``nsf_resample_host``: a rational polyphase filter with the arithmetic of
+  ``scipy.signal.resample_poly`` (Kaiser-windowed sinc), checked against a float64 NumPy oracle.  The
+  reference uses ``soxr_hq``, whose filter is not reproducible here, so this step is *not*
+  parity-pinned against the reference; the synthetic benchmark configurations never resample.
 """
 import io
 import struct
@@ -69,14 +71,10 @@ def decode_wav(data):
     return np.ascontiguousarray(x, dtype=np.float32), sr
 
 
-def _resample_host(y, orig_sr, target_sr):
-    """Polyphase resampling on the host (stands in for librosa's soxr_hq; not parity-pinned)."""
-    from math import gcd
-
-    from scipy.signal import resample_poly
-    y = _as_float(np.asarray(y))
-    g = gcd(int(orig_sr), int(target_sr))
-    return resample_poly(y, int(target_sr) // g, int(orig_sr) // g).astype(np.float32)
+def _resample(y, orig_sr, target_sr):
+    """``librosa.resample`` stand-in on the device (not parity-pinned against soxr_hq, see above)."""
+    f, h = _engine.frame_params(int(target_sr))
+    return _engine.get_engine(int(target_sr), f, h).resample_host(np.asarray(y), orig_sr, target_sr)
 
 
 def _read(source):
@@ -92,7 +90,7 @@ def decode(source, sr):
     """``librosa.load(source, sr=sr)`` without the normalisation: (pcm int16|float32, sr)."""
     pcm, native = decode_wav(_read(source))
     if sr is not None and native != sr:
-        pcm = _resample_host(pcm, native, sr)
+        pcm = _resample(pcm, native, sr)
         native = sr
     return pcm, native
 
@@ -119,7 +117,7 @@ def decode_for_path(audio_path, sr=88200):
     pcm, sr = decode(audio_path, sr)
     print(f"Loaded audio file '{audio_path}' with sample rate {sr}")
     if sr != REFERENCE_RATE:                                     # load_audio.py:8-10
-        pcm = _resample_host(_as_float(pcm), sr, REFERENCE_RATE)
+        pcm = _resample(pcm, sr, REFERENCE_RATE)
         sr = REFERENCE_RATE
     return pcm, sr
 

@@ -1,0 +1,56 @@
+"""CPU oracle of the sample-rate conversion step (TEST INFRASTRUCTURE ONLY - never imported by the
+product package).
+
+The reference resamples through librosa (``librosa.resample`` at ``utils/audio/load_audio.py:9``,
+``librosa.load(..., sr=sr)`` at :19, :25, :36), i.e. soxr_hq - a third-party filter that is neither
+vendored in /root/reference nor installable here, so THIS STEP IS PARITY-UNPINNED against the
+reference.  What the product implements, and what this file restates in
+plain float64 NumPy, is the rational polyphase resampler of ``scipy.signal.resample_poly``:
+
+    up/down = target_sr/orig_sr (reduced),  half_len = 10 max(up, down)
+    h = up * firwin(2 half_len + 1, 1 / max(up, down), window=('kaiser', 5.0))
+    out[j] = sum_n hpad[(j + n_pre_remove) down - n up] x[n],   j < ceil(len(x) up / down)
+    hpad = n_pre_pad zeros ++ h,  n_pre_pad = down - half_len % down,
+    n_pre_remove = (half_len + n_pre_pad) // down
+
+``tests/test_resample.py`` pins it to scipy itself (taps against ``scipy.signal.firwin``, output
+against ``scipy.signal.resample_poly`` on float64 input).
+"""
+from math import gcd
+
+import numpy as np
+
+
+def design(orig_sr, target_sr):
+    """-> (up, down, half_len, n_pre_pad, n_pre_remove, h float64)."""
+    g = gcd(int(orig_sr), int(target_sr))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    max_rate = max(up, down)
+    half_len = 10 * max_rate
+    n = 2 * half_len + 1
+    fc = 1.0 / max_rate
+    m = np.arange(n, dtype=np.float64) - 0.5 * (n - 1)
+    h = fc * np.sinc(fc * m) * np.kaiser(n, 5.0)
+    h = h / h.sum() * up
+    n_pre_pad = down - half_len % down
+    return up, down, half_len, n_pre_pad, (half_len + n_pre_pad) // down, h
+
+
+def resample(x, orig_sr, target_sr):
+    """float64 polyphase resampling of a 1-D signal (direct evaluation of the sum above)."""
+    x = np.asarray(x, dtype=np.float64)
+    up, down, half_len, n_pre_pad, n_pre_remove, h = design(orig_sr, target_sr)
+    n_in = len(x)
+    n_out = (n_in * up) // down + ((n_in * up) % down != 0)
+    out = np.zeros(n_out, dtype=np.float64)
+    j = np.arange(n_out, dtype=np.int64)
+    t = (j + n_pre_remove) * down - n_pre_pad
+    n_hi = t // up
+    phase = t - n_hi * up
+    kmax = (len(h) + up - 1) // up
+    for k in range(kmax):
+        q = phase + k * up              # tap index
+        n = n_hi - k                    # input index
+        ok = (q < len(h)) & (n >= 0) & (n < n_in)
+        out[ok] += h[q[ok]] * x[n[ok]]
+    return out
