@@ -116,6 +116,57 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants -----------------------------------------------------------
+// Two CTAs of one cluster (same TPC) execute ONE tcgen05.mma of M = 256: each supplies its own 128 rows
+// of A and HALF of the N rows of B from its own shared memory, and receives its 128 accumulator rows in
+// its own TMEM.  Only the leader (cluster rank 0) issues MMAs; both issue TMA loads whose completion
+// bytes land on the LEADER's mbarrier (peer bit of the shared::cluster address cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar,
+                                                 int32_t x, int32_t y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask),
+        "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {      // arrive on the even CTA's barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once the pair's previous MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -793,6 +844,213 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_tc_stft_mel_pair: the fused kernel on CTA PAIRS (product path).  k_tc_stft_mel is bound by operand
+// delivery L2 -> shared memory (every CTA streams the whole DFT matrix for each 128 frames; the kernel
+// sustains ~80 % of the L2 throughput cap with the tensor pipe 40 % active).  Here a cluster of two CTAs
+// works on 256 frames with tcgen05.mma.cta_group::2 (M = 256): each CTA still loads its own 128 frame rows
+// of A but only HALF of every DFT-matrix tile (64 of the 128 bin rows), the tensor cores read the other
+// half from the peer's shared memory.  Operand bytes per CTA and stage drop from 64 KB to 48 KB, which
+// also makes room for a third pipeline stage.
+//   hand-off: full[s]       leader's barrier; the leader's producer posts the bytes of BOTH CTAs, both
+//                           CTAs' TMA loads complete on it (peer bit cleared)
+//             empty[s]      per CTA; tcgen05.commit multicast from the leader's MMA thread
+//             tmem_full[b]  per CTA; tcgen05.commit multicast
+//             tmem_empty[b] leader's barrier, 8 arrivals: the four epilogue warps of both CTAs
+// Epilogue, mel accumulation and outputs are those of k_tc_stft_mel (each CTA owns its 128 rows).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPStages = 3;
+constexpr int kPTileA = BM * BK * 2;                 // 16 KiB: 128 frame rows
+constexpr int kPTileB = (BN / 2) * BK * 2;           // 8 KiB: 64 of the 128 bin rows
+constexpr int kPStageBytes = 2 * kPTileA + 2 * kPTileB;
+constexpr size_t kPairSmem = 1024 + static_cast<size_t>(kPStages) * kPStageBytes +
+                             static_cast<size_t>(BM) * kMelPitch * sizeof(float) + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   DeviceTables t, BatchView b, int64_t plane_rows, int kp, int np_ld,
+                   const int32_t* __restrict__ row_exp, float* __restrict__ db, uint32_t* __restrict__ dbmax_key) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* mel_acc = reinterpret_cast<float*>(smem + kPStages * kPStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPStages * kPStageBytes + BM * kMelPitch * sizeof(float));
+  uint64_t* empty_bar = full_bar + kPStages;
+  uint64_t* tmem_full = empty_bar + kPStages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int kblocks = (kp + BK - 1) / BK;
+  const int ntile[2] = {(t.np[0] + BN - 1) / BN, t.chains > 1 ? (t.np[1] + BN - 1) / BN : 0};
+  const int n_sub = ntile[0] + ntile[1];
+  const int64_t n_ptiles = (b.total_frames + 2 * BM - 1) / (2 * BM);
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int i = 0; i < kPStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  for (int i = threadIdx.x; i < BM * kMelPitch; i += blockDim.x) mel_acc[i] = 0.0f;
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // the peer's barriers are initialised before any remote arrive
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+        const int64_t g0 = pt * 2 * BM + static_cast<int64_t>(rank) * BM;      // this CTA's 128 frames
+        for (int sub = 0; sub < n_sub; ++sub) {
+          const int chain = sub < ntile[0] ? 0 : 1;
+          const int n0 = (chain == 0 ? sub : sub - ntile[0]) * BN + static_cast<int>(rank) * (BN / 2);
+          for (int part = 0; part < 2; ++part) {
+            const int cp = chain * 2 + part;
+            const int64_t a_row = static_cast<int64_t>(cp * 2) * plane_rows + g0;
+            const int b_row = (cp * 2) * np_ld + n0;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+              const int stage = it % kPStages;
+              mbar_wait(empty_bar + stage, ((it / kPStages) & 1) ^ 1);
+              uint8_t* st = tiles + stage * kPStageBytes;
+              if (leader) mbar_expect_tx(full_bar + stage, 2 * kPStageBytes);  // both CTAs' bytes
+              const int kx = kb * BK;
+              tma_load_2d_pair(st, &map_a, full_bar + stage, kx, static_cast<int32_t>(a_row));
+              tma_load_2d_pair(st + kPTileA, &map_a, full_bar + stage, kx, static_cast<int32_t>(a_row + plane_rows));
+              tma_load_2d_pair(st + 2 * kPTileA, &map_b, full_bar + stage, kx, b_row);
+              tma_load_2d_pair(st + 2 * kPTileA + kPTileB, &map_b, full_bar + stage, kx, b_row + np_ld);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      uint32_t it = 0, acc_it = 0;
+      for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+        for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
+          const uint32_t buf = acc_it & 1u;
+          mbar_wait(tmem_empty + buf, ((acc_it >> 1) & 1u) ^ 1u);     // both epilogues have drained this buffer
+          tcgen05_fence_after();
+          for (int part = 0; part < 2; ++part) {
+            const uint32_t d_tmem = tmem_base + buf * 256u + static_cast<uint32_t>(part * BN);
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+              const int stage = it % kPStages;
+              mbar_wait(full_bar + stage, (it / kPStages) & 1);
+              tcgen05_fence_after();
+              const uint32_t st = smem_u32(tiles + stage * kPStageBytes);
+              const int ksteps = min(BK / UK, (kp - kb * BK + UK - 1) / UK);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t koff = static_cast<uint32_t>(k * UK * 2);
+                const uint64_t a_hi = make_smem_desc(st + koff);
+                const uint64_t a_lo = make_smem_desc(st + kPTileA + koff);
+                const uint64_t b_hi = make_smem_desc(st + 2 * kPTileA + koff);
+                const uint64_t b_lo = make_smem_desc(st + 2 * kPTileA + kPTileB + koff);
+                umma_f16_pair(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+                umma_f16_pair(d_tmem, a_lo, b_hi, idesc, 1u);
+              }
+              umma_commit_pair(empty_bar + stage);
+            }
+          }
+          umma_commit_pair(tmem_full + buf);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;          // frame row of the tile owned by this thread
+    float* my_acc = mel_acc + row * kMelPitch;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t acc_it = 0;
+    for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+      const int64_t tile0 = pt * 2 * BM + static_cast<int64_t>(rank) * BM;
+      const int64_t g = tile0 + row;
+      const bool row_ok = g < b.total_frames;
+      const float sc = row_ok ? ldexpf(1.0f, -(__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+      for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
+        const int chain = sub < ntile[0] ? 0 : 1;
+        const int n0 = (chain == 0 ? sub : sub - ntile[0]) * BN;
+        const float4* tab = t.mel_col[chain] + n0;
+        const uint32_t buf = acc_it & 1u;
+        mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
+        tcgen05_fence_after();
+        int cur_m = -1;
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 1
+        for (int j = 0; j < BN; j += 32) {
+          float re[32], im[32];
+          tmem_ld_32x32(lane_addr + buf * 256u + static_cast<uint32_t>(j), re);
+          tmem_ld_32x32(lane_addr + buf * 256u + static_cast<uint32_t>(BN + j), im);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const float4 e = __ldg(tab + j + q);          // warp-uniform address: one broadcast load
+            const int m0 = __float_as_int(e.x);
+            // rows beyond the batch may hold another plane's data: keep them out of the arithmetic
+            const float a = row_ok ? re[q] * sc : 0.0f, c = row_ok ? im[q] * sc : 0.0f;
+            const float pw = fmaf(a, a, c * c);
+            if (m0 != cur_m) {                             // uniform branch
+              if (cur_m >= 0) { my_acc[cur_m] += s0; my_acc[cur_m + 1] += s1; }
+              cur_m = m0; s0 = 0.0f; s1 = 0.0f;
+            }
+            s0 = fmaf(pw, e.y, s0);
+            s1 = fmaf(pw, e.z, s1);
+          }
+        }
+        if (cur_m >= 0) { my_acc[cur_m] += s0; my_acc[cur_m + 1] += s1; }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tmem_empty + buf);
+      }
+      float vmax = -INFINITY;
+      for (int m = 0; m < t.n_mels; ++m) {
+        const float v = 10.0f * log10f(fmaxf(1e-10f, my_acc[m]));
+        my_acc[m] = v;
+        vmax = fmaxf(vmax, v);
+      }
+      __syncwarp();
+      const int64_t gw = tile0 + quarter * 32;          // first frame of this warp's 32 rows
+      for (int r = 0; r < 32; ++r) {
+        if (gw + r < b.total_frames) {
+          const float* src = mel_acc + (quarter * 32 + r) * kMelPitch;
+          for (int m = lane; m < t.n_mels; m += 32) db[(gw + r) * t.n_mels + m] = src[m];
+        }
+      }
+      __syncwarp();
+      for (int m = 0; m < kMelPitch; ++m) my_acc[m] = 0.0f;
+      {
+        const int clip = row_ok ? find_segment(b.frame_off, b.n_clips, g) : -1;
+        const uint32_t key = row_ok ? float_key(vmax) : 0u;
+        const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
+        const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
+        if (uniform) {
+          uint32_t k = key;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, o));
+          if (lane == 0 && first_clip >= 0) atomicMax(dbmax_key + first_clip, k);
+        } else if (clip >= 0) {
+          atomicMax(dbmax_key + clip, key);
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();                               // neither CTA leaves while the pair's MMAs may still read it
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -823,7 +1081,8 @@ bool encode_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-inline int64_t plane_rows_for(int64_t frames) { return (frames + BM - 1) / BM * BM; }
+// whole CTA-pair tiles (256 frames): the peer CTA of the last pair then never reads into the next plane
+inline int64_t plane_rows_for(int64_t frames) { return (frames + 2 * BM - 1) / (2 * BM) * (2 * BM); }
 
 }  // namespace
 
@@ -865,6 +1124,10 @@ nsf_status bind_stft_tc_tables(const Plan& p, const StftTcHostBlob& blob, const 
   out->col_off[1] = p.chain[0].np;
   if (!encode_map(&out->map_b, dev_ptr, static_cast<uint64_t>(blob.planes) * blob.np_ld, blob.kp, BN)) {
     set_error("cuTensorMapEncodeTiled failed for the DFT matrix");
+    return NSF_ERR_CUDA;
+  }
+  if (!encode_map(&out->map_b_half, dev_ptr, static_cast<uint64_t>(blob.planes) * blob.np_ld, blob.kp, BN / 2)) {
+    set_error("cuTensorMapEncodeTiled failed for the DFT matrix (half tiles)");
     return NSF_ERR_CUDA;
   }
   out->ready = true;
@@ -933,6 +1196,19 @@ int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTable
   const OperandView v = view_operands(tc, b.total_frames, operands);
   CUtensorMap map_a;
   if (!encode_map(&map_a, v.planes, static_cast<uint64_t>(tc.chains) * 4 * v.rows, tc.kp, BM)) return -1;
+  // NSF_STFT_1CTA=1 keeps the single-CTA kernel (validation / A-B timing)
+  static const bool one_cta = std::getenv("NSF_STFT_1CTA") != nullptr;
+  if (!one_cta) {
+    if (cudaFuncSetAttribute(k_tc_stft_mel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kPairSmem)) != cudaSuccess)
+      return -1;
+    int64_t pairs = v.rows / (2 * BM);
+    if (pairs > 74) pairs = 74;
+    if (pairs < 1) pairs = 1;
+    k_tc_stft_mel_pair<<<static_cast<unsigned>(2 * pairs), kThreads, kPairSmem, s>>>(
+        map_a, tc.map_b_half, t, b, v.rows, tc.kp, tc.np_ld, v.row_exp, db, dbmax_key);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   if (cudaFuncSetAttribute(k_tc_stft_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)) !=
       cudaSuccess)
     return -1;

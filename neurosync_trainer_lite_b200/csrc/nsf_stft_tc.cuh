@@ -26,7 +26,8 @@ struct StftTcTables {
   int kp = 0, np_ld = 0, chains = 0;
   int np[2] = {0, 0};
   int col_off[2] = {0, 0};   // column of chain c inside a power row (chain-major layout)
-  CUtensorMap map_b;
+  CUtensorMap map_b;        // box of 128 bin rows (single-CTA kernels)
+  CUtensorMap map_b_half;   // box of 64 bin rows (CTA-pair kernel: each CTA loads half of a tile)
   bool ready = false;
 };
 
