@@ -183,6 +183,20 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One lane of a fully converged warp (elect.sync).  The MMA warp runs its loops with all 32 lanes and
+// issues through the elected one: inside an `if (lane == 0)` region the compiler cannot prove that a
+// single thread is active and wraps every tcgen05 instruction in an ELECT / BRA.U.ANY retry loop, which
+// made instruction issue - not operand delivery - the limit of the first version of these kernels.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major, 128B-swizzled operand tile: rows are 128 bytes, 8-row groups are 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -725,36 +739,40 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
-      uint32_t it = 0, acc_it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
-          const uint32_t buf = acc_it & 1u;
-          mbar_wait(tmem_empty + buf, ((acc_it >> 1) & 1u) ^ 1u);     // epilogue has drained this buffer
-          tcgen05_fence_after();
-          for (int part = 0; part < 2; ++part) {
-            const uint32_t d_tmem = tmem_base + buf * 256u + static_cast<uint32_t>(part * BN);
-            for (int kb = 0; kb < kblocks; ++kb, ++it) {
-              const int stage = it % kFStages;
-              mbar_wait(full_bar + stage, (it / kFStages) & 1);
-              tcgen05_fence_after();
+    // all 32 lanes walk the schedule (and wait on the barriers) together; one elected lane issues.
+    // Descriptors of a stage are formed once; a K step of 16 fp16 = 32 bytes is +2 in the address field.
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+    uint32_t it = 0, acc_it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
+        const uint32_t buf = acc_it & 1u;
+        mbar_wait(tmem_empty + buf, ((acc_it >> 1) & 1u) ^ 1u);     // epilogue has drained this buffer
+        tcgen05_fence_after();
+        for (int part = 0; part < 2; ++part) {
+          const uint32_t d_tmem = tmem_base + buf * 256u + static_cast<uint32_t>(part * BN);
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const int stage = it % kFStages;
+            mbar_wait(full_bar + stage, (it / kFStages) & 1);
+            tcgen05_fence_after();
+            if (elect_one()) {
               const uint32_t st = smem_u32(tiles + stage * kStageBytes);
+              const uint64_t a_hi = make_smem_desc(st + 0 * kTileBytes), a_lo = make_smem_desc(st + 1 * kTileBytes);
+              const uint64_t b_hi = make_smem_desc(st + 2 * kTileBytes), b_lo = make_smem_desc(st + 3 * kTileBytes);
               const int ksteps = min(BK / UK, (kp - kb * BK + UK - 1) / UK);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t koff = static_cast<uint32_t>(k * UK * 2);
-                const uint64_t a_hi = make_smem_desc(st + 0 * kTileBytes + koff);
-                const uint64_t a_lo = make_smem_desc(st + 1 * kTileBytes + koff);
-                const uint64_t b_hi = make_smem_desc(st + 2 * kTileBytes + koff);
-                const uint64_t b_lo = make_smem_desc(st + 3 * kTileBytes + koff);
-                umma_f16(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
-                umma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / UK; ++k) {
+                if (k < ksteps) {
+                  const uint64_t ko = static_cast<uint64_t>(k * ((UK * 2) >> 4));
+                  umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+                  umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                  umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                }
               }
               umma_commit(empty_bar + stage);
+              if (part == 1 && kb == kblocks - 1) umma_commit(tmem_full + buf);
             }
+            __syncwarp();
           }
-          umma_commit(tmem_full + buf);
         }
       }
     }
@@ -932,7 +950,7 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {                                    // warp-uniform: the whole warp walks the schedule
       constexpr uint32_t idesc = make_idesc(2 * BM, BN);
       uint32_t it = 0, acc_it = 0;
       for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
@@ -946,22 +964,26 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
               const int stage = it % kPStages;
               mbar_wait(full_bar + stage, (it / kPStages) & 1);
               tcgen05_fence_after();
-              const uint32_t st = smem_u32(tiles + stage * kPStageBytes);
-              const int ksteps = min(BK / UK, (kp - kb * BK + UK - 1) / UK);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t koff = static_cast<uint32_t>(k * UK * 2);
-                const uint64_t a_hi = make_smem_desc(st + koff);
-                const uint64_t a_lo = make_smem_desc(st + kPTileA + koff);
-                const uint64_t b_hi = make_smem_desc(st + 2 * kPTileA + koff);
-                const uint64_t b_lo = make_smem_desc(st + 2 * kPTileA + kPTileB + koff);
-                umma_f16_pair(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                umma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1u);
-                umma_f16_pair(d_tmem, a_lo, b_hi, idesc, 1u);
+              if (elect_one()) {
+                const uint32_t st = smem_u32(tiles + stage * kPStageBytes);
+                const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + kPTileA);
+                const uint64_t b_hi = make_smem_desc(st + 2 * kPTileA), b_lo = make_smem_desc(st + 2 * kPTileA + kPTileB);
+                const int ksteps = min(BK / UK, (kp - kb * BK + UK - 1) / UK);
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k) {
+                  if (k < ksteps) {
+                    const uint64_t ko = static_cast<uint64_t>(k * ((UK * 2) >> 4));
+                    umma_f16_pair(d_tmem, a_hi + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_f16_pair(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                    umma_f16_pair(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                  }
+                }
+                umma_commit_pair(empty_bar + stage);
+                if (part == 1 && kb == kblocks - 1) umma_commit_pair(tmem_full + buf);
               }
-              umma_commit_pair(empty_bar + stage);
+              __syncwarp();
             }
           }
-          umma_commit_pair(tmem_full + buf);
         }
       }
     }
@@ -1198,7 +1220,10 @@ int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTable
   if (!encode_map(&map_a, v.planes, static_cast<uint64_t>(tc.chains) * 4 * v.rows, tc.kp, BM)) return -1;
   // NSF_STFT_1CTA=1 keeps the single-CTA kernel (validation / A-B timing)
   static const bool one_cta = std::getenv("NSF_STFT_1CTA") != nullptr;
-  if (!one_cta) {
+  // short K (16 kHz: two 64-column stages per accumulator) leaves the pair's longer hand-off exposed:
+  // measured 3.31 vs 3.06 ms on the C5 batch, so pairs are used from four K stages on
+  const int kblocks = (tc.kp + BK - 1) / BK;
+  if (!one_cta && kblocks >= 4) {
     if (cudaFuncSetAttribute(k_tc_stft_mel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(kPairSmem)) != cudaSuccess)
       return -1;
