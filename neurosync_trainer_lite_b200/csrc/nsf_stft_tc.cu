@@ -183,6 +183,27 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 accumulator columns of this thread's TMEM lane, asynchronously: the registers are valid only after
+// tmem_wait_ld() on the same arrays.  The wait lists the registers as read-write operands so that the
+// compiler cannot schedule a use in front of it.
+__device__ __forceinline__ void tmem_ld_32x16_async(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld(float (&a)[16], float (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]),
+                 "+f"(a[8]), "+f"(a[9]), "+f"(a[10]), "+f"(a[11]), "+f"(a[12]), "+f"(a[13]), "+f"(a[14]), "+f"(a[15]),
+                 "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]),
+                 "+f"(b[8]), "+f"(b[9]), "+f"(b[10]), "+f"(b[11]), "+f"(b[12]), "+f"(b[13]), "+f"(b[14]), "+f"(b[15])
+               :
+               : "memory");
+}
+
 // One lane of a fully converged warp (elect.sync).  The MMA warp runs its loops with all 32 lanes and
 // issues through the elected one: inside an `if (lane == 0)` region the compiler cannot prove that a
 // single thread is active and wraps every tcgen05 instruction in an ELECT / BRA.U.ANY retry loop, which
@@ -663,6 +684,51 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue of one 128-bin sub-tile, shared by the fused kernels.  The thread owns one frame row (one TMEM
+// lane) and walks the 128 Re / Im accumulator columns in chunks of 16, the TMEM loads of chunk c+1 in
+// flight while chunk c is consumed.  |X|^2 is formed from the RAW accumulators; the frame's power-of-two
+// scale sc2 = 2^(-2 (row_exp + 14)) is applied when a filter pair is flushed (exact, so the result does
+// not depend on where the scaling happens).  A bin lies under at most two adjacent triangular filters
+// (m0, m0 + 1): running sums are kept for the current pair and added to the row of the mel tile in shared
+// memory when m0 changes (rows beyond the batch are pointed at a scratch row by the caller, so the hot loop
+// carries no validity test).  tab: the sub-tile's table entries {bits(m0), w[m0], w[m0+1], 0} (global,
+// read-only path: the 16 warp-uniform loads of a chunk are issued together, ahead of its arithmetic).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mel_accumulate_subtile(uint32_t acc_addr, const float4* __restrict__ tab,
+                                                       float* my_acc, float sc2) {
+  float re[2][16], im[2][16];
+  tmem_ld_32x16_async(acc_addr, re[0]);
+  tmem_ld_32x16_async(acc_addr + BN, im[0]);
+  tmem_wait_ld(re[0], im[0]);
+  int cur_m = -1;
+  float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+  for (int c = 0; c < BN / 16; ++c) {
+    const int cur = c & 1, nxt = cur ^ 1;
+    if (c + 1 < BN / 16) {
+      tmem_ld_32x16_async(acc_addr + 16 * (c + 1), re[nxt]);
+      tmem_ld_32x16_async(acc_addr + BN + 16 * (c + 1), im[nxt]);
+    }
+    float4 e[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) e[q] = __ldg(tab + 16 * c + q);       // warp-uniform addresses: broadcast
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int m0 = __float_as_int(e[q].x);
+      const float pw = fmaf(re[cur][q], re[cur][q], im[cur][q] * im[cur][q]);
+      if (m0 != cur_m) {                               // uniform branch
+        if (cur_m >= 0) { my_acc[cur_m] += s0 * sc2; my_acc[cur_m + 1] += s1 * sc2; }
+        cur_m = m0; s0 = 0.0f; s1 = 0.0f;
+      }
+      s0 = fmaf(pw, e[q].y, s0);
+      s1 = fmaf(pw, e[q].z, s1);
+    }
+    if (c + 1 < BN / 16) tmem_wait_ld(re[nxt], im[nxt]);
+  }
+  if (cur_m >= 0) { my_acc[cur_m] += s0 * sc2; my_acc[cur_m + 1] += s1 * sc2; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_tc_stft_mel: PERSISTENT fused kernel, one CTA per SM looping over tiles of 128 hop-frames.
 // For every tile it runs the (chain, 128-bin) sub-tiles back to back; TMEM holds two 256-column
 // accumulator buffers (Re | Im), so the tensor pipe works on sub-tile s+1 while the epilogue warps
@@ -674,18 +740,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 constexpr int kFStages = 2;
 constexpr int kMelPitch = 129;                       // floats per frame row of the mel tile
+// BM frame rows + one scratch row (sink for rows beyond the batch), rounded so the mbarriers that follow
+// stay 8-byte aligned
+constexpr size_t kMelTileBytes = (static_cast<size_t>(BM + 1) * kMelPitch * sizeof(float) + 15) / 16 * 16;
 constexpr size_t kFusedSmem = 1024 + static_cast<size_t>(kFStages) * kStageBytes +
-                              static_cast<size_t>(BM) * kMelPitch * sizeof(float) + 256;
+                              kMelTileBytes + 256;
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               DeviceTables t, BatchView b, int64_t plane_rows, int kp, int np_ld,
               const int32_t* __restrict__ row_exp, float* __restrict__ db, uint32_t* __restrict__ dbmax_key) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128-byte swizzle) by OFFSETTING the shared array, not by rounding a generic pointer:
+  // the compiler then keeps the shared address space and emits LDS / STS for the mel tile
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* tiles = smem;
   float* mel_acc = reinterpret_cast<float*>(smem + kFStages * kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kFStages * kStageBytes + BM * kMelPitch * sizeof(float));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kFStages * kStageBytes + kMelTileBytes);
   uint64_t* empty_bar = full_bar + kFStages;
   uint64_t* tmem_full = empty_bar + kFStages;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
@@ -780,12 +851,13 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;          // frame row of the tile owned by this thread
     float* my_acc = mel_acc + row * kMelPitch;
+    float* scratch_row = mel_acc + BM * kMelPitch;   // sink for rows beyond the batch (never read)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t acc_it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t g = tile * BM + row;
       const bool row_ok = g < b.total_frames;
-      const float sc = row_ok ? ldexpf(1.0f, -(__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+      const float sc2 = row_ok ? ldexpf(1.0f, -2 * (__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
       for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
         const int chain = sub < ntile[0] ? 0 : 1;
         const int n0 = (chain == 0 ? sub : sub - ntile[0]) * BN;
@@ -793,30 +865,8 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const uint32_t buf = acc_it & 1u;
         mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
         tcgen05_fence_after();
-        // running partial sums for the current filter pair (m0, m0 + 1); flushed when m0 changes
-        int cur_m = -1;
-        float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll 1
-        for (int j = 0; j < BN; j += 32) {
-          float re[32], im[32];
-          tmem_ld_32x32(lane_addr + buf * 256u + static_cast<uint32_t>(j), re);
-          tmem_ld_32x32(lane_addr + buf * 256u + static_cast<uint32_t>(BN + j), im);
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const float4 e = __ldg(tab + j + q);          // warp-uniform address: one broadcast load
-            const int m0 = __float_as_int(e.x);
-            const float a = re[q] * sc, c = im[q] * sc;
-            const float pw = fmaf(a, a, c * c);
-            if (m0 != cur_m) {                             // uniform branch
-              if (cur_m >= 0) { my_acc[cur_m] += s0; my_acc[cur_m + 1] += s1; }
-              cur_m = m0; s0 = 0.0f; s1 = 0.0f;
-            }
-            s0 = fmaf(pw, e.y, s0);
-            s1 = fmaf(pw, e.z, s1);
-          }
-        }
-        if (cur_m >= 0) { my_acc[cur_m] += s0; my_acc[cur_m + 1] += s1; }
-        // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld_32x32)
+        mel_accumulate_subtile(lane_addr + buf * 256u, tab, row_ok ? my_acc : scratch_row, sc2);
+        // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the routine)
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + buf);
@@ -882,17 +932,19 @@ constexpr int kPTileA = BM * BK * 2;                 // 16 KiB: 128 frame rows
 constexpr int kPTileB = (BN / 2) * BK * 2;           // 8 KiB: 64 of the 128 bin rows
 constexpr int kPStageBytes = 2 * kPTileA + 2 * kPTileB;
 constexpr size_t kPairSmem = 1024 + static_cast<size_t>(kPStages) * kPStageBytes +
-                             static_cast<size_t>(BM) * kMelPitch * sizeof(float) + 256;
+                             kMelTileBytes + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    DeviceTables t, BatchView b, int64_t plane_rows, int kp, int np_ld,
                    const int32_t* __restrict__ row_exp, float* __restrict__ db, uint32_t* __restrict__ dbmax_key) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128-byte swizzle) by OFFSETTING the shared array, not by rounding a generic pointer:
+  // the compiler then keeps the shared address space and emits LDS / STS for the mel tile
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* tiles = smem;
   float* mel_acc = reinterpret_cast<float*>(smem + kPStages * kPStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPStages * kPStageBytes + BM * kMelPitch * sizeof(float));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPStages * kPStageBytes + kMelTileBytes);
   uint64_t* empty_bar = full_bar + kPStages;
   uint64_t* tmem_full = empty_bar + kPStages;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
@@ -991,13 +1043,14 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;          // frame row of the tile owned by this thread
     float* my_acc = mel_acc + row * kMelPitch;
+    float* scratch_row = mel_acc + BM * kMelPitch;   // sink for rows beyond the batch (never read)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t acc_it = 0;
     for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
       const int64_t tile0 = pt * 2 * BM + static_cast<int64_t>(rank) * BM;
       const int64_t g = tile0 + row;
       const bool row_ok = g < b.total_frames;
-      const float sc = row_ok ? ldexpf(1.0f, -(__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+      const float sc2 = row_ok ? ldexpf(1.0f, -2 * (__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
       for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
         const int chain = sub < ntile[0] ? 0 : 1;
         const int n0 = (chain == 0 ? sub : sub - ntile[0]) * BN;
@@ -1005,29 +1058,8 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t buf = acc_it & 1u;
         mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
         tcgen05_fence_after();
-        int cur_m = -1;
-        float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll 1
-        for (int j = 0; j < BN; j += 32) {
-          float re[32], im[32];
-          tmem_ld_32x32(lane_addr + buf * 256u + static_cast<uint32_t>(j), re);
-          tmem_ld_32x32(lane_addr + buf * 256u + static_cast<uint32_t>(BN + j), im);
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const float4 e = __ldg(tab + j + q);          // warp-uniform address: one broadcast load
-            const int m0 = __float_as_int(e.x);
-            // rows beyond the batch may hold another plane's data: keep them out of the arithmetic
-            const float a = row_ok ? re[q] * sc : 0.0f, c = row_ok ? im[q] * sc : 0.0f;
-            const float pw = fmaf(a, a, c * c);
-            if (m0 != cur_m) {                             // uniform branch
-              if (cur_m >= 0) { my_acc[cur_m] += s0; my_acc[cur_m + 1] += s1; }
-              cur_m = m0; s0 = 0.0f; s1 = 0.0f;
-            }
-            s0 = fmaf(pw, e.y, s0);
-            s1 = fmaf(pw, e.z, s1);
-          }
-        }
-        if (cur_m >= 0) { my_acc[cur_m] += s0; my_acc[cur_m + 1] += s1; }
+        mel_accumulate_subtile(lane_addr + buf * 256u, tab, row_ok ? my_acc : scratch_row, sc2);
+        // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the routine)
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(tmem_empty + buf);
