@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kSmCount = 148;
 constexpr int kFrontMargin = 16;   // halfs of zeros before X(0)  (B reads back to X(-7))
-constexpr int kBackMargin = 128;   // halfs of zeros after the last K-block (A reads up to +73)
+constexpr int kBackMargin = 160;   // halfs of zeros after the last K-block (the A prefetch of one block beyond reads up to +151)
 constexpr int kVals = 6;           // lags per thread that can be <= 191
 
 struct AmGeom { int nblk4; int len; };   // K-blocks (multiple of 4), halfs per copy
@@ -223,17 +223,31 @@ __device__ __noinline__ void am_fill_simple(const DeviceTables& t, const float* 
   __syncwarp();
 }
 
+__device__ __forceinline__ uint32_t am_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// Four 8x8 fp16 matrices in MMA fragment layout with one instruction: lane L supplies the address of
+// row L % 8 of matrix L / 8 (16 bytes each) and receives elements (row lane/4, columns 2 (lane%4), +1) of
+// matrix i in r[i].
+__device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+
 // The MMA half: normalised lags of the frame currently held in `copies` into val[0..5] (see lag_of).
 __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
-  // main loop: 6 MMAs per K-block, all fragment loads conflict-free 32-bit shared reads
   const int g = lane >> 2, tq = lane & 3;
   const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
   const uint32_t* E_lo = E_hi + geo.len / 2;
   const uint32_t* O_hi = E_lo + geo.len / 2;
   const uint32_t* O_lo = O_hi + geo.len / 2;
-  // A: pair at X(n0 + 2 tq + 8 g [+8][+64]) -> even offset, E copy
-  const uint32_t* Ah = E_hi + (kFrontMargin + 2 * tq + 8 * g) / 2;
-  const uint32_t* Al = E_lo + (kFrontMargin + 2 * tq + 8 * g) / 2;
+  // A[i][k] = X(n0 + k + 8 i): the rows of the four 8x8 blocks of the fragment are 16-byte aligned runs of
+  // the E copy (rows 8 samples apart; the row blocks 8..15 start 64 samples later, the k blocks 8..15 eight
+  // samples later), so ONE ldmatrix.x4 per split part loads (a0, a1, a2, a3) into four consecutive registers -
+  // no register ring between K-blocks and no fragment copies (12 instead of ~20 instructions per K-block).
+  const int mi = lane >> 3, mr = lane & 7;
+  const uint32_t a_off = 2u * static_cast<uint32_t>(kFrontMargin + 8 * mr + (mi & 1) * 64 + (mi >> 1) * 8);
+  uint32_t sa_h = am_smem_u32(copies) + a_off;                    // advances 32 bytes per K-block
+  const uint32_t lo_delta = 2u * static_cast<uint32_t>(geo.len);  // E_lo - E_hi in bytes
   // B: pair at X(n0 + 2 tq - g [+8]) -> parity of g picks the copy (O index = X index - 1)
   const int boff = kFrontMargin + 2 * tq - g - (g & 1);
   const uint32_t* Bh = ((g & 1) ? O_hi : E_hi) + boff / 2;
@@ -249,42 +263,40 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   uint32_t bp[4][4], bq[4][4];                // [slot][b0h, b1h, b0l, b1l]
 #pragma unroll
   for (int q = 0; q < 4; ++q) { bq[q][0] = bq[q][1] = bq[q][2] = bq[q][3] = 0u; }
-  // A rows g / g+8 are 64 samples = 4 K-blocks apart: (a1, a3) of block a are (a0, a2) of block a+4
-  uint32_t ar_h[4][2], ar_l[4][2];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    ar_h[q][0] = Ah[8 * q]; ar_h[q][1] = Ah[8 * q + 4];
-    ar_l[q][0] = Al[8 * q]; ar_l[q][1] = Al[8 * q + 4];
-  }
+  // A fragments of the current block; the next block's are requested before this block's MMAs are issued
+  uint32_t ah[4], al[4];
+  ldsm_x4(sa_h, ah);
+  ldsm_x4(sa_h + lo_delta, al);
   // one group = 4 K-blocks; `cur` receives this group's B fragments, `old` holds the previous group's
-  auto group = [&](const uint32_t* pa_h, const uint32_t* pa_l, const uint32_t* pb_h, const uint32_t* pb_l,
-                   uint32_t (&cur)[4][4], const uint32_t (&old)[4][4]) {
+  auto group = [&](const uint32_t* pb_h, const uint32_t* pb_l, uint32_t (&cur)[4][4], const uint32_t (&old)[4][4]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint32_t a1h = pa_h[8 * q + 32], a3h = pa_h[8 * q + 36];
-      const uint32_t a1l = pa_l[8 * q + 32], a3l = pa_l[8 * q + 36];
+      uint32_t nh[4], nl[4];
+      sa_h += 32u;
+      ldsm_x4(sa_h, nh);                       // one block beyond the last one reads the zero margin
+      ldsm_x4(sa_h + lo_delta, nl);
       cur[q][0] = pb_h[8 * q]; cur[q][1] = pb_h[8 * q + 4];
       cur[q][2] = pb_l[8 * q]; cur[q][3] = pb_l[8 * q + 4];
-      const uint32_t a0h = ar_h[q][0], a2h = ar_h[q][1], a0l = ar_l[q][0], a2l = ar_l[q][1];
       // the two cross products of a tile are placed four MMAs apart (dependent accumulator)
-      mma_16816(d0x, a0h, a1h, a2h, a3h, cur[q][2], cur[q][3]);
-      mma_16816(d1x, a0h, a1h, a2h, a3h, old[q][2], old[q][3]);
-      mma_16816(d0, a0h, a1h, a2h, a3h, cur[q][0], cur[q][1]);
-      mma_16816(d1, a0h, a1h, a2h, a3h, old[q][0], old[q][1]);
-      mma_16816(d0x, a0l, a1l, a2l, a3l, cur[q][0], cur[q][1]);
-      mma_16816(d1x, a0l, a1l, a2l, a3l, old[q][0], old[q][1]);
-      ar_h[q][0] = a1h; ar_h[q][1] = a3h; ar_l[q][0] = a1l; ar_l[q][1] = a3l;
+      mma_16816(d0x, ah[0], ah[1], ah[2], ah[3], cur[q][2], cur[q][3]);
+      mma_16816(d1x, ah[0], ah[1], ah[2], ah[3], old[q][2], old[q][3]);
+      mma_16816(d0, ah[0], ah[1], ah[2], ah[3], cur[q][0], cur[q][1]);
+      mma_16816(d1, ah[0], ah[1], ah[2], ah[3], old[q][0], old[q][1]);
+      mma_16816(d0x, al[0], al[1], al[2], al[3], cur[q][0], cur[q][1]);
+      mma_16816(d1x, al[0], al[1], al[2], al[3], old[q][0], old[q][1]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { ah[i] = nh[i]; al[i] = nl[i]; }
     }
   };
-  const uint32_t *pa_h = Ah, *pa_l = Al, *pb_h = Bh, *pb_l = Bl;
+  const uint32_t *pb_h = Bh, *pb_l = Bl;
   int left = geo.nblk4;
 #pragma unroll 1
   for (; left >= 8; left -= 8) {
-    group(pa_h, pa_l, pb_h, pb_l, bp, bq);
-    group(pa_h + 32, pa_l + 32, pb_h + 32, pb_l + 32, bq, bp);
-    pa_h += 64; pa_l += 64; pb_h += 64; pb_l += 64;
+    group(pb_h, pb_l, bp, bq);
+    group(pb_h + 32, pb_l + 32, bq, bp);
+    pb_h += 64; pb_l += 64;
   }
-  if (left) group(pa_h, pa_l, pb_h, pb_l, bp, bq);   // nblk4 is a multiple of 4
+  if (left) group(pb_h, pb_l, bp, bq);   // nblk4 is a multiple of 4
   // tile 0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  tile 1: c2,c3 = base+128, base+129.
   val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];
   val[4] = d1[2] + d1x[2]; val[5] = d1[3] + d1x[3];
@@ -308,7 +320,6 @@ __device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane
 }
 
 // ---- mbarrier helpers (producer / consumer hand-off of the frame buffers) -------------------------
-__device__ __forceinline__ uint32_t am_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void am_bar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(am_smem_u32(bar)), "r"(count));
 }
