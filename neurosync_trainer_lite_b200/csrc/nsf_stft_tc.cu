@@ -692,13 +692,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // (m0, m0 + 1): running sums are kept for the current pair and added to the row of the mel tile in shared
 // memory when m0 changes (rows beyond the batch are pointed at a scratch row by the caller, so the hot loop
 // carries no validity test).  tab: the sub-tile's table entries {bits(m0), w[m0], w[m0+1], 0} (global,
-// read-only path: the 16 warp-uniform loads of a chunk are issued together, ahead of its arithmetic).
+// read-only path: the 16 warp-uniform loads of chunk c+1 are issued before the arithmetic of chunk c).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mel_accumulate_subtile(uint32_t acc_addr, const float4* __restrict__ tab,
                                                        float* my_acc, float sc2) {
   float re[2][16], im[2][16];
+  float4 e[2][16];                                   // table entries, double-buffered like the accumulators
   tmem_ld_32x16_async(acc_addr, re[0]);
   tmem_ld_32x16_async(acc_addr + BN, im[0]);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) e[0][q] = __ldg(tab + q);            // warp-uniform addresses: broadcast
   tmem_wait_ld(re[0], im[0]);
   int cur_m = -1;
   float s0 = 0.0f, s1 = 0.0f;
@@ -708,20 +711,19 @@ __device__ __forceinline__ void mel_accumulate_subtile(uint32_t acc_addr, const 
     if (c + 1 < BN / 16) {
       tmem_ld_32x16_async(acc_addr + 16 * (c + 1), re[nxt]);
       tmem_ld_32x16_async(acc_addr + BN + 16 * (c + 1), im[nxt]);
-    }
-    float4 e[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) e[q] = __ldg(tab + 16 * c + q);       // warp-uniform addresses: broadcast
+      for (int q = 0; q < 16; ++q) e[nxt][q] = __ldg(tab + 16 * (c + 1) + q);
+    }
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const int m0 = __float_as_int(e[q].x);
+      const int m0 = __float_as_int(e[cur][q].x);
       const float pw = fmaf(re[cur][q], re[cur][q], im[cur][q] * im[cur][q]);
       if (m0 != cur_m) {                               // uniform branch
         if (cur_m >= 0) { my_acc[cur_m] += s0 * sc2; my_acc[cur_m + 1] += s1 * sc2; }
         cur_m = m0; s0 = 0.0f; s1 = 0.0f;
       }
-      s0 = fmaf(pw, e[q].y, s0);
-      s1 = fmaf(pw, e[q].z, s1);
+      s0 = fmaf(pw, e[cur][q].y, s0);
+      s1 = fmaf(pw, e[cur][q].z, s1);
     }
     if (c + 1 < BN / 16) tmem_wait_ld(re[nxt], im[nxt]);
   }
