@@ -39,7 +39,8 @@ constexpr int kStages = 3;
 constexpr int kTileBytes = BM * BK * 2;             // 16 KiB, A and B tiles have the same size
 constexpr int kStageBytes = 4 * kTileBytes;         // A_hi, A_lo, B_hi, B_lo
 constexpr int kTmemCols = 2 * BN;                   // Re | Im accumulators, fp32
-constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (k_tc_gemm)
+constexpr int kFusedThreads = 320;                  // fused kernels: warps 2-5 and 6-9 share the epilogue
 constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256;
 
 // ---- PTX wrappers --------------------------------------------------------------------------
@@ -685,7 +686,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue of one 128-bin sub-tile, shared by the fused kernels.  The thread owns one frame row (one TMEM
-// lane) and walks the 128 Re / Im accumulator columns in chunks of 16, the TMEM loads of chunk c+1 in
+// lane) and walks 64 of the 128 Re / Im accumulator columns in chunks of 16, the TMEM loads of chunk c+1 in
 // flight while chunk c is consumed.  |X|^2 is formed from the RAW accumulators; the frame's power-of-two
 // scale sc2 = 2^(-2 (row_exp + 14)) is applied when a filter pair is flushed (exact, so the result does
 // not depend on where the scaling happens).  A bin lies under at most two adjacent triangular filters
@@ -694,42 +695,73 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // carries no validity test).  tab: the sub-tile's table entries {bits(m0), w[m0], w[m0+1], 0} (global,
 // read-only path: the 16 warp-uniform loads of chunk c+1 are issued before the arithmetic of chunk c).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mel_accumulate_subtile(uint32_t acc_addr, const float4* __restrict__ tab,
-                                                       float* my_acc, float sc2) {
+// Two warps share every TMEM lane quarter, each taking 64 of the 128 columns.  Their filter ranges meet in
+// one place: the pair (m0, m0 + 1) that is open when the lower half ends may also be the first or second
+// pair of the upper half.  The upper-half warp (kUpper) therefore keeps its first two flushes in registers
+// (dm / d0 / d1) and applies them after the hand-shake with its partner (apply_deferred), so every element of
+// the mel tile still receives its contributions in a fixed order.
+struct MelDeferred { int m[2]; float s0[2], s1[2]; int n; };
+
+template <bool kUpper>
+__device__ __forceinline__ void mel_accumulate_half(uint32_t acc_addr, const float4* __restrict__ tab,
+                                                    float* my_acc, float sc2, MelDeferred& def) {
+  constexpr int kCols = BN / 2, kChunks = kCols / 16;
+  constexpr int c0 = kUpper ? kCols : 0;
   float re[2][16], im[2][16];
-  float4 e[2][16];                                   // table entries, double-buffered like the accumulators
-  tmem_ld_32x16_async(acc_addr, re[0]);
-  tmem_ld_32x16_async(acc_addr + BN, im[0]);
-#pragma unroll
-  for (int q = 0; q < 16; ++q) e[0][q] = __ldg(tab + q);            // warp-uniform addresses: broadcast
+  tmem_ld_32x16_async(acc_addr + c0, re[0]);
+  tmem_ld_32x16_async(acc_addr + BN + c0, im[0]);
   tmem_wait_ld(re[0], im[0]);
   int cur_m = -1;
   float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-  for (int c = 0; c < BN / 16; ++c) {
-    const int cur = c & 1, nxt = cur ^ 1;
-    if (c + 1 < BN / 16) {
-      tmem_ld_32x16_async(acc_addr + 16 * (c + 1), re[nxt]);
-      tmem_ld_32x16_async(acc_addr + BN + 16 * (c + 1), im[nxt]);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) e[nxt][q] = __ldg(tab + 16 * (c + 1) + q);
+  def.n = 0;
+  auto flush = [&]() {
+    if (cur_m < 0) return;
+    if (kUpper && def.n == 0) {                  // (static indices: the struct stays in registers)
+      def.m[0] = cur_m; def.s0[0] = s0 * sc2; def.s1[0] = s1 * sc2; def.n = 1;
+    } else if (kUpper && def.n == 1) {
+      def.m[1] = cur_m; def.s0[1] = s0 * sc2; def.s1[1] = s1 * sc2; def.n = 2;
+    } else {
+      my_acc[cur_m] += s0 * sc2;
+      my_acc[cur_m + 1] += s1 * sc2;
     }
+  };
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int cur = c & 1, nxt = cur ^ 1;
+    if (c + 1 < kChunks) {
+      tmem_ld_32x16_async(acc_addr + c0 + 16 * (c + 1), re[nxt]);
+      tmem_ld_32x16_async(acc_addr + BN + c0 + 16 * (c + 1), im[nxt]);
+    }
+    float4 e[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) e[q] = __ldg(tab + c0 + 16 * c + q);     // warp-uniform addresses: broadcast
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const int m0 = __float_as_int(e[cur][q].x);
+      const int m0 = __float_as_int(e[q].x);
       const float pw = fmaf(re[cur][q], re[cur][q], im[cur][q] * im[cur][q]);
       if (m0 != cur_m) {                               // uniform branch
-        if (cur_m >= 0) { my_acc[cur_m] += s0 * sc2; my_acc[cur_m + 1] += s1 * sc2; }
+        flush();
         cur_m = m0; s0 = 0.0f; s1 = 0.0f;
       }
-      s0 = fmaf(pw, e[cur][q].y, s0);
-      s1 = fmaf(pw, e[cur][q].z, s1);
+      s0 = fmaf(pw, e[q].y, s0);
+      s1 = fmaf(pw, e[q].z, s1);
     }
-    if (c + 1 < BN / 16) tmem_wait_ld(re[nxt], im[nxt]);
+    if (c + 1 < kChunks) tmem_wait_ld(re[nxt], im[nxt]);
   }
-  if (cur_m >= 0) { my_acc[cur_m] += s0 * sc2; my_acc[cur_m + 1] += s1 * sc2; }
+  flush();
+}
+__device__ __forceinline__ void apply_deferred(float* my_acc, const MelDeferred& def) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    if (i < def.n) { my_acc[def.m[i]] += def.s0[i]; my_acc[def.m[i] + 1] += def.s1[i]; }
+}
+// 64-thread named barrier of the two warps that share TMEM lane quarter `quarter` (ids 1..4; 0 is __syncthreads)
+__device__ __forceinline__ void pair_sync(int quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
 }
 
+// The epilogue of the fused kernels for one thread: `upper` selects the column half, the thread owns frame
+// row `row` of the tile (TMEM lane).  Called by warps 2..9; see k_tc_stft_mel for the surrounding protocol.
 // ------------------------------------------------------------------------------------------------
 // k_tc_stft_mel: PERSISTENT fused kernel, one CTA per SM looping over tiles of 128 hop-frames.
 // For every tile it runs the (chain, 128-bin) sub-tiles back to back; TMEM holds two 256-column
@@ -738,7 +770,8 @@ __device__ __forceinline__ void mel_accumulate_subtile(uint32_t acc_addr, const 
 // accumulates the triangular mel filters straight into a [128 frames][n_mels] fp32 tile in shared
 // memory (each thread owns one frame row; a bin feeds at most two adjacent filters), and after the
 // last sub-tile writes 10 log10(max(1e-10, mel)) plus the per-clip dB maximum.
-//   warp 0 : TMA producer      warp 1 : TMEM alloc + tcgen05.mma issuer      warps 2-5 : epilogue
+//   warp 0 : TMA producer      warp 1 : TMEM alloc + tcgen05.mma issuer      warps 2-9 : epilogue
+//   (two warps per TMEM lane quarter, 64 of the 128 accumulator columns each)
 // ------------------------------------------------------------------------------------------------
 constexpr int kFStages = 2;
 constexpr int kMelPitch = 129;                       // floats per frame row of the mel tile
@@ -748,7 +781,7 @@ constexpr size_t kMelTileBytes = (static_cast<size_t>(BM + 1) * kMelPitch * size
 constexpr size_t kFusedSmem = 1024 + static_cast<size_t>(kFStages) * kStageBytes +
                               kMelTileBytes + 256;
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFusedThreads, 1)
 k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               DeviceTables t, BatchView b, int64_t plane_rows, int kp, int np_ld,
               const int32_t* __restrict__ row_exp, float* __restrict__ db, uint32_t* __restrict__ dbmax_key) {
@@ -774,7 +807,7 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
     for (int i = 0; i < kFStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -851,15 +884,18 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     }
   } else {
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;          // frame row of the tile owned by this thread
+    const bool upper = warp >= 6;                 // warps 2-5: columns 0-63 of a sub-tile, warps 6-9: 64-127
+    const int row = quarter * 32 + lane;          // frame row of the tile owned by this thread (and its partner)
     float* my_acc = mel_acc + row * kMelPitch;
     float* scratch_row = mel_acc + BM * kMelPitch;   // sink for rows beyond the batch (never read)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t acc_it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t g = tile * BM + row;
+      const int64_t tile0 = tile * BM;
+      const int64_t g = tile0 + row;
       const bool row_ok = g < b.total_frames;
       const float sc2 = row_ok ? ldexpf(1.0f, -2 * (__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+      float* acc_row = row_ok ? my_acc : scratch_row;
       for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
         const int chain = sub < ntile[0] ? 0 : 1;
         const int n0 = (chain == 0 ? sub : sub - ntile[0]) * BN;
@@ -867,29 +903,35 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const uint32_t buf = acc_it & 1u;
         mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
         tcgen05_fence_after();
-        mel_accumulate_subtile(lane_addr + buf * 256u, tab, row_ok ? my_acc : scratch_row, sc2);
+        MelDeferred def;
+        if (upper) mel_accumulate_half<true>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
+        else mel_accumulate_half<false>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
         // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the routine)
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + buf);
+        pair_sync(quarter);                        // the lower half has flushed everything
+        if (upper) apply_deferred(acc_row, def);
       }
-      // tile finished: dB, per-clip maximum, coalesced store, reset of the accumulator rows
+      pair_sync(quarter);                          // deferred sums are in: the rows of this quarter are complete
+      // tile finished: dB (each warp its 64 mels), per-clip maximum, coalesced store, reset of the rows
+      const int m_lo = upper ? t.n_mels / 2 : 0, m_hi = upper ? t.n_mels : t.n_mels / 2;
       float vmax = -INFINITY;
-      for (int m = 0; m < t.n_mels; ++m) {
+      for (int m = m_lo; m < m_hi; ++m) {
         const float v = 10.0f * log10f(fmaxf(1e-10f, my_acc[m]));
         my_acc[m] = v;
         vmax = fmaxf(vmax, v);
       }
-      __syncwarp();
-      const int64_t gw = tile * BM + quarter * 32;          // first frame of this warp's 32 rows
-      for (int r = 0; r < 32; ++r) {
+      pair_sync(quarter);
+      const int64_t gw = tile0 + quarter * 32;          // first frame of this quarter's 32 rows
+      for (int r = upper ? 16 : 0; r < (upper ? 32 : 16); ++r) {
         if (gw + r < b.total_frames) {
           const float* src = mel_acc + (quarter * 32 + r) * kMelPitch;
           for (int m = lane; m < t.n_mels; m += 32) db[(gw + r) * t.n_mels + m] = src[m];
         }
       }
-      __syncwarp();
-      for (int m = 0; m < kMelPitch; ++m) my_acc[m] = 0.0f;
+      pair_sync(quarter);
+      for (int m = upper ? kMelPitch / 2 : 0; m < (upper ? kMelPitch : kMelPitch / 2); ++m) my_acc[m] = 0.0f;
       {
         const int clip = row_ok ? find_segment(b.frame_off, b.n_clips, g) : -1;
         const uint32_t key = row_ok ? float_key(vmax) : 0u;
@@ -926,7 +968,7 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 //                           CTAs' TMA loads complete on it (peer bit cleared)
 //             empty[s]      per CTA; tcgen05.commit multicast from the leader's MMA thread
 //             tmem_full[b]  per CTA; tcgen05.commit multicast
-//             tmem_empty[b] leader's barrier, 8 arrivals: the four epilogue warps of both CTAs
+//             tmem_empty[b] leader's barrier, 16 arrivals: the eight epilogue warps of both CTAs
 // Epilogue, mel accumulation and outputs are those of k_tc_stft_mel (each CTA owns its 128 rows).
 // ------------------------------------------------------------------------------------------------
 constexpr int kPStages = 3;
@@ -936,7 +978,7 @@ constexpr int kPStageBytes = 2 * kPTileA + 2 * kPTileB;
 constexpr size_t kPairSmem = 1024 + static_cast<size_t>(kPStages) * kPStageBytes +
                              kMelTileBytes + 256;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
 k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    DeviceTables t, BatchView b, int64_t plane_rows, int kp, int np_ld,
                    const int32_t* __restrict__ row_exp, float* __restrict__ db, uint32_t* __restrict__ dbmax_key) {
@@ -965,7 +1007,7 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
     for (int i = 0; i < kPStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 16); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
@@ -1043,7 +1085,8 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else {
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;          // frame row of the tile owned by this thread
+    const bool upper = warp >= 6;                 // warps 2-5: columns 0-63 of a sub-tile, warps 6-9: 64-127
+    const int row = quarter * 32 + lane;          // frame row of the tile owned by this thread (and its partner)
     float* my_acc = mel_acc + row * kMelPitch;
     float* scratch_row = mel_acc + BM * kMelPitch;   // sink for rows beyond the batch (never read)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -1053,6 +1096,7 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int64_t g = tile0 + row;
       const bool row_ok = g < b.total_frames;
       const float sc2 = row_ok ? ldexpf(1.0f, -2 * (__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+      float* acc_row = row_ok ? my_acc : scratch_row;
       for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
         const int chain = sub < ntile[0] ? 0 : 1;
         const int n0 = (chain == 0 ? sub : sub - ntile[0]) * BN;
@@ -1060,28 +1104,35 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t buf = acc_it & 1u;
         mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
         tcgen05_fence_after();
-        mel_accumulate_subtile(lane_addr + buf * 256u, tab, row_ok ? my_acc : scratch_row, sc2);
+        MelDeferred def;
+        if (upper) mel_accumulate_half<true>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
+        else mel_accumulate_half<false>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
         // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the routine)
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(tmem_empty + buf);
+        pair_sync(quarter);                        // the lower half has flushed everything
+        if (upper) apply_deferred(acc_row, def);
       }
+      pair_sync(quarter);                          // deferred sums are in: the rows of this quarter are complete
+      // tile finished: dB (each warp its 64 mels), per-clip maximum, coalesced store, reset of the rows
+      const int m_lo = upper ? t.n_mels / 2 : 0, m_hi = upper ? t.n_mels : t.n_mels / 2;
       float vmax = -INFINITY;
-      for (int m = 0; m < t.n_mels; ++m) {
+      for (int m = m_lo; m < m_hi; ++m) {
         const float v = 10.0f * log10f(fmaxf(1e-10f, my_acc[m]));
         my_acc[m] = v;
         vmax = fmaxf(vmax, v);
       }
-      __syncwarp();
-      const int64_t gw = tile0 + quarter * 32;          // first frame of this warp's 32 rows
-      for (int r = 0; r < 32; ++r) {
+      pair_sync(quarter);
+      const int64_t gw = tile0 + quarter * 32;          // first frame of this quarter's 32 rows
+      for (int r = upper ? 16 : 0; r < (upper ? 32 : 16); ++r) {
         if (gw + r < b.total_frames) {
           const float* src = mel_acc + (quarter * 32 + r) * kMelPitch;
           for (int m = lane; m < t.n_mels; m += 32) db[(gw + r) * t.n_mels + m] = src[m];
         }
       }
-      __syncwarp();
-      for (int m = 0; m < kMelPitch; ++m) my_acc[m] = 0.0f;
+      pair_sync(quarter);
+      for (int m = upper ? kMelPitch / 2 : 0; m < (upper ? kMelPitch : kMelPitch / 2); ++m) my_acc[m] = 0.0f;
       {
         const int clip = row_ok ? find_segment(b.frame_off, b.n_clips, g) : -1;
         const uint32_t key = row_ok ? float_key(vmax) : 0u;
@@ -1264,7 +1315,7 @@ int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTable
     int64_t pairs = v.rows / (2 * BM);
     if (pairs > 74) pairs = 74;
     if (pairs < 1) pairs = 1;
-    k_tc_stft_mel_pair<<<static_cast<unsigned>(2 * pairs), kThreads, kPairSmem, s>>>(
+    k_tc_stft_mel_pair<<<static_cast<unsigned>(2 * pairs), kFusedThreads, kPairSmem, s>>>(
         map_a, tc.map_b_half, t, b, v.rows, tc.kp, tc.np_ld, v.row_exp, db, dbmax_key);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
@@ -1274,7 +1325,7 @@ int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTable
   int64_t grid = v.rows / BM;
   if (grid > 148) grid = 148;
   if (grid < 1) grid = 1;
-  k_tc_stft_mel<<<static_cast<unsigned>(grid), kThreads, kFusedSmem, s>>>(map_a, tc.map_b, t, b, v.rows, tc.kp, tc.np_ld,
+  k_tc_stft_mel<<<static_cast<unsigned>(grid), kFusedThreads, kFusedSmem, s>>>(map_a, tc.map_b, t, b, v.rows, tc.kp, tc.np_ld,
                                                                             v.row_exp, db, dbmax_key);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
