@@ -142,3 +142,22 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(base, f)).read()
                 assert "feature_oracle" not in text and "librosa_standin" not in text, f
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+
+
+def test_build_stamp_is_path_independent_and_build_is_locked(tmp_path, monkeypatch):
+    """The library built in this checkout must be recognised as current in a COPY of the checkout (the GPU
+    box runs from a different path; a rebuild there raced between torchrun ranks), and concurrent callers
+    must serialise on the build lock instead of loading a half-written file."""
+    import shutil
+
+    from neurosync_trainer_lite_b200 import build as b
+    here = b._digest()
+    root2 = tmp_path / "elsewhere"
+    shutil.copytree(b.CSRC, root2 / "neurosync_trainer_lite_b200" / "csrc")
+    (root2 / "include").mkdir()
+    shutil.copy(os.path.join(b.ROOT, "include", "nsf.h"), root2 / "include" / "nsf.h")
+    monkeypatch.setattr(b, "ROOT", str(root2))
+    monkeypatch.setattr(b, "CSRC", str(root2 / "neurosync_trainer_lite_b200" / "csrc"))
+    assert b._digest() == here
+    src = open(b.__file__).read()
+    assert "fcntl.flock" in src and "os.replace(lib_tmp, LIB_PATH)" in src
