@@ -441,3 +441,50 @@ def test_properties_at_c2_scale(engine, nv):
     t = eng.extract_host(base[2], [0, len(base[2])], nv.NO_AUTOCORR | nv.NO_REDUCE | nv.NO_DELTAS)
     assert np.abs(t.mean(axis=0, dtype=np.float64)).max() < 1e-4
     assert np.abs(t.std(axis=0, dtype=np.float64) - 1).max() < 1e-4
+
+
+def test_collect_properties_at_c4_rank_scale(engine, oracle):
+    """One rank's share of C4 (60 clips x 1801 feature rows + 1800 facial rows, fast + slow + blend(30)):
+    row counts of SURVEY section 8 (6239 per clip), float64 bit-exactness against the oracle on sampled clips,
+    cross-fade end points, and that identical inputs give identical outputs wherever they sit in the batch."""
+    eng = engine.get_engine(88200, 1470, 735)
+    rng = np.random.default_rng(5)
+    base_a = [rng.standard_normal((1801, 256)) for _ in range(3)]
+    base_f = [rng.uniform(0, 1, (1800, 61)) for _ in range(3)]
+    n = 60
+    audio = np.concatenate([base_a[i % 3] for i in range(n)])
+    facial = np.concatenate([base_f[i % 3] for i in range(n)])
+    a_off = np.arange(n + 1, dtype=np.int64) * 1801
+    f_off = np.arange(n + 1, dtype=np.int64) * 1800
+    oa, of, o_off = eng.collect_host(audio, a_off, facial, f_off, True, True, True, 30)
+    assert np.array_equal(np.diff(o_off), np.full(n, 6239))                 # 2670 + 3599 - 30
+    assert oa.shape == (n * 6239, 256) and of.shape == (n * 6239, 61)
+    for i in (0, 1, 2):
+        wa, wf = oracle.collect_from_arrays(base_a[i], base_f[i], True, True, True, 30)
+        np.testing.assert_array_equal(oa[o_off[i]:o_off[i + 1]], wa)
+        np.testing.assert_array_equal(of[o_off[i]:o_off[i + 1]], wf)
+    for i in range(3, n):                                                     # position independence
+        np.testing.assert_array_equal(oa[o_off[i]:o_off[i + 1]], oa[o_off[i % 3]:o_off[i % 3 + 1]])
+    # first blended row is purely the original stream, last blended row purely the next one (linspace ends)
+    trimmed = base_a[0][:1800]                                                # centre trim of 1801 vs 1800: diff 1 -> left 0
+    np.testing.assert_array_equal(oa[:1770], trimmed[:1770])
+    np.testing.assert_array_equal(oa[1770], trimmed[1770])
+
+
+def test_properties_at_c5_scale(engine, oracle):
+    """C5: 10 000 clips x 2 s @ 16 kHz in ONE batched call: 121 rows per clip, finite, bounded
+    autocorrelation, identical clips -> identical rows, sampled clips against the oracle."""
+    eng = engine.get_engine(16000, 266, 133)
+    base = [synth.synth_clip(2.0, 16000, seed=40 + s, kind=("voiced", "noise", "gated", "voiced")[s % 4]) for s in range(8)]
+    n = 10000
+    packed, off = engine.pack_clips([base[i % 8] for i in range(n)])
+    rows = eng.extract_host(packed, off)
+    assert rows.shape == (n * 121, 256) and np.isfinite(rows).all()
+    assert np.abs(rows[:, 69:]).max() <= 1.0 + 1e-5
+    r = rows.reshape(n, 121, 256)
+    for s in range(8):
+        assert np.array_equal(r[s::8], np.broadcast_to(r[s], r[s::8].shape))
+    for s in (0, 2, 5):
+        want = oracle.extract_and_combine_features(base[s], 16000, 266, 133)
+        d = np.abs(r[s] - want)
+        assert d[:, :69].max() < 1e-3 and d[:, 69:].max() < 2e-5
