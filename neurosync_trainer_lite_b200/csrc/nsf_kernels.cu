@@ -561,11 +561,24 @@ __global__ void __launch_bounds__(256, 3) k_delta_reduce(BatchView b, const floa
   const int64_t r_end = min(r_begin + chunk, b.total_rows);
   int cached_clip = -1;
   float cached_mu = 0.0f, cached_inv = 1.0f;       // channel `lane` of cached_clip
+  float win[10];                                   // frames win_ta-4 .. win_ta+5 of clip win_clip, channel `lane`
+  int win_clip = -1;
+  int64_t win_ta = 0;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) win[k] = 0.0f;
+  // clip of the current row: looked up only when the run crosses into the next clip (the lookup is a chain
+  // of dependent loads - most of a row's latency when it is repeated per row)
+  int clip = -1;
+  int64_t f0 = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
   for (int64_t r = r_begin; r < r_end; ++r) {
-    const int clip = find_segment(b.row_off, b.n_clips, r);
-    const int64_t f0 = __ldg(b.frame_off + clip);
-    const int64_t T = __ldg(b.frame_off + clip + 1) - f0;
-    const int64_t lr = r - __ldg(b.row_off + clip);
+    if (r >= clip_row_end) {
+      clip = find_segment(b.row_off, b.n_clips, r);
+      f0 = __ldg(b.frame_off + clip);
+      T = __ldg(b.frame_off + clip + 1) - f0;
+      clip_row0 = __ldg(b.row_off + clip);
+      clip_row_end = __ldg(b.row_off + clip + 1);
+    }
+    const int64_t lr = r - clip_row0;
     const int64_t ta = reduce ? 2 * lr : lr;
     const bool pair = reduce && (ta + 1 < T);
     // window centres (edges replicate the value at frame 4 / T-5: savgol mode='interp')
@@ -573,6 +586,53 @@ __global__ void __launch_bounds__(256, 3) k_delta_reduce(BatchView b, const floa
     const int64_t cb = min(max(ta + 1, static_cast<int64_t>(4)), T - 5);
     const bool shared_taps = pair && cb == ca + 1;
     const double inv_T = cmvn ? 1.0 / static_cast<double>(T) : 0.0;
+    // Fast path (MFCC block: C <= 32, deltas, pair reduction): an interior row's two windows are the ten
+    // consecutive frames ta-4 .. ta+5, and the next row's are the same ten shifted by two - the lane keeps
+    // them in registers and fetches only the two new frames per row.  Same arithmetic, same order as below.
+    const bool interior = deltas && pair && C <= 32 && ta >= 4 && ta + 1 <= T - 5;
+    if (interior) {
+      const int ch = lane;
+      if (ch < C) {
+        float mu = 0.0f, inv = 1.0f;
+        if (cmvn) {
+          if (clip == cached_clip) {
+            mu = cached_mu;
+            inv = cached_inv;
+          } else {
+            const double m = __ldg(sum + static_cast<int64_t>(clip) * C + ch) * inv_T;
+            const double var = fmax(0.0, fma(__ldg(sumsq + static_cast<int64_t>(clip) * C + ch), inv_T, -m * m));
+            mu = static_cast<float>(m);
+            inv = __fdiv_rn(1.0f, sqrtf(static_cast<float>(var)) + 1e-10f);
+            cached_mu = mu; cached_inv = inv;
+          }
+        }
+        const float* p = in + (f0 + ta - 4) * in_ld + ch;
+        if (win_clip == clip && win_ta + 2 == ta) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) win[k] = win[k + 2];
+          win[8] = __ldg(p + 8 * in_ld);
+          win[9] = __ldg(p + 9 * in_ld);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 10; ++k) win[k] = __ldg(p + k * in_ld);
+        }
+        float xa[9], xb[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { xa[k] = win[k] - mu; xb[k] = win[k + 1] - mu; }   // centred: constants give exact 0
+        const float va = 0.5f * ((win[4] - mu) * inv + (win[5] - mu) * inv);
+        const float d1 = 0.5f * (sg_d1(xa) + sg_d1(xb)) * inv;
+        const float d2 = 0.5f * (sg_d2(xa) + sg_d2(xb)) * inv;
+        float* o = out + r * out_ld + col0;
+        o[ch] = va;
+        o[C + ch] = d1;
+        o[2 * C + ch] = d2;
+      }
+      win_clip = clip;
+      win_ta = ta;
+      cached_clip = clip;
+      continue;
+    }
+    win_clip = -1;
     for (int ch = lane; ch < C; ch += 32) {
       float mu = 0.0f, inv = 1.0f;
       if (cmvn) {
