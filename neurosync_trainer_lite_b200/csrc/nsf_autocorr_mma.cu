@@ -375,15 +375,25 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
     }
   }
   __syncthreads();
-  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kAmPairs + pair;
-  const int64_t row_stride = static_cast<int64_t>(gridDim.x) * kAmPairs;
+  // Every pair owns a CONTIGUOUS run of rows: consecutive frames share half of their samples (L1 / L2 hits
+  // for the producer) and almost always the clip, whose descriptor - a chain of dependent loads - is then
+  // looked up once per clip instead of once per row, on both sides of the hand-off.
+  const int64_t n_pairs_total = static_cast<int64_t>(gridDim.x) * kAmPairs;
+  const int64_t chunk = (b.total_rows + n_pairs_total - 1) / n_pairs_total;
+  const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * kAmPairs + pair) * chunk;
+  const int64_t r_end = min(r_begin + chunk, b.total_rows);
   uint32_t it = 0;                                  // frames handed over so far (buffer = it & 1)
-  for (int64_t r = row0; r < b.total_rows; r += row_stride) {
-    const int clip = find_segment(b.row_off, b.n_clips, r);
-    const int64_t base = __ldg(b.clip_off + clip);
-    const int64_t len = __ldg(b.clip_off + clip + 1) - base;
-    const int64_t T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
-    const int64_t lr = r - __ldg(b.row_off + clip);
+  int64_t base = 0, len = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
+  for (int64_t r = r_begin; r < r_end; ++r) {
+    if (r >= clip_row_end) {
+      const int clip = find_segment(b.row_off, b.n_clips, r);
+      base = __ldg(b.clip_off + clip);
+      len = __ldg(b.clip_off + clip + 1) - base;
+      T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
+      clip_row0 = __ldg(b.row_off + clip);
+      clip_row_end = __ldg(b.row_off + clip + 1);
+    }
+    const int64_t lr = r - clip_row0;
     const int64_t tf0 = reduce ? 2 * lr : lr;
     const int n_frames = (reduce && tf0 + 1 < T) ? 2 : 1;   // odd T: the last row passes through
     if (producer) {
