@@ -356,12 +356,13 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
   __shared__ uint64_t s_bar[kAmPairs][4];          // per pair: full[2], empty[2]
   const AmGeom geo = am_geom(t.F);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = warp % kAmPairs;
-  const bool producer = warp >= kAmPairs;
+  const int n_pairs = static_cast<int>(blockDim.x >> 6);   // kAmPairs, fewer when the frame buffers of four do not fit
+  const int pair = warp % n_pairs;
+  const bool producer = warp >= n_pairs;
   __half* bufs = s_am + static_cast<size_t>(pair) * 2 * 4 * geo.len;      // two buffers of 4 copies
   // np.hanning(F) staged in shared memory: with ~220 KB of the SM carved out for buffers the L1 is too
   // small to keep the table resident next to the streaming frame loads
-  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len);
+  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(n_pairs) * 2 * 4 * geo.len);
   const int n_it = (t.F / 2 + 1 + 31) / 32;          // register-staging iterations the frame needs
   for (int n = threadIdx.x; n < 64 * n_it; n += blockDim.x) hann[n] = n < t.F ? __ldg(t.hann_sym + n) : 0.0f;
   uint64_t* full = s_bar[pair];
@@ -378,9 +379,9 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
   // Every pair owns a CONTIGUOUS run of rows: consecutive frames share half of their samples (L1 / L2 hits
   // for the producer) and almost always the clip, whose descriptor - a chain of dependent loads - is then
   // looked up once per clip instead of once per row, on both sides of the hand-off.
-  const int64_t n_pairs_total = static_cast<int64_t>(gridDim.x) * kAmPairs;
+  const int64_t n_pairs_total = static_cast<int64_t>(gridDim.x) * n_pairs;
   const int64_t chunk = (b.total_rows + n_pairs_total - 1) / n_pairs_total;
-  const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * kAmPairs + pair) * chunk;
+  const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * n_pairs + pair) * chunk;
   const int64_t r_end = min(r_begin + chunk, b.total_rows);
   uint32_t it = 0;                                  // frames handed over so far (buffer = it & 1)
   int64_t base = 0, len = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
@@ -451,17 +452,24 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   if (t.n_lags > 191) return -1;
   const int iters = (t.F / 2 + 1 + 31) / 32;      // register-staging iterations the frame needs
   const size_t hann_bytes = static_cast<size_t>(64) * iters * sizeof(float);   // np.hanning(F), zero padded
-  const size_t smem = static_cast<size_t>(kAmPairs) * 2 * 4 * geo.len * sizeof(__half) + hann_bytes;
-  if (smem > 220 * 1024) return -1;
+  // four (consumer, producer) pairs per block when their eight frame buffers fit twice per SM or at least
+  // once; long frames (F > ~1530, e.g. 96 kHz) run with three or two pairs per block
+  int pairs = kAmPairs;
+  size_t smem = 0;
+  for (; pairs >= 1; --pairs) {
+    smem = static_cast<size_t>(pairs) * 2 * 4 * geo.len * sizeof(__half) + hann_bytes;
+    if (smem <= 220 * 1024) break;
+  }
+  if (pairs < 1) return -1;
   int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
-  int64_t grid = (b.total_rows + kAmPairs - 1) / kAmPairs;
+  int64_t grid = (b.total_rows + pairs - 1) / pairs;
   if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
   if (grid < 1) grid = 1;
   auto go = [&](auto kernel) {
     // per call: all instantiations share this lambda (same function-pointer type), so no static flag
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
-    kernel<<<static_cast<int>(grid), kAmPairs * 64, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+    kernel<<<static_cast<int>(grid), pairs * 64, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   };
   if (iters == 23) return go(k_autocorr_mma<23, true>);   // 88.2 kHz: F = 1470

@@ -201,7 +201,10 @@ def test_silence_dc_impulse(golden, ef, efu):
 
 
 @pytest.mark.parametrize("kind,sr,seconds", [("voiced", 88200, 0.31), ("noise", 16000, 0.4),
-                                             ("gated", 88200, 2.2), ("voiced", 48000, 0.5)])
+                                             ("gated", 88200, 2.2), ("voiced", 48000, 0.5),
+                                             # long frames: F = 1600 (three autocorrelation pairs per block) and
+                                             # F = 3200 (two pairs, two-pass fold kernel)
+                                             ("voiced", 96000, 0.4), ("noise", 192000, 0.25)])
 def test_against_oracle_seeded(kind, sr, seconds, oracle, ef):
     y = synth.synth_clip(seconds, sr, seed=77, kind=kind)
     F, H = oracle.frame_params(sr)
