@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the audio feature front-end (BASELINE.json metric: audio-seconds per second).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2|c3|c4|c5]
 
 A *step* is one pass of the hot path over one batch of synthetic input: workload ``c2`` (default,
 BASELINE configs[1]) = a 30-minute single-actor dataset, 60 clips x 30 s @ 88.2 kHz, features only
@@ -10,6 +10,9 @@ At N > 1 (torchrun, one rank per GPU) every rank extracts its own 60-clip shard 
 clip with no collective - so scaling is *weak* and ``value`` is N x 1800 x K / max-over-ranks time.
 
 One JSON line on rank 0:
+Workloads ``c3`` / ``c4`` append the ``collect_features`` augmentation (fast / fast + slow, blend 30) to every step
+and add its kernel to ``kernels``; ``c5`` is the 10 000 x 2 s @ 16 kHz small-clip batch.
+
 * ``value``   device-resident throughput (PCM already in HBM), CUDA events on the launch stream;
 * ``e2e``     the same metric through ``nsf_extract_host`` (C ABI, HOST buffers: pinned float32 PCM in,
               pinned float32 rows out, H2D and D2H inside the timed region);
@@ -40,7 +43,16 @@ WORKLOADS = {
     "c2": (88200, 1470, 735, 60, 30.0,
            "C2: 30-min single-actor dataset, 60 clips x 30 s @ 88.2 kHz, features only"),
     "c5": (16000, 266, 133, 10000, 2.0, "C5: 10000 clips x 2 s @ 16 kHz, batched small clips"),
+    # the same 30-minute dataset followed by the collect_features augmentation (BASELINE configs[2] and [3],
+    # one rank's share: every rank of the 2/4/8-GPU runs processes 60 clips)
+    "c3": (88200, 1470, 735, 60, 30.0,
+           "C3: 30-min dataset + collect_features(include_fast, blend_boundaries, blend_frames=30)"),
+    "c4": (88200, 1470, 735, 60, 30.0,
+           "C4 (one rank's 60 clips of 480): features + collect_features(include_fast, include_slow, blend 30)"),
 }
+COLLECT = {"c3": dict(include_fast=True, include_slow=False, blend_boundaries=True, blend_frames=30),
+           "c4": dict(include_fast=True, include_slow=True, blend_boundaries=True, blend_frames=30)}
+FACIAL_ROWS, FACIAL_COLS = 1800, 61                    # 30 s of 60 fps blendshape rows per clip
 # algorithmic work per hop-frame; bytes are float32 in / float32 out
 N_MELS, N_MFCC, N_LAGS = 128, 23, 187
 
@@ -216,7 +228,7 @@ def bind_to_gpu_numa_node(index):
 def make_inputs(workload, rank):
     from neurosync_trainer_lite_b200 import engine, synth
     sr, Fr, Hr, n_clips, seconds, _ = WORKLOADS[workload]
-    n_base = 6 if workload == "c2" else 50           # distinct signals; the rest are rotations of them
+    n_base = 50 if workload == "c5" else 6           # distinct signals; the rest are rotations of them
     kinds = ("voiced", "voiced", "noise", "voiced", "gated", "voiced")
     base = [synth.synth_clip(seconds, sr, seed=100 * rank + s, kind=kinds[s % 6]) for s in range(n_base)]
     clips = []
@@ -269,15 +281,36 @@ def run_native(args, rank, world, local_rank):
     out = torch.empty((rows, 256), dtype=torch.float32, device=dev)
     ws = torch.empty(eng.workspace_bytes(len(packed), n_clips), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
-    for _ in range(max(args.warmup, 3)):
+    # collect_features augmentation after the extraction (workloads c3 / c4): device-resident float32
+    collect = COLLECT.get(args.workload)
+    col = None
+    if collect:
+        from neurosync_trainer_lite_b200 import synth
+        facial_h = np.concatenate([synth.synth_facial(FACIAL_ROWS, seed=100 * rank + i % 6)
+                                   for i in range(n_clips)]).astype(np.float32)
+        f_off = np.arange(n_clips + 1, dtype=np.int64) * FACIAL_ROWS
+        a_off = eng.row_offsets(off)
+        o_off = eng.collect_rows(a_off, f_off, **collect)
+        col = {"facial_h": facial_h, "facial": torch.from_numpy(facial_h).to(dev), "f_off": f_off, "a_off": a_off,
+               "o_off": o_off,
+               "out_a": torch.empty((int(o_off[-1]), 256), dtype=torch.float32, device=dev),
+               "out_f": torch.empty((int(o_off[-1]), FACIAL_COLS), dtype=torch.float32, device=dev)}
+
+    def device_step():
         eng.extract_device(pcm, off, 0, out=out, workspace=ws)
+        if col:
+            eng.collect_device(out, col["a_off"], col["facial"], col["f_off"], out_audio=col["out_a"],
+                               out_facial=col["out_f"], out_offsets=col["o_off"], **collect)
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        eng.extract_device(pcm, off, 0, out=out, workspace=ws)
+        device_step()
     e1.record(stream)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -293,6 +326,15 @@ def run_native(args, rank, world, local_rank):
         for k, v in eng.stage_times_ms().items():
             acc[k] = acc.get(k, 0.0) + v / reps
     eng.set_profiling(False)
+    if col:                                            # the augmentation kernel on its own (CUDA events, same stream)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(reps):
+            eng.collect_device(out, col["a_off"], col["facial"], col["f_off"], out_audio=col["out_a"],
+                               out_facial=col["out_f"], out_offsets=col["o_off"], **collect)
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        acc["collect"] = c0.elapsed_time(c1) / reps
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     pin_in = engine.PinnedBuffer(packed.nbytes)
@@ -303,9 +345,16 @@ def run_native(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         eng.extract_host(h_in, off, 0, out=h_out)
     barrier()
+    def host_step():
+        eng.extract_host(h_in, off, 0, out=h_out)     # synchronous: returns when rows are on the host
+        if col:                                       # nsf_collect_host: rows and facial data up, augmented rows back
+            return eng.collect_host(h_out, col["a_off"], col["facial_h"], col["f_off"], **collect)
+
+    if col:
+        host_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.extract_host(h_in, off, 0, out=h_out)     # synchronous: returns when rows are on the host
+        host_step()
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -355,6 +404,10 @@ def run_native(args, rank, world, local_rank):
         alg["stft_gemm"] = ("tensor", alg["stft_gemm"][1] + 2 * bins * N_MELS, "FLOP")
         acc["stft_gemm"] = acc.get("stft_gemm", 0.0) + acc.pop("mel_db", 0.0)
         alg.pop("mel_db")
+    if col:
+        # rows in and rows out, 256 + 61 float32 columns each, expressed per hop-frame
+        moved = (int(col["a_off"][-1]) + int(col["o_off"][-1])) * (256 + FACIAL_COLS) * 4
+        alg["collect"] = ("hbm", moved / frames, "B")
     kernels = []
     for name, (bound, units, unit) in alg.items():
         ms = acc.get(name, 0.0)
@@ -422,11 +475,14 @@ def run_native(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": desc, "clips_per_gpu": n_clips, "audio_seconds_per_gpu_step": audio_s,
                    "rows_per_gpu_step": rows, "hop_frames_per_gpu_step": frames, "pcm": "float32",
+                   "collect_rows_per_gpu_step": int(col["o_off"][-1]) if col else None,
                    "sharding": f"by clip, {world} rank(s), no collective", "cpu_affinity": numa,
                    "l2": f"inputs {packed.nbytes / 1e6:.0f} MB + intermediates exceed the 126 MB L2 every step"},
         "e2e": {"value": total_audio * args.steps / e2e_s, "unit": "audio-s/s",
-                "h2d_bytes_per_step": int(packed.nbytes), "d2h_bytes_per_step": int(rows * 256 * 4),
-                "ms_per_step": e2e_s / args.steps * 1e3, "api": "nsf_extract_host (pinned host buffers)"},
+                "h2d_bytes_per_step": int(packed.nbytes) + (int(rows * 256 * 4 + col["facial_h"].nbytes) if col else 0),
+                "d2h_bytes_per_step": int(rows * 256 * 4) + (int(col["o_off"][-1]) * (256 + FACIAL_COLS) * 4 if col else 0),
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "api": "nsf_extract_host (pinned host buffers)" + (" + nsf_collect_host (float32)" if col else "")},
         "e2e_int16_pcm": {"value": total_audio * args.steps / e2e16_s, "unit": "audio-s/s",
                           "h2d_bytes_per_step": int(pcm16.nbytes), "d2h_bytes_per_step": int(rows * 256 * 4),
                           "ms_per_step": e2e16_s / args.steps * 1e3,

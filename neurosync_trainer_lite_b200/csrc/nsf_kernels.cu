@@ -905,6 +905,30 @@ __device__ __forceinline__ T version_value(const T* __restrict__ src, int64_t ld
   return A::mul(A::add(slow(j - 1), slow(j)), static_cast<T>(0.5));  // smooth_facial_data
 }
 
+// float4 form of version_value for the float32 audio block (256 columns): four columns per lane and load,
+// the same operations in the same order per component.
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+__device__ __forceinline__ float4 mul4(float4 a, float s) {
+  return make_float4(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s), __fmul_rn(a.w, s));
+}
+__device__ __forceinline__ float4 mul4s(float s, float4 a) {      // scalar first, like A::mul(w, val)
+  return make_float4(__fmul_rn(s, a.x), __fmul_rn(s, a.y), __fmul_rn(s, a.z), __fmul_rn(s, a.w));
+}
+__device__ __forceinline__ float4 version_value4(const float* __restrict__ src, int64_t ld, int ver, int64_t j,
+                                                 int c4, bool smooth_slow) {
+  auto at = [&](int64_t row) { return __ldg(reinterpret_cast<const float4*>(src + row * ld) + c4); };
+  auto slow = [&](int64_t k) -> float4 {
+    if ((k & 1) == 0) return at(k >> 1);
+    return mul4(add4(at(k >> 1), at((k >> 1) + 1)), 0.5f);
+  };
+  if (ver == 0) return at(j);
+  if (ver == 1) return at(2 * j);
+  if (!smooth_slow || j == 0) return slow(j);
+  return mul4(add4(slow(j - 1), slow(j)), 0.5f);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) k_collect(CollectView v, const T* __restrict__ audio,
                                                  int a_cols, const T* __restrict__ facial, int f_cols,
@@ -964,6 +988,97 @@ __global__ void __launch_bounds__(128) k_collect(CollectView v, const T* __restr
       }
       if (is_a) out_audio[r * a_cols + cc] = val; else out_facial[r * f_cols + cc] = val;
     }
+  }
+}
+
+// Product variant of k_collect: a WARP per output row, every warp walking a contiguous run of rows.  The
+// stack geometry of a clip (trim offsets, version lengths, blend zones) is derived once per clip and kept in
+// registers - it was recomputed, behind a chain of dependent loads, by all 128 threads of a block for every
+// single row - and the lanes stream the 256 + 61 columns of the row with fully coalesced 128-byte requests.
+// Same arithmetic (Arith<T>, linspace_at, version_value), so the float64 variant stays bit-exact.
+template <typename T>
+__global__ void __launch_bounds__(256) k_collect_rows(CollectView v, const T* __restrict__ audio, int a_cols,
+                                                      const T* __restrict__ facial, int f_cols,
+                                                      T* __restrict__ out_audio, T* __restrict__ out_facial) {
+  using A = Arith<T>;
+  const int lane = threadIdx.x & 31, wr = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * wpb;
+  const int64_t chunk = (v.total_out_rows + n_warps - 1) / n_warps;
+  const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * wpb + wr) * chunk;
+  const int64_t r_end = min(r_begin + chunk, v.total_out_rows);
+  int64_t clip_o0 = 0, clip_o_end = -1, a0 = 0, f0 = 0;
+  int ver[3] = {0, 0, 0};
+  int nv = 0;
+  int64_t len_before[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
+  for (int64_t r = r_begin; r < r_end; ++r) {
+    if (r >= clip_o_end) {
+      const int clip = find_segment(v.o_off, v.n_clips, r);
+      clip_o0 = __ldg(v.o_off + clip);
+      clip_o_end = __ldg(v.o_off + clip + 1);
+      a0 = __ldg(v.a_off + clip);
+      f0 = __ldg(v.f_off + clip);
+      const int64_t na = __ldg(v.a_off + clip + 1) - a0, nf = __ldg(v.f_off + clip + 1) - f0;
+      // centre-trim the longer stream (data_processing.py:126-145)
+      if (na > nf) a0 += (na - nf) / 2; else if (nf > na) f0 += (nf - na) / 2;
+      const int64_t n = min(na, nf);
+      // version lengths and blend zones (stack_with_blend, data_processing.py:179-197)
+      int64_t vlen[3];
+      nv = 0;
+      ver[nv] = 0; vlen[nv++] = n;
+      if (v.flags & NSF_COLLECT_FAST) { ver[nv] = 1; vlen[nv++] = (n + 1) / 2; }
+      if (v.flags & NSF_COLLECT_SLOW) { ver[nv] = 2; vlen[nv++] = n > 0 ? 2 * n - 1 : 0; }
+      const bool blend = (v.flags & NSF_COLLECT_BLEND) != 0;
+      int64_t total = vlen[0];
+      len_before[0] = 0; nb[0] = 0;
+      for (int i = 1; i < nv; ++i) {
+        int64_t k = blend ? min(min(static_cast<int64_t>(v.blend_frames), total), vlen[i]) : 0;
+        if (k < 0) k = 0;
+        len_before[i] = total; nb[i] = k;
+        total += vlen[i] - k;
+      }
+    }
+    const int64_t p = r - clip_o0;
+    // Resolve row p by walking from the last stacked version down (see k_collect).
+    int term_ver = ver[0];
+    int64_t term_row = p;
+    int n_blend = 0, blend_level[2] = {0, 0};
+    int64_t blend_q[2] = {0, 0};
+    for (int level = nv - 1; level >= 1; --level) {
+      const int64_t L = len_before[level], k = nb[level];
+      if (p >= L) { term_ver = ver[level]; term_row = p - L + k; break; }
+      if (p >= L - k) { blend_level[n_blend] = level; blend_q[n_blend] = p - (L - k); ++n_blend; }
+    }
+    T w1[2] = {static_cast<T>(0), static_cast<T>(0)}, w2[2] = {static_cast<T>(0), static_cast<T>(0)};
+    for (int bi = 0; bi < n_blend; ++bi) {
+      w1[bi] = static_cast<T>(linspace_at(1.0, 0.0, nb[blend_level[bi]], blend_q[bi]));
+      w2[bi] = static_cast<T>(linspace_at(0.0, 1.0, nb[blend_level[bi]], blend_q[bi]));
+    }
+    auto row_out = [&](const T* src, int64_t ld, int cols, bool smooth_slow, T* dst) {
+      for (int c = lane; c < cols; c += 32) {
+        T val = version_value<T>(src, ld, term_ver, term_row, c, smooth_slow);
+        for (int bi = n_blend - 1; bi >= 0; --bi) {
+          const T nv_val = version_value<T>(src, ld, ver[blend_level[bi]], blend_q[bi], c, smooth_slow);
+          val = A::add(A::mul(w1[bi], val), A::mul(w2[bi], nv_val));
+        }
+        dst[c] = val;
+      }
+    };
+    if (sizeof(T) == 4 && (a_cols & 3) == 0) {
+      // float32 audio block: 16 bytes per lane and request (a row of 256 columns is two warp requests)
+      const float* src = reinterpret_cast<const float*>(audio) + a0 * a_cols;
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_audio) + r * a_cols);
+      for (int c4 = lane; c4 < (a_cols >> 2); c4 += 32) {
+        float4 val = version_value4(src, a_cols, term_ver, term_row, c4, false);
+        for (int bi = n_blend - 1; bi >= 0; --bi) {
+          const float4 nv_val = version_value4(src, a_cols, ver[blend_level[bi]], blend_q[bi], c4, false);
+          val = add4(mul4s(static_cast<float>(w1[bi]), val), mul4s(static_cast<float>(w2[bi]), nv_val));
+        }
+        dst[c4] = val;
+      }
+    } else {
+      row_out(audio + a0 * a_cols, a_cols, a_cols, false, out_audio + r * a_cols);
+    }
+    row_out(facial + f0 * f_cols, f_cols, f_cols, true, out_facial + r * f_cols);
   }
 }
 
@@ -1196,6 +1311,21 @@ int launch_smooth(cudaStream_t s, const BatchView& b, const float* in, int64_t i
 int launch_collect(cudaStream_t s, int dtype, const CollectView& v, const void* audio, int a_cols,
                    const void* facial, int f_cols, void* out_audio, void* out_facial) {
   if (v.total_out_rows == 0) return 0;
+  // NSF_COLLECT_BLOCKROW=1 keeps the block-per-row kernel (validation / A-B timing)
+  static const bool block_row = std::getenv("NSF_COLLECT_BLOCKROW") != nullptr;
+  if (!block_row) {
+    const int grid = grid_for(v.total_out_rows, 8 * 8, kSmCount * 8);       // >= 8 rows per warp when there are enough
+    if (dtype == NSF_F64)
+      k_collect_rows<double><<<grid, 256, 0, s>>>(v, static_cast<const double*>(audio), a_cols,
+                                                  static_cast<const double*>(facial), f_cols,
+                                                  static_cast<double*>(out_audio), static_cast<double*>(out_facial));
+    else
+      k_collect_rows<float><<<grid, 256, 0, s>>>(v, static_cast<const float*>(audio), a_cols,
+                                                 static_cast<const float*>(facial), f_cols,
+                                                 static_cast<float*>(out_audio), static_cast<float*>(out_facial));
+    NSF_CHECK_LAUNCH();
+    return 1;
+  }
   const int grid = grid_for(v.total_out_rows, 1, kSmCount * 32);
   if (dtype == NSF_F64)
     k_collect<double><<<grid, 128, 0, s>>>(v, static_cast<const double*>(audio), a_cols,

@@ -241,6 +241,47 @@ class Engine:
         return ((nv.COLLECT_FAST if include_fast else 0) | (nv.COLLECT_SLOW if include_slow else 0) |
                 (nv.COLLECT_BLEND if blend_boundaries else 0))
 
+    def collect_rows(self, audio_offsets, facial_offsets, include_fast=True, include_slow=False,
+                     blend_boundaries=True, blend_frames=30):
+        """Prefix sum of ``nsf_collect_rows`` per clip (output packing of the collect calls)."""
+        a_off = np.asarray(audio_offsets, dtype=np.int64)
+        f_off = np.asarray(facial_offsets, dtype=np.int64)
+        flags = self.collect_flags(include_fast, include_slow, blend_boundaries)
+        rows = [nv.lib.nsf_collect_rows(int(a_off[i + 1] - a_off[i]), int(f_off[i + 1] - f_off[i]), flags,
+                                        int(blend_frames)) for i in range(len(a_off) - 1)]
+        o_off = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(rows, out=o_off[1:])
+        return o_off
+
+    def collect_device(self, audio, audio_offsets, facial, facial_offsets, include_fast=True,
+                       include_slow=False, blend_boundaries=True, blend_frames=30, out_audio=None,
+                       out_facial=None, stream=None, out_offsets=None):
+        """Device-resident ``collect_features`` arithmetic (``nsf_collect_batch``): CUDA tensors in
+        (float32 or float64, packed rows), CUDA tensors out.  Stream-ordered, no host sync."""
+        import torch
+        assert audio.is_cuda and facial.is_cuda and audio.dtype == facial.dtype
+        assert audio.is_contiguous() and facial.is_contiguous()
+        dtype = {torch.float32: nv.F32, torch.float64: nv.F64}[audio.dtype]
+        a_off, a_p = nv.i64_array(audio_offsets)
+        f_off, f_p = nv.i64_array(facial_offsets)
+        # out_offsets: the caller's cached result of collect_rows() for these inputs (saves n_clips small calls)
+        o_off = (self.collect_rows(a_off, f_off, include_fast, include_slow, blend_boundaries, blend_frames)
+                 if out_offsets is None else np.ascontiguousarray(out_offsets, dtype=np.int64))
+        _, o_p = nv.i64_array(o_off)
+        n_out = int(o_off[-1])
+        if out_audio is None:
+            out_audio = torch.empty((n_out, audio.shape[1]), dtype=audio.dtype, device=audio.device)
+        if out_facial is None:
+            out_facial = torch.empty((n_out, facial.shape[1]), dtype=audio.dtype, device=audio.device)
+        s = torch.cuda.current_stream(audio.device) if stream is None else stream
+        flags = self.collect_flags(include_fast, include_slow, blend_boundaries)
+        with self._lock:
+            nv.check(nv.lib.nsf_collect_batch(
+                self.handle, C.c_void_p(s.cuda_stream), dtype, C.c_void_p(audio.data_ptr()), audio.shape[1], a_p,
+                C.c_void_p(facial.data_ptr()), facial.shape[1], f_p, len(a_off) - 1, flags, int(blend_frames),
+                C.c_void_p(out_audio.data_ptr()), C.c_void_p(out_facial.data_ptr()), o_p))
+        return out_audio, out_facial, o_off
+
     def collect_host(self, audio, audio_offsets, facial, facial_offsets, include_fast=True,
                      include_slow=False, blend_boundaries=True, blend_frames=30):
         """Packed row-major audio / facial rows (same float dtype) -> augmented (audio, facial, offsets)."""
