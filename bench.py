@@ -345,13 +345,24 @@ def run_native(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         eng.extract_host(h_in, off, 0, out=h_out)
     barrier()
+    if col:                                           # pinned staging for the fused extract + collect call
+        n_o = int(col["o_off"][-1])
+        pin_f = engine.PinnedBuffer(col["facial_h"].nbytes)
+        pin_oa = engine.PinnedBuffer(n_o * 256 * 4)
+        pin_of = engine.PinnedBuffer(n_o * FACIAL_COLS * 4)
+        h_f = pin_f.view(np.float32, col["facial_h"].shape)
+        h_f[:] = col["facial_h"]
+        h_oa, h_of = pin_oa.view(np.float32, (n_o, 256)), pin_of.view(np.float32, (n_o, FACIAL_COLS))
+
     def host_step():
-        eng.extract_host(h_in, off, 0, out=h_out)     # synchronous: returns when rows are on the host
-        if col:                                       # nsf_collect_host: rows and facial data up, augmented rows back
-            return eng.collect_host(h_out, col["a_off"], col["facial_h"], col["f_off"], **collect)
+        if col:       # nsf_extract_collect_host: PCM and facial rows up, augmented rows back, features stay on the device
+            eng.extract_collect_host(h_in, off, h_f, col["f_off"], 0, out_audio=h_oa, out_facial=h_of, **collect)
+        else:
+            eng.extract_host(h_in, off, 0, out=h_out)     # synchronous: returns when rows are on the host
 
     if col:
         host_step()
+        eng.extract_host(h_in, off, 0, out=h_out)         # clip 0 rows for the parity spot check below
     t0 = time.perf_counter()
     for _ in range(args.steps):
         host_step()
@@ -479,10 +490,10 @@ def run_native(args, rank, world, local_rank):
                    "sharding": f"by clip, {world} rank(s), no collective", "cpu_affinity": numa,
                    "l2": f"inputs {packed.nbytes / 1e6:.0f} MB + intermediates exceed the 126 MB L2 every step"},
         "e2e": {"value": total_audio * args.steps / e2e_s, "unit": "audio-s/s",
-                "h2d_bytes_per_step": int(packed.nbytes) + (int(rows * 256 * 4 + col["facial_h"].nbytes) if col else 0),
-                "d2h_bytes_per_step": int(rows * 256 * 4) + (int(col["o_off"][-1]) * (256 + FACIAL_COLS) * 4 if col else 0),
+                "h2d_bytes_per_step": int(packed.nbytes) + (int(col["facial_h"].nbytes) if col else 0),
+                "d2h_bytes_per_step": (int(col["o_off"][-1]) * (256 + FACIAL_COLS) * 4 if col else int(rows * 256 * 4)),
                 "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "nsf_extract_host (pinned host buffers)" + (" + nsf_collect_host (float32)" if col else "")},
+                "api": "nsf_extract_collect_host (pinned host buffers)" if col else "nsf_extract_host (pinned host buffers)"},
         "e2e_int16_pcm": {"value": total_audio * args.steps / e2e16_s, "unit": "audio-s/s",
                           "h2d_bytes_per_step": int(pcm16.nbytes), "d2h_bytes_per_step": int(rows * 256 * 4),
                           "ms_per_step": e2e16_s / args.steps * 1e3,

@@ -185,6 +185,19 @@ NSF_API nsf_status nsf_collect_host(nsf_ctx* ctx, int32_t dtype, const void* aud
                             int32_t n_clips, uint32_t collect_flags, int32_t blend_frames,
                             void* out_audio_host, void* out_facial_host);
 
+/* Fused host entry point for the dataset builders (dataset/data_processing.py:44-78 process_folder ->
+ * :108-177 collect_features): features of a batch of clips AND their collect_features augmentation in one
+ * pipelined pass.  The feature rows never leave the device between the two steps - only PCM and facial rows go
+ * up, only augmented rows come back.  float32 throughout (the training format, dataset/dataset.py:75); the
+ * float64 bit-exact arithmetic of the reference remains available through nsf_collect_host.  Clip i owns
+ * samples [clip_offsets[i], clip_offsets[i+1]) of pcm and rows [facial_offsets[i], facial_offsets[i+1]) of
+ * facial; outputs are packed at the prefix sum of nsf_collect_rows(nsf_feature_rows(..), facial rows, ..). */
+NSF_API nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
+                                            const int64_t* clip_offsets_host, int32_t n_clips, uint32_t flags,
+                                            const float* facial_host, int32_t facial_cols,
+                                            const int64_t* facial_offsets_host, uint32_t collect_flags,
+                                            int32_t blend_frames, float* out_audio_host, float* out_facial_host);
+
 /* ---- stand-alone array helpers of the reference API, on HOST arrays --------------------------
  * Row-wise helpers of dataset/data_processing.py (float32 or float64, the reference's exact
  * rounding order), computed on the device:

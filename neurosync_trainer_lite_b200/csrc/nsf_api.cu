@@ -129,6 +129,7 @@ struct PinnedArena {
 struct Slot {  // one in-flight clip group of the host pipeline
   cudaStream_t stream = nullptr;
   Arena pcm, out, work, ynorm;
+  Arena fac_in, col_a, col_f, col_desc;   // fused extract + collect path
   cudaEvent_t done = nullptr;
 };
 
@@ -406,6 +407,7 @@ void nsf_ctx_destroy(nsf_ctx* ctx) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
     s.pcm.release(); s.out.release(); s.work.release(); s.ynorm.release();
+    s.fac_in.release(); s.col_a.release(); s.col_f.release(); s.col_desc.release();
   }
   for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
   if (ctx->desc_copied) cudaEventDestroy(ctx->desc_copied);
@@ -838,6 +840,95 @@ nsf_status nsf_collect_host(nsf_ctx* ctx, int32_t dtype, const void* audio_host,
   NSF_CUDA(cudaMemcpyAsync(out_audio_host, ctx->collect_out_a.ptr, o_rows * audio_cols * esz, cudaMemcpyDeviceToHost, sl->stream));
   NSF_CUDA(cudaMemcpyAsync(out_facial_host, ctx->collect_out_f.ptr, o_rows * facial_cols * esz, cudaMemcpyDeviceToHost, sl->stream));
   NSF_CUDA(cudaStreamSynchronize(sl->stream));
+  return NSF_OK;
+}
+
+// ---- fused extract + collect (dataset builders) -------------------------------------------------------
+nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
+                                    const int64_t* clip_offsets, int32_t n_clips, uint32_t flags,
+                                    const float* facial_host, int32_t facial_cols, const int64_t* f_off,
+                                    uint32_t collect_flags, int32_t blend_frames, float* out_audio_host,
+                                    float* out_facial_host) {
+  if (!ctx || !pcm_host || !clip_offsets || !facial_host || !f_off || !out_audio_host || !out_facial_host ||
+      n_clips <= 0 || facial_cols <= 0) {
+    set_error("nsf_extract_collect_host: NULL argument"); return NSF_ERR_BAD_ARG;
+  }
+  if (pcm_format != NSF_PCM_F32 && pcm_format != NSF_PCM_I16) { set_error("unknown pcm_format"); return NSF_ERR_BAD_ARG; }
+  const Plan& p = ctx->plan->p;
+  const int cols = nsf_feature_cols(ctx->plan, flags);
+  HostDesc all;
+  nsf_status st = build_desc(p, clip_offsets, n_clips, flags, nullptr, &all);
+  if (st != NSF_OK) return st;
+  // output packing over the whole batch (validates the facial offsets)
+  std::vector<int64_t> a_rows(n_clips + 1), o_all;
+  for (int i = 0; i <= n_clips; ++i) a_rows[i] = all.row_off[i];
+  if ((st = collect_offsets(a_rows.data(), f_off, n_clips, collect_flags, blend_frames, nullptr, &o_all)) != NSF_OK) return st;
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = pcm_format == NSF_PCM_I16 ? 2 : 4;
+  const int64_t kGroupSamples = int64_t(24) << 20;
+  int first = 0, turn = 0;
+  while (first < n_clips) {
+    int last = first;
+    int64_t samples = 0;
+    while (last < n_clips && (last == first || samples + (clip_offsets[last + 1] - clip_offsets[last]) <= kGroupSamples)) {
+      samples += clip_offsets[last + 1] - clip_offsets[last];
+      ++last;
+    }
+    const int gn = last - first;
+    Slot* sl = &ctx->slot[turn & 1];
+    if ((st = ensure_slot(sl)) != NSF_OK) return st;
+    NSF_CUDA(cudaStreamSynchronize(sl->stream));      // the slot's previous group has fully drained
+    const int64_t rows = all.row_off[last] - all.row_off[first];
+    const int64_t frows = f_off[last] - f_off[first];
+    const int64_t orows = o_all[last] - o_all[first];
+    const int64_t wbytes = nsf_workspace_bytes(ctx->plan, samples, gn, flags);
+    const size_t n1 = static_cast<size_t>(gn) + 1;
+    if ((st = sl->pcm.reserve(samples * esz)) != NSF_OK) return st;
+    if ((st = sl->out.reserve(static_cast<size_t>(rows) * cols * sizeof(float))) != NSF_OK) return st;
+    if ((st = sl->work.reserve(wbytes)) != NSF_OK) return st;
+    if ((st = sl->fac_in.reserve(static_cast<size_t>(frows) * facial_cols * sizeof(float))) != NSF_OK) return st;
+    if ((st = sl->col_a.reserve(static_cast<size_t>(orows) * cols * sizeof(float))) != NSF_OK) return st;
+    if ((st = sl->col_f.reserve(static_cast<size_t>(orows) * facial_cols * sizeof(float))) != NSF_OK) return st;
+    if ((st = sl->col_desc.reserve(3 * n1 * sizeof(int64_t))) != NSF_OK) return st;
+    const char* src = static_cast<const char*>(pcm_host) + clip_offsets[first] * esz;
+    NSF_CUDA(cudaMemcpyAsync(sl->pcm.ptr, src, samples * esz, cudaMemcpyHostToDevice, sl->stream));
+    NSF_CUDA(cudaMemcpyAsync(sl->fac_in.ptr, facial_host + f_off[first] * facial_cols,
+                             static_cast<size_t>(frows) * facial_cols * sizeof(float), cudaMemcpyHostToDevice, sl->stream));
+    // collect descriptors of this group (relative offsets) through the guarded pinned staging buffer.  Staged
+    // BEFORE the extraction kernels are enqueued: the next wait on the staging buffer then ends as soon as this
+    // group's uploads have run, so the host can start the next group's upload while these kernels execute
+    if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
+    if ((st = ctx->desc_host.reserve(3 * n1 * sizeof(int64_t))) != NSF_OK) return st;
+    int64_t* h = static_cast<int64_t*>(ctx->desc_host.ptr);
+    for (size_t i = 0; i < n1; ++i) {
+      h[i] = all.row_off[first + i] - all.row_off[first];
+      h[n1 + i] = f_off[first + i] - f_off[first];
+      h[2 * n1 + i] = o_all[first + i] - o_all[first];
+    }
+    int64_t* d = static_cast<int64_t*>(sl->col_desc.ptr);
+    NSF_CUDA(cudaMemcpyAsync(d, h, 3 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, sl->stream));
+    NSF_CUDA(cudaEventRecord(ctx->desc_copied, sl->stream));
+    ctx->desc_pending = true;
+    st = nsf_extract_batch(ctx, sl->stream, sl->pcm.ptr, pcm_format, clip_offsets + first, gn, flags,
+                           static_cast<float*>(sl->out.ptr), cols, nullptr, nullptr, sl->work.ptr,
+                           static_cast<int64_t>(sl->work.bytes));
+    if (st != NSF_OK) return st;
+    CollectView v;
+    v.a_off = d; v.f_off = d + n1; v.o_off = d + 2 * n1;
+    v.n_clips = gn; v.total_out_rows = orows; v.flags = collect_flags; v.blend_frames = blend_frames;
+    const int n = launch_collect(sl->stream, NSF_F32, v, sl->out.ptr, cols, sl->fac_in.ptr, facial_cols, sl->col_a.ptr,
+                                 sl->col_f.ptr);
+    if (n < 0) { set_error(cuda_msg("launch_collect", cudaGetLastError())); return NSF_ERR_CUDA; }
+    ctx->launches += n;
+    NSF_CUDA(cudaMemcpyAsync(out_audio_host + o_all[first] * cols, sl->col_a.ptr,
+                             static_cast<size_t>(orows) * cols * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+    NSF_CUDA(cudaMemcpyAsync(out_facial_host + o_all[first] * facial_cols, sl->col_f.ptr,
+                             static_cast<size_t>(orows) * facial_cols * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+    first = last;
+    ++turn;
+  }
+  for (auto& sl : ctx->slot)
+    if (sl.stream) NSF_CUDA(cudaStreamSynchronize(sl.stream));
   return NSF_OK;
 }
 

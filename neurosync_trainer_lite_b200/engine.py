@@ -282,6 +282,33 @@ class Engine:
                 C.c_void_p(out_audio.data_ptr()), C.c_void_p(out_facial.data_ptr()), o_p))
         return out_audio, out_facial, o_off
 
+    def extract_collect_host(self, pcm, offsets, facial, facial_offsets, flags=0, include_fast=True,
+                             include_slow=False, blend_boundaries=True, blend_frames=30, out_audio=None,
+                             out_facial=None):
+        """Features of a batch of clips AND their ``collect_features`` augmentation in one pipelined pass
+        (``nsf_extract_collect_host``): the feature rows stay on the device between the two steps.
+        float32 in (facial) and out; returns (audio rows, facial rows, output row offsets)."""
+        pcm = np.ascontiguousarray(pcm)
+        fmt = self._pcm_format(pcm)
+        facial = np.ascontiguousarray(facial, dtype=np.float32)
+        off, off_p = nv.i64_array(offsets)
+        f_off, f_p = nv.i64_array(facial_offsets)
+        cols = self.plan.feature_cols(flags)
+        o_off = self.collect_rows(self.row_offsets(off, flags), f_off, include_fast, include_slow,
+                                  blend_boundaries, blend_frames)
+        n_out = int(o_off[-1])
+        if out_audio is None:
+            out_audio = np.empty((n_out, cols), dtype=np.float32)
+        if out_facial is None:
+            out_facial = np.empty((n_out, facial.shape[1]), dtype=np.float32)
+        assert out_audio.shape == (n_out, cols) and out_facial.shape == (n_out, facial.shape[1])
+        cflags = self.collect_flags(include_fast, include_slow, blend_boundaries)
+        with self._lock:
+            nv.check(nv.lib.nsf_extract_collect_host(self.handle, nv.ptr(pcm), fmt, off_p, len(off) - 1, flags,
+                                                     nv.ptr(facial), facial.shape[1], f_p, cflags,
+                                                     int(blend_frames), nv.ptr(out_audio), nv.ptr(out_facial)))
+        return out_audio, out_facial, o_off
+
     def collect_host(self, audio, audio_offsets, facial, facial_offsets, include_fast=True,
                      include_slow=False, blend_boundaries=True, blend_frames=30):
         """Packed row-major audio / facial rows (same float dtype) -> augmented (audio, facial, offsets)."""

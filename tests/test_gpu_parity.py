@@ -491,3 +491,24 @@ def test_properties_at_c5_scale(engine, oracle):
         want = oracle.extract_and_combine_features(base[s], 16000, 266, 133)
         d = np.abs(r[s] - want)
         assert d[:, :69].max() < 1e-3 and d[:, 69:].max() < 2e-5
+
+
+def test_fused_extract_collect_equals_two_calls(engine, nv):
+    """nsf_extract_collect_host (features stay on the device) == nsf_extract_host followed by nsf_collect_host,
+    bit for bit in float32, on a ragged batch that spans several pipeline groups."""
+    eng = engine.get_engine(88200, 1470, 735)
+    secs = [0.9, 2.3, 0.4, 31.0, 1.7, 30.0, 12.0, 30.5, 29.0, 3.1]          # > 24 Mi samples in total: 2+ groups
+    clips = [synth.synth_clip(s, 88200, seed=60 + i, kind=("voiced", "gated", "noise")[i % 3]) for i, s in enumerate(secs)]
+    packed, off = engine.pack_clips(clips)
+    roff = eng.row_offsets(off)
+    n_f = [int(roff[i + 1] - roff[i]) + (i % 3) - 1 for i in range(len(clips))]   # facial rows: R-1, R, R+1
+    facial = np.concatenate([synth.synth_facial(n, seed=i) for i, n in enumerate(n_f)]).astype(np.float32)
+    f_off = np.concatenate([[0], np.cumsum(n_f)]).astype(np.int64)
+    for kw in (dict(include_fast=True, include_slow=False), dict(include_fast=True, include_slow=True),
+               dict(include_fast=False, include_slow=False, blend_boundaries=False)):
+        rows = eng.extract_host(packed, off)
+        wa, wf, wo = eng.collect_host(rows, roff, facial, f_off, blend_frames=30, **kw)
+        ga, gf, go = eng.extract_collect_host(packed, off, facial, f_off, blend_frames=30, **kw)
+        assert np.array_equal(go, wo)
+        np.testing.assert_array_equal(ga, wa)
+        np.testing.assert_array_equal(gf, wf)
