@@ -126,6 +126,15 @@ struct PinnedArena {
   void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; bytes = 0; }
 };
 
+// Host pipeline: clip groups rotate over three slots (stream + arenas each), so the upload of group g+1, the
+// kernels of group g and the download of group g-1 overlap without the upload engine ever waiting for a
+// download to release its slot.  The first groups are small (the pipeline fills after a short upload instead of
+// a 96 MB one), later groups carry up to 24 Mi samples.
+constexpr int kSlots = 3;
+constexpr int64_t kGroupSamples = int64_t(24) << 20;       // ~96 MB of float32 PCM per in-flight group
+constexpr int64_t kFirstGroupSamples = int64_t(6) << 20;   // groups 0 and 1
+inline int64_t group_budget(int turn) { return turn < 2 ? kFirstGroupSamples : kGroupSamples; }
+
 struct Slot {  // one in-flight clip group of the host pipeline
   cudaStream_t stream = nullptr;
   Arena pcm, out, work, ynorm;
@@ -145,7 +154,7 @@ struct nsf_ctx {
   nsf::PinnedArena desc_host;
   cudaEvent_t desc_copied = nullptr;
   bool desc_pending = false;
-  nsf::Slot slot[2];
+  nsf::Slot slot[nsf::kSlots];
   int64_t launches = 0;
   bool profiling = false;
   cudaEvent_t stage_ev[nsf::kStages + 1] = {};
@@ -609,17 +618,16 @@ nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_form
   if (st != NSF_OK) return st;
   NSF_CUDA(cudaSetDevice(ctx->device));
   const size_t esz = pcm_format == NSF_PCM_I16 ? 2 : 4;
-  const int64_t kGroupSamples = int64_t(24) << 20;  // ~96 MB of float32 PCM per in-flight group
   int first = 0, turn = 0;
   while (first < n_clips) {
     int last = first;
     int64_t samples = 0;
-    while (last < n_clips && (last == first || samples + (clip_offsets[last + 1] - clip_offsets[last]) <= kGroupSamples)) {
+    while (last < n_clips && (last == first || samples + (clip_offsets[last + 1] - clip_offsets[last]) <= group_budget(turn))) {
       samples += clip_offsets[last + 1] - clip_offsets[last];
       ++last;
     }
     const int gn = last - first;
-    Slot* sl = &ctx->slot[turn & 1];
+    Slot* sl = &ctx->slot[turn % kSlots];
     st = ensure_slot(sl);
     if (st != NSF_OK) return st;
     // the slot's previous group must have fully drained before its buffers are reused
@@ -865,17 +873,16 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
   if ((st = collect_offsets(a_rows.data(), f_off, n_clips, collect_flags, blend_frames, nullptr, &o_all)) != NSF_OK) return st;
   NSF_CUDA(cudaSetDevice(ctx->device));
   const size_t esz = pcm_format == NSF_PCM_I16 ? 2 : 4;
-  const int64_t kGroupSamples = int64_t(24) << 20;
   int first = 0, turn = 0;
   while (first < n_clips) {
     int last = first;
     int64_t samples = 0;
-    while (last < n_clips && (last == first || samples + (clip_offsets[last + 1] - clip_offsets[last]) <= kGroupSamples)) {
+    while (last < n_clips && (last == first || samples + (clip_offsets[last + 1] - clip_offsets[last]) <= group_budget(turn))) {
       samples += clip_offsets[last + 1] - clip_offsets[last];
       ++last;
     }
     const int gn = last - first;
-    Slot* sl = &ctx->slot[turn & 1];
+    Slot* sl = &ctx->slot[turn % kSlots];
     if ((st = ensure_slot(sl)) != NSF_OK) return st;
     NSF_CUDA(cudaStreamSynchronize(sl->stream));      // the slot's previous group has fully drained
     const int64_t rows = all.row_off[last] - all.row_off[first];
