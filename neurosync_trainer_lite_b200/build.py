@@ -69,17 +69,23 @@ def build(force=False, verbose=False):
                 return LIB_PATH
             tmp = tempfile.mkdtemp(prefix=".build-", dir=LIB_DIR)
             try:
-                objs = []
-                for src in SOURCES:
+                from concurrent.futures import ThreadPoolExecutor
+
+                def compile_one(src):
                     obj = os.path.join(tmp, os.path.splitext(src)[0] + ".o")
                     cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                            "-DNSF_BUILDING=1", "-c", os.path.join(CSRC, src), "-o", obj]
                     res = subprocess.run(cmd, capture_output=True, text=True)
-                    if verbose or res.returncode != 0:
-                        sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
-                    if res.returncode != 0:
-                        raise RuntimeError(f"nvcc failed on {src}")
-                    objs.append(obj)
+                    return src, obj, cmd, res
+
+                objs = []
+                with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+                    for src, obj, cmd, res in pool.map(compile_one, SOURCES):     # translation units in parallel
+                        if verbose or res.returncode != 0:
+                            sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+                        if res.returncode != 0:
+                            raise RuntimeError(f"nvcc failed on {src}")
+                        objs.append(obj)
                 lib_tmp = os.path.join(tmp, "libnsf.so")
                 cmd = [_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
                        "-o", lib_tmp, *objs]
