@@ -149,6 +149,8 @@ struct nsf_ctx {
   int device = 0;
   nsf::DeviceTables tables{};
   nsf::StftTcTables tc{};
+  nsf::DctCoef dct_coef{};       // DCT matrix as a kernel parameter (default 128 -> 23 shape only)
+  bool dct_coef_ok = false;
   nsf::Arena table_mem;
   // descriptor staging (pinned), guarded by an event so back-to-back calls cannot race the copy
   nsf::PinnedArena desc_host;
@@ -218,6 +220,11 @@ nsf_status upload_tables(nsf_ctx* ctx) {
   for (int k = 0; k < p.n_mfcc; ++k)
     for (int m = 0; m < p.n_mels; ++m) dct_t[static_cast<size_t>(m) * 32 + k] = p.dct[static_cast<size_t>(k) * p.n_mels + m];
   const size_t off_dct = put(dct_t.data(), dct_t.size() * sizeof(float));
+  ctx->dct_coef_ok = p.n_mels == kDctConstMels && p.n_mfcc == kDctConstMfcc;
+  if (ctx->dct_coef_ok)
+    for (int m = 0; m < kDctConstMels; ++m)
+      for (int k = 0; k < kDctConstMfcc; ++k)
+        ctx->dct_coef.v[m * kDctConstLd + k] = p.dct[static_cast<size_t>(k) * p.n_mels + m];
   // column -> (first filter, two weights) table for the fused mel epilogue of the tcgen05 kernel
   size_t off_melcol[2] = {0, 0};
   int mel_col_ok = 1;
@@ -564,7 +571,8 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
   // stage 4: floor + DCT + CMVN statistics
   timer.mark(4);
   if (do_mfcc) {
-    NSF_LAUNCH(launch_dct_sum(s, t, b, L.db, L.dbmax_key, L.mfcc_raw, L.sum, L.sumsq));
+    NSF_LAUNCH(launch_dct_sum(s, t, b, L.db, L.dbmax_key, L.mfcc_raw, L.sum, L.sumsq,
+                              ctx->dct_coef_ok ? &ctx->dct_coef : nullptr));
   }
   // stage 5: CMVN + deltas + pair reduce -> columns [0, mfcc_cols)
   timer.mark(5);

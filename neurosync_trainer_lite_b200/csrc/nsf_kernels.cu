@@ -527,6 +527,77 @@ __global__ void __launch_bounds__(kDct2Warps * 32, 2) k_dct_rows(DeviceTables t,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 (product variant for the reference's 128 mels -> 23 MFCCs): k_dct_rows with the coefficients in the
+// CONSTANT BANK.  k_dct_rows issues 768 broadcast LDS.128 per 32 frames and stalls on the shared-memory
+// instruction queue (ncu: short_scoreboard + mio_throttle, 0.089 ms on C2 = 22 % of the HBM roofline).  Here
+// the matrix is a kernel parameter, the mel loop is fully unrolled, and ptxas turns every coefficient into
+// a uniform-register FFMA operand fetched by LDCU.128 on the uniform datapath: per frame-lane 2944 FFMA +
+// 128 FMNMX + 32 LDG.128, no LDS.  Same accumulation order over the mels as k_dct_rows / k_dct_sum
+// (bit-identical MFCCs); the staging / moment tail is the same code.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDct2Warps * 32, 3) k_dct_const(const __grid_constant__ DctCoef c, BatchView b,
+                                                                  const float* __restrict__ db,
+                                                                  const uint32_t* __restrict__ dbmax_key,
+                                                                  float* __restrict__ mfcc_raw,
+                                                                  double* __restrict__ sum,
+                                                                  double* __restrict__ sumsq) {
+  constexpr int NM = kDctConstMels, NC = kDctConstMfcc, LD = kDctConstLd;
+  __shared__ float s_stage[kDct2Warps * 32 * NC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_o = s_stage + warp * 32 * NC;
+  const int64_t n_tiles = (b.total_frames + 31) / 32;
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * kDct2Warps + warp; tile < n_tiles;
+       tile += static_cast<int64_t>(gridDim.x) * kDct2Warps) {
+    const int64_t g0 = tile * 32;
+    const int nf = static_cast<int>(min(static_cast<int64_t>(32), b.total_frames - g0));
+    const bool valid = lane < nf;
+    const int clip = valid ? find_segment(b.frame_off, b.n_clips, g0 + lane) : -1;
+    const float floor_db = valid ? key_float(__ldg(dbmax_key + clip)) - 80.0f : 0.0f;
+    const float4* row = reinterpret_cast<const float4*>(db + (g0 + (valid ? lane : 0)) * NM);
+    float acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[k] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < NM / 4; ++q) {
+      const float4 x4 = __ldg(row + q);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x = fmaxf(xs[e], floor_db);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc[k] = fmaf(c.v[(4 * q + e) * LD + k], x, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) s_o[lane * NC + k] = valid ? acc[k] : 0.0f;
+    __syncwarp();
+    for (int i = lane; i < nf * NC; i += 32) mfcc_raw[g0 * NC + i] = s_o[i];
+    const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
+    const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
+    if (uniform) {
+      if (lane < NC && first_clip >= 0) {
+        double ts = 0.0, tq = 0.0;
+        for (int f = 0; f < nf; ++f) {
+          const double a = static_cast<double>(s_o[f * NC + lane]);
+          ts += a;
+          tq = fma(a, a, tq);
+        }
+        atomicAdd(sum + static_cast<int64_t>(first_clip) * NC + lane, ts);
+        atomicAdd(sumsq + static_cast<int64_t>(first_clip) * NC + lane, tq);
+      }
+    } else if (valid) {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const double a = static_cast<double>(acc[k]);
+        atomicAdd(sum + static_cast<int64_t>(clip) * NC + k, a);
+        atomicAdd(sumsq + static_cast<int64_t>(clip) * NC + k, a * a);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: CMVN -> Savitzky-Golay delta / delta-delta (width 9, edges = value at frame 4 / T-5)
 //     -> pair reduction.  Thread per (output row, channel).
 //     extract_features_utils.py:5-8,21-27,33-44; librosa.feature.delta == scipy savgol 'interp'.
@@ -1247,9 +1318,18 @@ int launch_resample(cudaStream_t s, const void* pcm, int pcm_format, int64_t n_i
 }
 
 int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* db,
-                   const uint32_t* dbmax_key, float* mfcc_raw, double* sum, double* sumsq) {
+                   const uint32_t* dbmax_key, float* mfcc_raw, double* sum, double* sumsq,
+                   const DctCoef* coef) {
   if (t.n_mels > 128 || t.n_mfcc > 32) return -1;
   const int kp = t.n_mfcc <= 24 ? 24 : 32;
+  // NSF_DCT_SMEM=1 keeps the shared-memory coefficient kernels for the default shape too (validation / A-B timing)
+  static const bool force_smem = std::getenv("NSF_DCT_SMEM") != nullptr;
+  if (coef && !force_smem && t.n_mels == kDctConstMels && t.n_mfcc == kDctConstMfcc) {
+    const int grid_c = grid_for((b.total_frames + 31) / 32, kDct2Warps, kSmCount * 3);
+    k_dct_const<<<grid_c, kDct2Warps * 32, 0, s>>>(*coef, b, db, dbmax_key, mfcc_raw, sum, sumsq);
+    NSF_CHECK_LAUNCH();
+    return 1;
+  }
   // NSF_DCT_TILE=1 keeps the transposing-tile kernel (validation / A-B timing); it is also the path for
   // mel counts that are not a multiple of 4 (rows would not be 16-byte aligned)
   static const bool force_tile = std::getenv("NSF_DCT_TILE") != nullptr;
