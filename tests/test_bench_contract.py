@@ -8,7 +8,7 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NATIVE = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r01[fgh]_*.json")))
+NATIVE = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r01[fghi]_*.json")))
 REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
 
