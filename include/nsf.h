@@ -10,7 +10,9 @@
  *   - plain C types only; every buffer is caller-owned unless stated otherwise;
  *   - "dev" pointers are CUDA device pointers on the context's device, "host" pointers are CPU
  *     memory (pinned memory makes the *_host calls faster but is not required);
- *   - device-level calls are stream-ordered and never synchronise the host;
+ *   - device-level calls (nsf_extract_batch, nsf_collect_batch) are stream-ordered and do not wait for
+ *     the device: their descriptor arrays travel through a ring of 8 pinned staging buffers, so the
+ *     host blocks only if the descriptor uploads of the 8 previous calls have not run yet;
  *   - every call returns an nsf_status; nsf_last_error() gives a thread-local message;
  *   - one nsf_ctx per device and per host thread; plans are immutable and may be shared.
  *   - there is NO CPU fallback: compute calls fail with NSF_ERR_NO_DEVICE / NSF_ERR_CUDA when no
@@ -57,6 +59,10 @@ typedef enum nsf_status {
 #define NSF_AC_DELTAS 0x020u      /* compute_autocorr_with_deltas (extract_features_utils.py:131-135)*/
 #define NSF_NO_REDUCE 0x040u      /* skip reduce_features: one row per hop-frame (utils API parity)  */
 #define NSF_NO_MFCC 0x080u        /* autocorrelation block only (extract_autocorrelation_features)   */
+#define NSF_AC_NO_PAD 0x800u      /* pad_signal=False of extract_overlapping_autocorr (extract_features_utils.py:54-61):
+                                     frame t = y[t H : t H + F], T = (L - F) // H + 1; needs NSF_NO_MFCC.
+                                     Other padding_mode values / trim_padded are host-side index work around
+                                     this flag (np.pad before the call, column selection after it). */
 #define NSF_DEBUG_SIMT_DFT 0x100u /* validation aid: run the STFT GEMM on CUDA cores in fp32 instead
                                      of tcgen05 (never selected automatically)                      */
 
@@ -130,6 +136,15 @@ NSF_API void nsf_ctx_destroy(nsf_ctx* ctx);
 /* Pinned host memory helpers for callers without their own allocator. */
 NSF_API nsf_status nsf_host_alloc(void** out_ptr, int64_t bytes);
 NSF_API void nsf_host_free(void* ptr);
+/* Page-lock caller memory (cudaHostRegister, portable) so that the *_host calls can DMA into / out of it
+ * directly - e.g. ONE host array shared by the ranks of a box (a /dev/shm mapping every process registers and
+ * fills at its own row offsets: the "gathered to host" array of the multi-GPU dataset builders). */
+NSF_API nsf_status nsf_host_register(void* ptr, int64_t bytes);
+NSF_API nsf_status nsf_host_unregister(void* ptr);
+/* Per-context options.  NSF_OPT_EDGE_ZERO_THRESHOLD: zero_threshold of fix_edge_frames_autocorr
+ * (utils/audio/extraction/extract_features_utils.py:105; default 1e-7). */
+#define NSF_OPT_EDGE_ZERO_THRESHOLD 0
+NSF_API nsf_status nsf_ctx_set_option(nsf_ctx* ctx, int32_t option, double value);
 
 /* ---- feature extraction --------------------------------------------------------------------
  * Replaces, for a BATCH of clips, extract_and_combine_features (extract_features.py:26-46) and,
@@ -153,7 +168,9 @@ NSF_API nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void
                              void* workspace_dev, int64_t workspace_bytes);
 
 /* Same contract with HOST buffers: uploads, extracts and downloads using context-owned device
- * arenas and streams, overlapping H2D / kernels / D2H across clip groups.  Synchronous. */
+ * arenas and streams, overlapping H2D / kernels / D2H across clip groups.  Synchronous.  Pinned (or
+ * registered) buffers are read and written by the copy engines directly; pageable buffers are staged
+ * group by group through context-owned pinned arenas, so the pipeline stays asynchronous either way. */
 NSF_API nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
                             const int64_t* clip_offsets_host, int32_t n_clips, uint32_t flags,
                             float* out_host, int64_t out_ld, float* y_norm_host /* optional */);

@@ -17,6 +17,7 @@ PCM_F32, PCM_I16 = 0, 1
 PEAK_NORMALIZE, NO_AUTOCORR, SMOOTH, NO_CMVN, NO_DELTAS, AC_DELTAS, NO_REDUCE = (
     0x001, 0x002, 0x004, 0x008, 0x010, 0x020, 0x040)
 NO_MFCC = 0x080
+AC_NO_PAD = 0x800
 DEBUG_SIMT_DFT = 0x100
 DEBUG_FMA_AUTOCORR = 0x200
 DEBUG_UNFUSED_MEL = 0x400
@@ -24,6 +25,7 @@ COLLECT_FAST, COLLECT_SLOW, COLLECT_BLEND = 0x1, 0x2, 0x4
 F32, F64 = 0, 1
 TABLE_MEL, TABLE_DCT, TABLE_HANN_SYM, TABLE_HANN_PER = 0, 1, 2, 3
 ROWS_INTERP_SLOWER, ROWS_SMOOTH, ROWS_BLEND_STACK = 0, 1, 2
+OPT_EDGE_ZERO_THRESHOLD = 0
 POST_EDGEFIX, POST_CMVN, POST_DELTAS, POST_REDUCE = 0x1, 0x2, 0x4, 0x8
 STAGE_NAMES = ("peak_normalize", "fold", "stft_gemm", "mel_db", "dct_stats", "cmvn_delta_reduce",
                "autocorr", "post")
@@ -70,6 +72,9 @@ _SIGS = {
     "nsf_ctx_destroy": (None, [_vp]),
     "nsf_host_alloc": (_i32, [C.POINTER(_vp), _i64]),
     "nsf_host_free": (None, [_vp]),
+    "nsf_host_register": (_i32, [_vp, _i64]),
+    "nsf_host_unregister": (_i32, [_vp]),
+    "nsf_ctx_set_option": (_i32, [_vp, _i32, C.c_double]),
     "nsf_workspace_bytes": (_i64, [_vp, _i64, _i32, _u32]),
     "nsf_extract_batch": (_i32, [_vp, _vp, _vp, _i32, _i64p, _i32, _u32, _vp, _i64, _i64p, _vp, _vp,
                                  _i64]),

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nsf.h"
@@ -65,9 +66,9 @@ size_t plan_layout(const Plan& p, const Sizes& z, uint32_t flags, bool need_y, v
                    Layout* L, bool* ok) {
   Carver c(base ? base : reinterpret_cast<void*>(0x1000), base ? cap : ~size_t(0) >> 1);
   const size_t n1 = static_cast<size_t>(z.n_clips) + 1;
-  L->clip_off = c.take<int64_t>(n1);
-  L->frame_off = c.take<int64_t>(n1);
-  L->row_off = c.take<int64_t>(n1);
+  L->clip_off = c.take<int64_t>(3 * n1);   // one block, one upload: [clip_off | frame_off | row_off]
+  L->frame_off = L->clip_off ? L->clip_off + n1 : nullptr;
+  L->row_off = L->clip_off ? L->clip_off + 2 * n1 : nullptr;
   L->zero_begin = c.used;
   L->peak_bits = c.take<uint32_t>(z.n_clips);
   L->dbmax_key = c.take<uint32_t>(z.n_clips);
@@ -140,6 +141,28 @@ struct Slot {  // one in-flight clip group of the host pipeline
   Arena pcm, out, work, ynorm;
   Arena fac_in, col_a, col_f, col_desc;   // fused extract + collect path
   cudaEvent_t done = nullptr;
+  // pageable callers: the group's PCM is gathered into `stage_in` (pinned) before its upload and its rows
+  // come back through `stage_out` (pinned); `pending_*` describe the copy-out owed to the caller's buffers
+  PinnedArena stage_in, stage_out, stage_aux;
+  struct CopyOut { void* dst; const void* src; size_t bytes; size_t dst_pitch, src_pitch, width; int64_t rows; };
+  CopyOut pending[3];
+  int n_pending = 0;
+};
+
+// Ring of pinned descriptor staging buffers.  A stream-ordered call writes its (tiny) descriptor arrays into
+// the next ring entry, enqueues the upload and records the entry's event; the entry is reused kDescRing calls
+// later, so the host only ever waits when that many calls' descriptor uploads are still outstanding.
+constexpr int kDescRing = 8;
+struct DescEntry {
+  PinnedArena mem;
+  cudaEvent_t copied = nullptr;
+  bool pending = false;
+};
+
+// Host-side descriptor arrays of a batch (kept in the context: no heap traffic per call after the first).
+struct HostDesc {
+  std::vector<int64_t> clip_off, frame_off, row_off;
+  int64_t total_samples = 0, total_frames = 0, total_rows = 0;
 };
 
 }  // namespace nsf
@@ -152,10 +175,10 @@ struct nsf_ctx {
   nsf::DctCoef dct_coef{};       // DCT matrix as a kernel parameter (default 128 -> 23 shape only)
   bool dct_coef_ok = false;
   nsf::Arena table_mem;
-  // descriptor staging (pinned), guarded by an event so back-to-back calls cannot race the copy
-  nsf::PinnedArena desc_host;
-  cudaEvent_t desc_copied = nullptr;
-  bool desc_pending = false;
+  nsf::DescEntry desc[nsf::kDescRing];
+  int desc_next = 0;
+  nsf::HostDesc hd_batch, hd_all;   // scratch of nsf_extract_batch / the host pipelines
+  float edge_zero_threshold = 1e-7f;   // fix_edge_frames_autocorr(zero_threshold=1e-7)
   nsf::Slot slot[nsf::kSlots];
   int64_t launches = 0;
   bool profiling = false;
@@ -259,6 +282,7 @@ nsf_status upload_tables(nsf_ctx* ctx) {
   char* base = static_cast<char*>(ctx->table_mem.ptr);
   DeviceTables& t = ctx->tables;
   t.F = p.F; t.H = p.H; t.pad = p.pad; t.bins = p.bins;
+  t.edge_thr = ctx->edge_zero_threshold;
   t.bins_ld = p.chain[0].np + (p.chains > 1 ? p.chain[1].np : 0);
   t.col_off[0] = col_off[0]; t.col_off[1] = col_off[1];
   t.n_mfcc = p.n_mfcc; t.n_mels = p.n_mels; t.n_lags = p.n_lags; t.chains = p.chains;
@@ -287,12 +311,24 @@ nsf_status upload_tables(nsf_ctx* ctx) {
   return bind_stft_tc_tables(p, tcblob, base + off_tc, &ctx->tc);
 }
 
-// Host-side descriptor build + validation shared by the device and host entry points.
-struct HostDesc {
-  std::vector<int64_t> clip_off, frame_off, row_off;
-  int64_t total_samples = 0, total_frames = 0, total_rows = 0;
-};
+// Next entry of the descriptor ring with room for `bytes`; waits only if the entry's previous upload (issued
+// kDescRing calls ago) has not run yet.
+nsf_status desc_acquire(nsf_ctx* ctx, size_t bytes, DescEntry** out) {
+  DescEntry& d = ctx->desc[ctx->desc_next];
+  ctx->desc_next = (ctx->desc_next + 1) % kDescRing;
+  if (d.pending) { NSF_CUDA(cudaEventSynchronize(d.copied)); d.pending = false; }
+  const nsf_status st = d.mem.reserve(bytes);
+  if (st != NSF_OK) return st;
+  *out = &d;
+  return NSF_OK;
+}
+nsf_status desc_commit(DescEntry* d, cudaStream_t s) {
+  NSF_CUDA(cudaEventRecord(d->copied, s));
+  d->pending = true;
+  return NSF_OK;
+}
 
+// Host-side descriptor build + validation shared by the device and host entry points.
 nsf_status build_desc(const Plan& p, const int64_t* clip_offsets, int32_t n_clips, uint32_t flags,
                       const int64_t* out_row_offsets, HostDesc* d) {
   if (!clip_offsets || n_clips <= 0) {
@@ -308,13 +344,15 @@ nsf_status build_desc(const Plan& p, const int64_t* clip_offsets, int32_t n_clip
   for (int i = 0; i < n_clips; ++i) {
     const int64_t len = clip_offsets[i + 1] - clip_offsets[i];
     if (len < 0) { set_error("clip_offsets must be non-decreasing"); return NSF_ERR_BAD_ARG; }
-    const int64_t T = nsf_hop_frames(len, p.F, p.H);
+    // NSF_AC_NO_PAD (pad_signal=False): frames are y[t H : t H + F], as many as fit
+    const bool no_pad = (flags & NSF_AC_NO_PAD) != 0;
+    const int64_t T = no_pad ? (len >= p.F ? nsf_guard_frames(len, p.F, p.H) : 0) : nsf_hop_frames(len, p.F, p.H);
     // librosa.feature.delta(width=9) raises below 9 frames; the edge fix and reflect padding need
     // 2 frames and F/2 + 1 samples.  (The 9-frame *guard* of extract_features.py:16 counts
     // un-padded frames and belongs to the caller: see nsf_guard_frames.)
     const bool any_delta = (!(flags & NSF_NO_DELTAS) && !(flags & NSF_NO_MFCC)) ||
                            ((flags & NSF_AC_DELTAS) && !(flags & NSF_NO_AUTOCORR));
-    const int64_t need = any_delta ? kMinGuardFrames : 2;
+    const int64_t need = any_delta ? kMinGuardFrames : (no_pad ? 1 : 2);
     if (T < need || len <= p.F / 2) {
       char buf[160];
       std::snprintf(buf, sizeof buf, "clip %d is too short: %lld hop-frames, required: %lld", i,
@@ -381,6 +419,32 @@ nsf_status nsf_host_alloc(void** out_ptr, int64_t bytes) {
 
 void nsf_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 
+nsf_status nsf_host_register(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) { set_error("nsf_host_register: bad argument"); return NSF_ERR_BAD_ARG; }
+  NSF_CUDA(cudaHostRegister(ptr, static_cast<size_t>(bytes), cudaHostRegisterPortable));
+  return NSF_OK;
+}
+
+nsf_status nsf_host_unregister(void* ptr) {
+  if (!ptr) { set_error("nsf_host_unregister: NULL"); return NSF_ERR_BAD_ARG; }
+  NSF_CUDA(cudaHostUnregister(ptr));
+  return NSF_OK;
+}
+
+nsf_status nsf_ctx_set_option(nsf_ctx* ctx, int32_t option, double value) {
+  if (!ctx) { set_error("nsf_ctx_set_option: NULL context"); return NSF_ERR_BAD_ARG; }
+  switch (option) {
+    case NSF_OPT_EDGE_ZERO_THRESHOLD:
+      if (!(value >= 0.0)) { set_error("zero_threshold must be >= 0"); return NSF_ERR_BAD_ARG; }
+      ctx->edge_zero_threshold = static_cast<float>(value);
+      ctx->tables.edge_thr = ctx->edge_zero_threshold;
+      return NSF_OK;
+    default:
+      set_error("nsf_ctx_set_option: unknown option");
+      return NSF_ERR_BAD_ARG;
+  }
+}
+
 nsf_status nsf_ctx_create(const nsf_plan* plan, int32_t device, nsf_ctx** out_ctx) {
   if (!plan || !out_ctx) { set_error("nsf_ctx_create: NULL argument"); return NSF_ERR_BAD_ARG; }
   *out_ctx = nullptr;
@@ -403,8 +467,14 @@ nsf_status nsf_ctx_create(const nsf_plan* plan, int32_t device, nsf_ctx** out_ct
   ctx->device = device;
   nsf_status st = upload_tables(ctx);
   if (st != NSF_OK) { nsf_ctx_destroy(ctx); return st; }
-  if (cudaEventCreateWithFlags(&ctx->desc_copied, cudaEventDisableTiming) != cudaSuccess) {
-    set_error("cudaEventCreate failed"); nsf_ctx_destroy(ctx); return NSF_ERR_CUDA;
+  for (auto& d : ctx->desc) {
+    if (cudaEventCreateWithFlags(&d.copied, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("cudaEventCreate failed"); nsf_ctx_destroy(ctx); return NSF_ERR_CUDA;
+    }
+  }
+  // opt-in shared-memory limits of every kernel, once per device: no launch path touches function attributes
+  if (!init_kernel_attributes() || !init_autocorr_mma_attributes() || !init_stft_tc_attributes()) {
+    set_error(cuda_msg("cudaFuncSetAttribute", cudaGetLastError())); nsf_ctx_destroy(ctx); return NSF_ERR_CUDA;
   }
   for (int i = 0; i <= kStages; ++i) {
     if (cudaEventCreate(&ctx->stage_ev[i]) != cudaSuccess) {
@@ -424,10 +494,13 @@ void nsf_ctx_destroy(nsf_ctx* ctx) {
     if (s.done) cudaEventDestroy(s.done);
     s.pcm.release(); s.out.release(); s.work.release(); s.ynorm.release();
     s.fac_in.release(); s.col_a.release(); s.col_f.release(); s.col_desc.release();
+    s.stage_in.release(); s.stage_out.release(); s.stage_aux.release();
   }
   for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
-  if (ctx->desc_copied) cudaEventDestroy(ctx->desc_copied);
-  ctx->desc_host.release();
+  for (auto& d : ctx->desc) {
+    if (d.copied) cudaEventDestroy(d.copied);
+    d.mem.release();
+  }
   ctx->table_mem.release();
   ctx->collect_in_a.release(); ctx->collect_in_f.release();
   ctx->collect_out_a.release(); ctx->collect_out_f.release(); ctx->collect_desc.release();
@@ -471,7 +544,8 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
   const Plan& p = ctx->plan->p;
   const int cols = nsf_feature_cols(ctx->plan, flags);
   if (out_ld < cols) { set_error("out_ld smaller than the feature width"); return NSF_ERR_BAD_ARG; }
-  HostDesc hd;
+  if (workspace_bytes <= 0) { set_error("workspace_bytes must be positive; size it with nsf_workspace_bytes()"); return NSF_ERR_WORKSPACE; }
+  HostDesc& hd = ctx->hd_batch;
   nsf_status st = build_desc(p, clip_offsets_host, n_clips, flags, out_row_offsets_host, &hd);
   if (st != NSF_OK) return st;
   NSF_CUDA(cudaSetDevice(ctx->device));
@@ -486,27 +560,25 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
   bool fits = false;
   // 256-byte align the caller's pointer
   char* wbase = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace_dev)));
-  const size_t wcap = static_cast<size_t>(workspace_bytes) - static_cast<size_t>(wbase - static_cast<char*>(workspace_dev));
+  const size_t wslack = static_cast<size_t>(wbase - static_cast<char*>(workspace_dev));
+  if (static_cast<size_t>(workspace_bytes) <= wslack) { set_error("workspace too small; size it with nsf_workspace_bytes()"); return NSF_ERR_WORKSPACE; }
+  const size_t wcap = static_cast<size_t>(workspace_bytes) - wslack;
   plan_layout(p, z, flags, need_y && !y_norm_dev, wbase, wcap, &L, &fits);
   if (!fits) { set_error("workspace too small; size it with nsf_workspace_bytes()"); return NSF_ERR_WORKSPACE; }
 
-  // descriptors: pinned staging -> device, stream ordered
+  // descriptors: next entry of the pinned ring -> device, one stream-ordered upload, no host wait
   const size_t n1 = static_cast<size_t>(n_clips) + 1;
-  if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
-  st = ctx->desc_host.reserve(3 * n1 * sizeof(int64_t));
-  if (st != NSF_OK) return st;
-  int64_t* hstage = static_cast<int64_t*>(ctx->desc_host.ptr);
+  DescEntry* de = nullptr;
+  if ((st = desc_acquire(ctx, 3 * n1 * sizeof(int64_t), &de)) != NSF_OK) return st;
+  int64_t* hstage = static_cast<int64_t*>(de->mem.ptr);
   const int64_t row_origin = hd.row_off[0];
   for (size_t i = 0; i < n1; ++i) {
     hstage[i] = hd.clip_off[i];
     hstage[n1 + i] = hd.frame_off[i];
     hstage[2 * n1 + i] = hd.row_off[i] - row_origin;
   }
-  NSF_CUDA(cudaMemcpyAsync(L.clip_off, hstage, n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  NSF_CUDA(cudaMemcpyAsync(L.frame_off, hstage + n1, n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  NSF_CUDA(cudaMemcpyAsync(L.row_off, hstage + 2 * n1, n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  NSF_CUDA(cudaEventRecord(ctx->desc_copied, s));
-  ctx->desc_pending = true;
+  NSF_CUDA(cudaMemcpyAsync(L.clip_off, hstage, 3 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  if ((st = desc_commit(de, s)) != NSF_OK) return st;
   NSF_CUDA(cudaMemsetAsync(wbase + L.zero_begin, 0, L.zero_bytes, s));
 
   BatchView b;
@@ -544,6 +616,12 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
   const bool do_mfcc = !(flags & NSF_NO_MFCC);
   const int mfcc_cols = do_mfcc ? p.n_mfcc * (deltas ? 3 : 1) : 0;
   if (!do_mfcc && (flags & NSF_NO_AUTOCORR)) { set_error("NSF_NO_MFCC | NSF_NO_AUTOCORR leaves nothing to compute"); return NSF_ERR_BAD_ARG; }
+  // pad_signal=False exists for the autocorrelation branch only (librosa's STFT always centre-pads)
+  DeviceTables t_ac = t;
+  if (flags & NSF_AC_NO_PAD) {
+    if (do_mfcc) { set_error("NSF_AC_NO_PAD needs NSF_NO_MFCC: only the autocorrelation branch has a pad_signal switch"); return NSF_ERR_UNSUPPORTED; }
+    t_ac.pad = 0;
+  }
 
   // stages 1-3: STFT power -> mel -> dB (+ per-clip max)
   bool fused_mel = false;
@@ -585,13 +663,13 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
     if (flags & NSF_AC_DELTAS) {
       BatchView bf = b;  // un-reduced: one row per hop-frame
       bf.row_off = L.frame_off; bf.total_rows = hd.total_frames;
-      if (flags & NSF_DEBUG_FMA_AUTOCORR) NSF_LAUNCH(launch_autocorr(s, t, bf, y, false, L.ac_raw, p.n_lags, 0));
-      else NSF_LAUNCH(launch_autocorr_mma(s, t, bf, y, false, L.ac_raw, p.n_lags, 0));
+      if (flags & NSF_DEBUG_FMA_AUTOCORR) NSF_LAUNCH(launch_autocorr(s, t_ac, bf, y, false, L.ac_raw, p.n_lags, 0));
+      else NSF_LAUNCH(launch_autocorr_mma(s, t_ac, bf, y, false, L.ac_raw, p.n_lags, 0));
       NSF_LAUNCH(launch_delta_reduce(s, b, L.ac_raw, p.n_lags, p.n_lags, nullptr, nullptr, false, true,
                                      reduce, stage_out, stage_ld, mfcc_cols));
     } else {
-      if (flags & NSF_DEBUG_FMA_AUTOCORR) NSF_LAUNCH(launch_autocorr(s, t, b, y, reduce, stage_out, stage_ld, mfcc_cols));
-      else NSF_LAUNCH(launch_autocorr_mma(s, t, b, y, reduce, stage_out, stage_ld, mfcc_cols));
+      if (flags & NSF_DEBUG_FMA_AUTOCORR) NSF_LAUNCH(launch_autocorr(s, t_ac, b, y, reduce, stage_out, stage_ld, mfcc_cols));
+      else NSF_LAUNCH(launch_autocorr_mma(s, t_ac, b, y, reduce, stage_out, stage_ld, mfcc_cols));
     }
   }
   // stage 7: optional smoothing
@@ -610,6 +688,54 @@ static nsf_status ensure_slot(Slot* sl) {
   return NSF_OK;
 }
 
+// Is `p` memory the copy engines can reach directly (cudaHostAlloc / cudaHostRegister / managed)?  Pageable
+// buffers are staged through the slot's pinned arenas so that uploads and downloads stay asynchronous.
+static bool dma_reachable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// memcpy split over a few threads once it is large enough to be bound by one core's copy bandwidth.
+static void host_copy(void* dst, const void* src, size_t bytes) {
+  constexpr size_t kChunk = size_t(8) << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t n = bytes / kChunk;
+  if (n > 8) n = 8;
+  if (hw && n > hw) n = hw;
+  if (n < 2) { std::memcpy(dst, src, bytes); return; }
+  const size_t part = (bytes / n + 63) & ~size_t(63);
+  std::vector<std::thread> th;
+  th.reserve(n - 1);
+  for (size_t i = 1; i < n; ++i) {
+    const size_t off = i * part;
+    if (off >= bytes) break;
+    const size_t len = std::min(part, bytes - off);
+    th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+  }
+  std::memcpy(dst, src, std::min(part, bytes));
+  for (auto& t : th) t.join();
+}
+
+// Copy-outs a slot owes to pageable caller buffers; run once the slot's stream has drained.
+static void flush_pending(Slot* sl) {
+  for (int i = 0; i < sl->n_pending; ++i) {
+    const Slot::CopyOut& c = sl->pending[i];
+    if (c.rows <= 1 || (c.dst_pitch == c.width && c.src_pitch == c.width)) {
+      host_copy(c.dst, c.src, c.rows <= 1 ? c.bytes : c.width * static_cast<size_t>(c.rows));
+    } else {
+      for (int64_t r = 0; r < c.rows; ++r)
+        std::memcpy(static_cast<char*>(c.dst) + r * c.dst_pitch, static_cast<const char*>(c.src) + r * c.src_pitch, c.width);
+    }
+  }
+  sl->n_pending = 0;
+}
+static nsf_status drain_slot(Slot* sl) {
+  NSF_CUDA(cudaStreamSynchronize(sl->stream));
+  flush_pending(sl);
+  return NSF_OK;
+}
+
 nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
                             const int64_t* clip_offsets, int32_t n_clips, uint32_t flags,
                             float* out_host, int64_t out_ld, float* y_norm_host) {
@@ -621,11 +747,16 @@ nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_form
   const int cols = nsf_feature_cols(ctx->plan, flags);
   if (out_ld < cols) { set_error("out_ld smaller than the feature width"); return NSF_ERR_BAD_ARG; }
   // validate everything up front so nothing is launched for a bad batch
-  HostDesc all;
+  HostDesc& all = ctx->hd_all;
   nsf_status st = build_desc(p, clip_offsets, n_clips, flags, nullptr, &all);
   if (st != NSF_OK) return st;
   NSF_CUDA(cudaSetDevice(ctx->device));
+  for (auto& sl : ctx->slot) sl.n_pending = 0;   // nothing is owed from an earlier call (errors drop their copy-outs)
   const size_t esz = pcm_format == NSF_PCM_I16 ? 2 : 4;
+  // pageable caller buffers go through the slot's pinned staging arenas: the host copies group g + 1 in (and
+  // group g - 2 out) while the copy engines and kernels work on the groups in between
+  const bool in_dma = dma_reachable(pcm_host), out_dma = dma_reachable(out_host);
+  const bool y_dma = y_norm_host ? dma_reachable(y_norm_host) : true;
   int first = 0, turn = 0;
   while (first < n_clips) {
     int last = first;
@@ -639,14 +770,20 @@ nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_form
     st = ensure_slot(sl);
     if (st != NSF_OK) return st;
     // the slot's previous group must have fully drained before its buffers are reused
-    NSF_CUDA(cudaStreamSynchronize(sl->stream));
+    if ((st = drain_slot(sl)) != NSF_OK) return st;
     const int64_t rows = all.row_off[last] - all.row_off[first];
     const int64_t wbytes = nsf_workspace_bytes(ctx->plan, samples, gn, flags);
+    const size_t out_bytes = static_cast<size_t>(rows) * cols * sizeof(float);
     if ((st = sl->pcm.reserve(samples * esz)) != NSF_OK) return st;
-    if ((st = sl->out.reserve(static_cast<size_t>(rows) * cols * sizeof(float))) != NSF_OK) return st;
+    if ((st = sl->out.reserve(out_bytes)) != NSF_OK) return st;
     if ((st = sl->work.reserve(wbytes)) != NSF_OK) return st;
     if (y_norm_host && (st = sl->ynorm.reserve(samples * sizeof(float))) != NSF_OK) return st;
     const char* src = static_cast<const char*>(pcm_host) + clip_offsets[first] * esz;
+    if (!in_dma) {
+      if ((st = sl->stage_in.reserve(samples * esz)) != NSF_OK) return st;
+      host_copy(sl->stage_in.ptr, src, samples * esz);
+      src = static_cast<const char*>(sl->stage_in.ptr);
+    }
     NSF_CUDA(cudaMemcpyAsync(sl->pcm.ptr, src, samples * esz, cudaMemcpyHostToDevice, sl->stream));
     st = nsf_extract_batch(ctx, sl->stream, sl->pcm.ptr, pcm_format, clip_offsets + first, gn, flags,
                            static_cast<float*>(sl->out.ptr), cols, nullptr,
@@ -654,22 +791,33 @@ nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_form
                            static_cast<int64_t>(sl->work.bytes));
     if (st != NSF_OK) return st;
     float* dst = out_host + all.row_off[first] * out_ld;
-    if (out_ld == cols) {
-      NSF_CUDA(cudaMemcpyAsync(dst, sl->out.ptr, static_cast<size_t>(rows) * cols * sizeof(float),
-                               cudaMemcpyDeviceToHost, sl->stream));
+    if (!out_dma) {
+      if ((st = sl->stage_out.reserve(out_bytes)) != NSF_OK) return st;
+      NSF_CUDA(cudaMemcpyAsync(sl->stage_out.ptr, sl->out.ptr, out_bytes, cudaMemcpyDeviceToHost, sl->stream));
+      sl->pending[sl->n_pending++] = Slot::CopyOut{dst, sl->stage_out.ptr, out_bytes, static_cast<size_t>(out_ld) * sizeof(float),
+                                                   static_cast<size_t>(cols) * sizeof(float),
+                                                   static_cast<size_t>(cols) * sizeof(float), rows};
+    } else if (out_ld == cols) {
+      NSF_CUDA(cudaMemcpyAsync(dst, sl->out.ptr, out_bytes, cudaMemcpyDeviceToHost, sl->stream));
     } else {
       NSF_CUDA(cudaMemcpy2DAsync(dst, out_ld * sizeof(float), sl->out.ptr, cols * sizeof(float),
                                  cols * sizeof(float), rows, cudaMemcpyDeviceToHost, sl->stream));
     }
     if (y_norm_host) {
-      NSF_CUDA(cudaMemcpyAsync(y_norm_host + (clip_offsets[first] - clip_offsets[0]), sl->ynorm.ptr,
-                               samples * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+      float* ydst = y_norm_host + (clip_offsets[first] - clip_offsets[0]);
+      if (!y_dma) {
+        if ((st = sl->stage_aux.reserve(samples * sizeof(float))) != NSF_OK) return st;
+        NSF_CUDA(cudaMemcpyAsync(sl->stage_aux.ptr, sl->ynorm.ptr, samples * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+        sl->pending[sl->n_pending++] = Slot::CopyOut{ydst, sl->stage_aux.ptr, samples * sizeof(float), 0, 0, 0, 1};
+      } else {
+        NSF_CUDA(cudaMemcpyAsync(ydst, sl->ynorm.ptr, samples * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+      }
     }
     first = last;
     ++turn;
   }
   for (auto& sl : ctx->slot)
-    if (sl.stream) NSF_CUDA(cudaStreamSynchronize(sl.stream));
+    if (sl.stream && (st = drain_slot(&sl)) != NSF_OK) return st;
   return NSF_OK;
 }
 
@@ -695,15 +843,14 @@ nsf_status nsf_normalize_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_fo
   if ((st = sl->pcm.reserve(samples * esz)) != NSF_OK) return st;
   if ((st = sl->ynorm.reserve(samples * sizeof(float))) != NSF_OK) return st;
   if ((st = sl->work.reserve(off_b + align_up(n_clips * sizeof(uint32_t)))) != NSF_OK) return st;
-  if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
-  if ((st = ctx->desc_host.reserve(n1 * sizeof(int64_t))) != NSF_OK) return st;
-  int64_t* h = static_cast<int64_t*>(ctx->desc_host.ptr);
+  DescEntry* de = nullptr;
+  if ((st = desc_acquire(ctx, n1 * sizeof(int64_t), &de)) != NSF_OK) return st;
+  int64_t* h = static_cast<int64_t*>(de->mem.ptr);
   for (size_t i = 0; i < n1; ++i) h[i] = clip_offsets[i] - clip_offsets[0];
   int64_t* d_off = static_cast<int64_t*>(sl->work.ptr);
   uint32_t* d_peak = reinterpret_cast<uint32_t*>(static_cast<char*>(sl->work.ptr) + off_b);
   NSF_CUDA(cudaMemcpyAsync(d_off, h, n1 * sizeof(int64_t), cudaMemcpyHostToDevice, sl->stream));
-  NSF_CUDA(cudaEventRecord(ctx->desc_copied, sl->stream));
-  ctx->desc_pending = true;
+  if ((st = desc_commit(de, sl->stream)) != NSF_OK) return st;
   NSF_CUDA(cudaMemsetAsync(d_peak, 0, n_clips * sizeof(uint32_t), sl->stream));
   const char* src = static_cast<const char*>(pcm_host) + clip_offsets[0] * esz;
   NSF_CUDA(cudaMemcpyAsync(sl->pcm.ptr, src, samples * esz, cudaMemcpyHostToDevice, sl->stream));
@@ -793,10 +940,10 @@ nsf_status nsf_collect_batch(nsf_ctx* ctx, void* cuda_stream, int32_t dtype, con
   NSF_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t n1 = static_cast<size_t>(n_clips) + 1;
-  if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
-  if ((st = ctx->desc_host.reserve(3 * n1 * sizeof(int64_t))) != NSF_OK) return st;
+  DescEntry* de = nullptr;
+  if ((st = desc_acquire(ctx, 3 * n1 * sizeof(int64_t), &de)) != NSF_OK) return st;
   if ((st = ctx->collect_desc.reserve(3 * n1 * sizeof(int64_t))) != NSF_OK) return st;
-  int64_t* h = static_cast<int64_t*>(ctx->desc_host.ptr);
+  int64_t* h = static_cast<int64_t*>(de->mem.ptr);
   const int64_t a0 = audio_offsets_host[0], f0 = facial_offsets_host[0];
   const int64_t o0 = out_offsets_host ? out_offsets_host[0] : 0;
   for (size_t i = 0; i < n1; ++i) {
@@ -806,8 +953,7 @@ nsf_status nsf_collect_batch(nsf_ctx* ctx, void* cuda_stream, int32_t dtype, con
   }
   int64_t* d = static_cast<int64_t*>(ctx->collect_desc.ptr);
   NSF_CUDA(cudaMemcpyAsync(d, h, 3 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  NSF_CUDA(cudaEventRecord(ctx->desc_copied, s));
-  ctx->desc_pending = true;
+  if ((st = desc_commit(de, s)) != NSF_OK) return st;
   CollectView v;
   v.a_off = d; v.f_off = d + n1; v.o_off = d + 2 * n1;
   v.n_clips = n_clips; v.total_out_rows = o_off[n_clips]; v.flags = collect_flags; v.blend_frames = blend_frames;
@@ -872,7 +1018,7 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
   if (pcm_format != NSF_PCM_F32 && pcm_format != NSF_PCM_I16) { set_error("unknown pcm_format"); return NSF_ERR_BAD_ARG; }
   const Plan& p = ctx->plan->p;
   const int cols = nsf_feature_cols(ctx->plan, flags);
-  HostDesc all;
+  HostDesc& all = ctx->hd_all;
   nsf_status st = build_desc(p, clip_offsets, n_clips, flags, nullptr, &all);
   if (st != NSF_OK) return st;
   // output packing over the whole batch (validates the facial offsets)
@@ -912,9 +1058,9 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
     // collect descriptors of this group (relative offsets) through the guarded pinned staging buffer.  Staged
     // BEFORE the extraction kernels are enqueued: the next wait on the staging buffer then ends as soon as this
     // group's uploads have run, so the host can start the next group's upload while these kernels execute
-    if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
-    if ((st = ctx->desc_host.reserve(3 * n1 * sizeof(int64_t))) != NSF_OK) return st;
-    int64_t* h = static_cast<int64_t*>(ctx->desc_host.ptr);
+    DescEntry* de = nullptr;
+    if ((st = desc_acquire(ctx, 3 * n1 * sizeof(int64_t), &de)) != NSF_OK) return st;
+    int64_t* h = static_cast<int64_t*>(de->mem.ptr);
     for (size_t i = 0; i < n1; ++i) {
       h[i] = all.row_off[first + i] - all.row_off[first];
       h[n1 + i] = f_off[first + i] - f_off[first];
@@ -922,8 +1068,7 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
     }
     int64_t* d = static_cast<int64_t*>(sl->col_desc.ptr);
     NSF_CUDA(cudaMemcpyAsync(d, h, 3 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, sl->stream));
-    NSF_CUDA(cudaEventRecord(ctx->desc_copied, sl->stream));
-    ctx->desc_pending = true;
+    if ((st = desc_commit(de, sl->stream)) != NSF_OK) return st;
     st = nsf_extract_batch(ctx, sl->stream, sl->pcm.ptr, pcm_format, clip_offsets + first, gn, flags,
                            static_cast<float*>(sl->out.ptr), cols, nullptr, nullptr, sl->work.ptr,
                            static_cast<int64_t>(sl->work.bytes));
@@ -1000,19 +1145,18 @@ nsf_status nsf_post_host(nsf_ctx* ctx, const float* in_host, int64_t T, int32_t 
   int64_t* d_desc = reinterpret_cast<int64_t*>(base + in_b + out_b);
   double* d_sum = reinterpret_cast<double*>(base + in_b + out_b + desc_b);
   double* d_sq = reinterpret_cast<double*>(base + in_b + out_b + desc_b + st_b);
-  if (ctx->desc_pending) { NSF_CUDA(cudaEventSynchronize(ctx->desc_copied)); ctx->desc_pending = false; }
-  if ((st = ctx->desc_host.reserve(6 * sizeof(int64_t))) != NSF_OK) return st;
-  int64_t* h = static_cast<int64_t*>(ctx->desc_host.ptr);
+  DescEntry* de = nullptr;
+  if ((st = desc_acquire(ctx, 6 * sizeof(int64_t), &de)) != NSF_OK) return st;
+  int64_t* h = static_cast<int64_t*>(de->mem.ptr);
   h[0] = 0; h[1] = 0;           // clip_off (unused by the post kernels)
   h[2] = 0; h[3] = T;           // frame_off
   h[4] = 0; h[5] = rows;        // row_off
   NSF_CUDA(cudaMemcpyAsync(d_desc, h, 6 * sizeof(int64_t), cudaMemcpyHostToDevice, sl->stream));
-  NSF_CUDA(cudaEventRecord(ctx->desc_copied, sl->stream));
-  ctx->desc_pending = true;
+  if ((st = desc_commit(de, sl->stream)) != NSF_OK) return st;
   NSF_CUDA(cudaMemcpyAsync(d_in, in_host, T * Cc * sizeof(float), cudaMemcpyHostToDevice, sl->stream));
   int launched = 0, n;
   if (pf & NSF_POST_EDGEFIX) {
-    if ((n = launch_edge_fix(sl->stream, d_in, T, Cc)) < 0) { set_error(cuda_msg("launch_edge_fix", cudaGetLastError())); return NSF_ERR_CUDA; }
+    if ((n = launch_edge_fix(sl->stream, d_in, T, Cc, ctx->edge_zero_threshold)) < 0) { set_error(cuda_msg("launch_edge_fix", cudaGetLastError())); return NSF_ERR_CUDA; }
     launched += n;
   }
   if (cmvn) {

@@ -309,12 +309,12 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   __syncwarp();
 }
 
-__device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane, int n_lags) {
+__device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane, int n_lags, float thr) {
   bool small = true;
 #pragma unroll
   for (int v = 0; v < kVals; ++v) {
     const int lag = lag_of(lane, v);
-    if (lag >= 1 && lag <= n_lags && !(fabsf(val[v]) < 1e-7f)) small = false;
+    if (lag >= 1 && lag <= n_lags && !(fabsf(val[v]) < thr)) small = false;
   }
   return __all_sync(0xffffffffu, small);
 }
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
         am_mma(copies, geo, lane, val);
         // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
         // rare, so the consumer refills the buffer it still owns itself
-        if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags)) {
+        if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
           am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
           am_mma(copies, geo, lane, val);
         }
@@ -467,8 +467,6 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
   if (grid < 1) grid = 1;
   auto go = [&](auto kernel) {
-    // per call: all instantiations share this lambda (same function-pointer type), so no static flag
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
     kernel<<<static_cast<int>(grid), pairs * 64, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   };
@@ -479,6 +477,19 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   if (iters <= 24) return go(k_autocorr_mma<24, false>);  // F <= 1534  (48 kHz: 800)
   if (iters <= 40) return go(k_autocorr_mma<40, false>);  // F <= 2558
   return go(k_autocorr_mma<66, false>);                   // F <= 4096  (plan limit)
+}
+
+// Opt-in shared-memory limit of every instantiation, once per device (called by nsf_ctx_create after
+// cudaSetDevice; the attribute is per device and a process may drive several).
+bool init_autocorr_mma_attributes() {
+  bool ok = true;
+  auto set = [&](auto kernel) {
+    ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess;
+  };
+  set(k_autocorr_mma<23, true>); set(k_autocorr_mma<5, true>); set(k_autocorr_mma<6, false>);
+  set(k_autocorr_mma<12, false>); set(k_autocorr_mma<24, false>); set(k_autocorr_mma<40, false>);
+  set(k_autocorr_mma<66, false>);
+  return ok;
 }
 
 }  // namespace nsf

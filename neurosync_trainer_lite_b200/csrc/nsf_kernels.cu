@@ -854,13 +854,13 @@ __device__ __forceinline__ void autocorr_frame(const DeviceTables& t, const floa
 }
 
 // true when every kept coefficient (lags 1..n_lags) is below the 1e-7 threshold
-__device__ __forceinline__ bool ac_all_small(const float (&acc)[kAcLagsPerLane], int lane, int n_lags) {
+__device__ __forceinline__ bool ac_all_small(const float (&acc)[kAcLagsPerLane], int lane, int n_lags, float thr) {
   const int q = lane & 15;
   bool small = true;
 #pragma unroll
   for (int j = 0; j < kAcLagsPerLane; ++j) {
     const int lag = q * kAcLagsPerLane + j;
-    if (lag >= 1 && lag <= n_lags && !(fabsf(acc[j]) < 1e-7f)) small = false;
+    if (lag >= 1 && lag <= n_lags && !(fabsf(acc[j]) < thr)) small = false;
   }
   return __all_sync(0xffffffffu, small);
 }
@@ -889,24 +889,24 @@ __global__ void __launch_bounds__(kAcWarps * 32, 4) k_autocorr(DeviceTables t, B
       if (pair) {
         autocorr_frame(t, y, base, len, ta + 1, xs, hann, geo, lane, vb);
         // fix_edge_frames_autocorr: first frame copies frame 1, last frame copies frame T-2
-        if (ta == 0 && ac_all_small(va, lane, t.n_lags)) {
+        if (ta == 0 && ac_all_small(va, lane, t.n_lags, t.edge_thr)) {
 #pragma unroll
           for (int j = 0; j < kAcLagsPerLane; ++j) va[j] = vb[j];
         }
-        if (ta + 1 == T - 1 && ac_all_small(vb, lane, t.n_lags)) {
+        if (ta + 1 == T - 1 && ac_all_small(vb, lane, t.n_lags, t.edge_thr)) {
 #pragma unroll
           for (int j = 0; j < kAcLagsPerLane; ++j) vb[j] = va[j];
         }
 #pragma unroll
         for (int j = 0; j < kAcLagsPerLane; ++j) va[j] = 0.5f * (va[j] + vb[j]);
-      } else if (ta == T - 1 && ac_all_small(va, lane, t.n_lags)) {
+      } else if (ta == T - 1 && ac_all_small(va, lane, t.n_lags, t.edge_thr)) {
         autocorr_frame(t, y, base, len, T - 2, xs, hann, geo, lane, va);  // odd T: last row passes through
       }
     } else {
       autocorr_frame(t, y, base, len, lr, xs, hann, geo, lane, va);
-      if (lr == 0 && ac_all_small(va, lane, t.n_lags)) {
+      if (lr == 0 && ac_all_small(va, lane, t.n_lags, t.edge_thr)) {
         autocorr_frame(t, y, base, len, 1, xs, hann, geo, lane, va);
-      } else if (lr == T - 1 && ac_all_small(va, lane, t.n_lags)) {
+      } else if (lr == T - 1 && ac_all_small(va, lane, t.n_lags, t.edge_thr)) {
         autocorr_frame(t, y, base, len, T - 2, xs, hann, geo, lane, va);
       }
     }
@@ -1213,13 +1213,13 @@ __global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ in,
 }
 
 // fix_edge_frames_autocorr on a frame-major [T][C] matrix, single block
-__global__ void __launch_bounds__(256) k_edge_fix(float* __restrict__ d, int64_t T, int C) {
+__global__ void __launch_bounds__(256) k_edge_fix(float* __restrict__ d, int64_t T, int C, float thr) {
   __shared__ int s_big[2];
   if (threadIdx.x < 2) s_big[threadIdx.x] = 0;
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    if (!(fabsf(d[c]) < 1e-7f)) s_big[0] = 1;
-    if (!(fabsf(d[(T - 1) * C + c]) < 1e-7f)) s_big[1] = 1;
+    if (!(fabsf(d[c]) < thr)) s_big[0] = 1;
+    if (!(fabsf(d[(T - 1) * C + c]) < thr)) s_big[1] = 1;
   }
   __syncthreads();
   const bool fix_first = s_big[0] == 0, fix_last = s_big[1] == 0;
@@ -1291,9 +1291,6 @@ int launch_mel_db(cudaStream_t s, const DeviceTables& t, const BatchView& b, con
   if (t.n_mels > kMelWarps * kMelPerWarp) return -1;
   const int chain_cols = t.np[0] > t.np[1] ? t.np[0] : t.np[1];
   const size_t smem = (static_cast<size_t>(chain_cols) * kMelPitch + kMelFrames * (t.n_mels + 1)) * sizeof(float);
-  // per launch: the attribute is per device, and a process may drive several devices
-  if (cudaFuncSetAttribute(k_mel_db, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-    return -1;
   if (smem > 200 * 1024) return -1;
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
@@ -1344,10 +1341,8 @@ int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, co
   const size_t smem = (static_cast<size_t>(t.n_mels) * kp + static_cast<size_t>(kDctWarps) * t.n_mels * kDctPitch) * sizeof(float);
   const int grid = grid_for((b.total_frames + 31) / 32, kDctWarps, kSmCount * 2);
   if (kp == 24) {
-    if (cudaFuncSetAttribute(k_dct_sum<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return -1;
     k_dct_sum<24><<<grid, kDctWarps * 32, smem, s>>>(t, b, db, dbmax_key, mfcc_raw, sum, sumsq);
   } else {
-    if (cudaFuncSetAttribute(k_dct_sum<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return -1;
     k_dct_sum<32><<<grid, kDctWarps * 32, smem, s>>>(t, b, db, dbmax_key, mfcc_raw, sum, sumsq);
   }
   NSF_CHECK_LAUNCH();
@@ -1367,9 +1362,6 @@ int launch_autocorr(cudaStream_t s, const DeviceTables& t, const BatchView& b, c
                     bool reduce, float* out, int64_t out_ld, int col0) {
   const AcGeom geo = ac_geom(t.F);
   const size_t smem = static_cast<size_t>(kAcWarps) * geo.row_floats * sizeof(float);
-  // per launch: the attribute is per device, and a process may drive several devices
-  if (cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-    return -1;
   if (smem > 200 * 1024) return -1;
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
@@ -1439,10 +1431,24 @@ int launch_col_stats(cudaStream_t s, const float* in, int64_t T, int C, double* 
   return 1;
 }
 
-int launch_edge_fix(cudaStream_t s, float* data, int64_t T, int C) {
-  k_edge_fix<<<1, 256, 0, s>>>(data, T, C);
+int launch_edge_fix(cudaStream_t s, float* data, int64_t T, int C, float zero_threshold) {
+  k_edge_fix<<<1, 256, 0, s>>>(data, T, C, zero_threshold);
   NSF_CHECK_LAUNCH();
   return 1;
+}
+
+// Opt-in shared-memory limits of the kernels in this file, once per device (nsf_ctx_create, after
+// cudaSetDevice): the attribute is per device and a process may drive several.
+bool init_kernel_attributes() {
+  bool ok = true;
+  auto set = [&](auto kernel, int bytes) {
+    ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+  };
+  set(k_mel_db, 200 * 1024);
+  set(k_dct_sum<24>, 100 * 1024);
+  set(k_dct_sum<32>, 100 * 1024);
+  set(k_autocorr, 200 * 1024);
+  return ok;
 }
 
 }  // namespace nsf

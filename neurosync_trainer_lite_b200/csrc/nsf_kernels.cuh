@@ -21,6 +21,7 @@ struct BatchView {
 // Constant tables of a plan, uploaded once per context.
 struct DeviceTables {
   int F, H, pad, bins, bins_ld, n_mfcc, n_mels, n_lags, chains;
+  float edge_thr;             // zero_threshold of fix_edge_frames_autocorr (1e-7 unless nsf_ctx_set_option changed it)
   int kp[2], np[2], nbins[2];
   int col_off[2];             // power rows are chain-major: column = col_off[chain] + m
   const int32_t* tap_idx[2];  // [part][tap][kp]
@@ -108,7 +109,13 @@ int launch_resample(cudaStream_t s, const void* pcm, int pcm_format, int64_t n_i
                     int n_pre_pad, int n_pre_remove, const double* taps_pm, int kmax, float* out, int64_t n_out);
 // generic per-channel statistics of one [T][C] matrix and the edge fix
 int launch_col_stats(cudaStream_t s, const float* in, int64_t T, int C, double* sum, double* sumsq);
-int launch_edge_fix(cudaStream_t s, float* data, int64_t T, int C);
+int launch_edge_fix(cudaStream_t s, float* data, int64_t T, int C, float zero_threshold);
+
+// One-time (per device) cudaFuncSetAttribute calls of each translation unit; nsf_ctx_create runs them so that no
+// launch path touches function attributes.
+bool init_kernel_attributes();        // nsf_kernels.cu
+bool init_autocorr_mma_attributes();  // nsf_autocorr_mma.cu
+bool init_stft_tc_attributes();       // nsf_stft_tc.cu
 
 }  // namespace nsf
 #endif  // NSF_KERNELS_CUH_

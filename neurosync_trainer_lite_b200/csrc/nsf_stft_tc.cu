@@ -1306,8 +1306,6 @@ int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
   if (grid > 148 * per_sm) grid = 148 * per_sm;
   if (grid < 1) grid = 1;
   auto go = [&](auto kernel) {
-    // per launch: the attribute is per device, and a process may drive several devices
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
     kernel<<<static_cast<int>(grid), kFoldWarps * 32, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp, buf_floats, wp_pairs);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   };
@@ -1318,7 +1316,6 @@ int launch_stft_tc_fold(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
     if (iters <= 6) return go(k_tc_fold_r<6>);       // 88.2 kHz: F = 1470, kp = 368; 44.1 kHz: F = 735 (odd), kp = 368
     return go(k_tc_fold_r<8>);
   }
-  if (cudaFuncSetAttribute(k_tc_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
   k_tc_fold<<<static_cast<int>(grid), kFoldWarps * 32, smem, s>>>(t, b, y, v.planes, v.rows, v.row_exp, buf_floats);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -1335,9 +1332,6 @@ int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTable
   // measured 3.31 vs 3.06 ms on the C5 batch, so pairs are used from four K stages on
   const int kblocks = (tc.kp + BK - 1) / BK;
   if (!one_cta && kblocks >= 4) {
-    if (cudaFuncSetAttribute(k_tc_stft_mel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(kPairSmem)) != cudaSuccess)
-      return -1;
     int64_t pairs = v.rows / (2 * BM);
     if (pairs > 74) pairs = 74;
     if (pairs < 1) pairs = 1;
@@ -1345,9 +1339,6 @@ int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTable
         map_a, tc.map_b_half, t, b, v.rows, tc.kp, tc.np_ld, v.row_exp, db, dbmax_key);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
-  if (cudaFuncSetAttribute(k_tc_stft_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)) !=
-      cudaSuccess)
-    return -1;
   int64_t grid = v.rows / BM;
   if (grid > 148) grid = 148;
   if (grid < 1) grid = 1;
@@ -1362,10 +1353,6 @@ int launch_stft_tc_gemm(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
   const OperandView v = view_operands(tc, b.total_frames, operands);
   CUtensorMap map_a;
   if (!encode_map(&map_a, v.planes, static_cast<uint64_t>(tc.chains) * 4 * v.rows, tc.kp, BM)) return -1;
-  // per launch: the attribute is per device, and a process may drive several devices
-  if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)) !=
-      cudaSuccess)
-    return -1;
   const int np_max = std::max(tc.np[0], tc.np[1]);
   const int n_tiles = (np_max + BN - 1) / BN;
   const int64_t grid = (v.rows / BM) * n_tiles * tc.chains;
@@ -1374,6 +1361,20 @@ int launch_stft_tc_gemm(cudaStream_t s, const StftTcTables& tc, const DeviceTabl
       map_a, tc.map_b, b.total_frames, v.rows, n_tiles, tc.chains, tc.kp, tc.np_ld, tc.np[0], tc.np[1],
       tc.col_off[1], t.bins_ld, v.row_exp, power);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// Opt-in shared-memory limits, once per device (nsf_ctx_create, after cudaSetDevice).
+bool init_stft_tc_attributes() {
+  bool ok = true;
+  auto set = [&](auto kernel, int bytes) {
+    ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+  };
+  set(k_tc_fold_r<2>, 220 * 1024); set(k_tc_fold_r<3>, 220 * 1024); set(k_tc_fold_r<4>, 220 * 1024);
+  set(k_tc_fold_r<6>, 220 * 1024); set(k_tc_fold_r<8>, 220 * 1024); set(k_tc_fold, 220 * 1024);
+  set(k_tc_stft_mel_pair, static_cast<int>(kPairSmem));
+  set(k_tc_stft_mel, static_cast<int>(kFusedSmem));
+  set(k_tc_gemm, static_cast<int>(kSmemBytes));
+  return ok;
 }
 
 }  // namespace nsf

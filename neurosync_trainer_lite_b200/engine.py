@@ -142,7 +142,11 @@ class Engine:
     # ---- geometry ------------------------------------------------------------------------
     def row_offsets(self, offsets, flags=0):
         lens = np.diff(np.asarray(offsets, dtype=np.int64))
-        if flags & nv.NO_REDUCE:
+        if flags & nv.AC_NO_PAD:          # pad_signal=False: as many whole frames as fit
+            rows = [max(0, self.plan.guard_frames(n)) if n >= self.plan.F else 0 for n in lens]
+            if not flags & nv.NO_REDUCE:
+                rows = [(t + 1) // 2 for t in rows]
+        elif flags & nv.NO_REDUCE:
             rows = [self.plan.hop_frames(n) for n in lens]
         else:
             rows = [self.plan.feature_rows(n) for n in lens]
@@ -367,6 +371,10 @@ class Engine:
     # ---- instrumentation ---------------------------------------------------------------------
     def launch_count(self):
         return nv.lib.nsf_launch_count(self.handle)
+
+    def set_edge_zero_threshold(self, value):
+        """``zero_threshold`` of ``fix_edge_frames_autocorr`` (extract_features_utils.py:105) for this context."""
+        nv.check(nv.lib.nsf_ctx_set_option(self.handle, nv.OPT_EDGE_ZERO_THRESHOLD, float(value)))
 
     def set_profiling(self, on):
         nv.lib.nsf_set_profiling(self.handle, 1 if on else 0)

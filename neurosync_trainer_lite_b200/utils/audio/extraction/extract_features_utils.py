@@ -82,22 +82,53 @@ def smooth_features(features):
 
 def extract_overlapping_autocorr(y, sr, frame_length, hop_length, num_autocorr_coeff=187,
                                  pad_signal=True, padding_mode="reflect", trim_padded=False):
-    """reference :54-102 -> ``[num_autocorr_coeff, T]`` float64 (lags 1..n, edge frames fixed)."""
-    if not pad_signal or padding_mode != "reflect" or trim_padded:
-        raise NotImplementedError(
-            "the CUDA path implements the reference defaults only "
-            "(pad_signal=True, padding_mode='reflect', trim_padded=False)")
-    rows = _extract(y, sr, frame_length, hop_length, nv.NO_MFCC | nv.NO_REDUCE,
-                    n_lags=num_autocorr_coeff)
+    """reference :54-102 -> ``[num_autocorr_coeff, T]`` float64 (lags 1..n, edge frames fixed).
+
+    The defaults run as one fused device pass (reflect indexing inside the kernel).  The other knob
+    settings keep the arithmetic on the device and do the *index* work on the host exactly where the
+    reference does it: ``np.pad(y, F // 2, mode=padding_mode)`` before the call (:57-59), the kernel
+    then frames the given signal as is (``NSF_AC_NO_PAD``), and ``trim_padded`` selects the frame
+    columns of :67-74 before the edge fix (:100)."""
+    y = _signal(y)
+    base = nv.NO_MFCC | nv.NO_REDUCE
+    if pad_signal and padding_mode == "reflect" and not trim_padded:
+        rows = _extract(y, sr, frame_length, hop_length, base, n_lags=num_autocorr_coeff)
+        return np.ascontiguousarray(rows.T, dtype=np.float64)
+    pad = frame_length // 2
+    if y.dtype == np.int16:
+        y = y.astype(np.float32) / np.float32(32768)
+    y_padded = np.pad(y, pad_width=pad, mode=padding_mode) if pad_signal else y          # :56-61
+    eng = _engine_for(sr, frame_length, hop_length, n_lags=num_autocorr_coeff)
+    if pad_signal and trim_padded:
+        # :67-74 drops frames that touch the padding BEFORE fix_edge_frames_autocorr sees them, so the fix
+        # must run on the kept columns only: extract with the in-kernel fix disabled (threshold 0 can never
+        # be undercut), select, then apply the fix as its own call
+        eng.set_edge_zero_threshold(0.0)
+        try:
+            rows = eng.extract_host(np.ascontiguousarray(y_padded, dtype=np.float32), [0, len(y_padded)],
+                                    base | nv.AC_NO_PAD)
+        finally:
+            eng.set_edge_zero_threshold(1e-7)
+        start = np.arange(rows.shape[0]) * hop_length
+        valid = np.where((start >= pad) & (start + frame_length <= len(y) + pad))[0]
+        feats = np.ascontiguousarray(rows[valid].T, dtype=np.float64)
+        return fix_edge_frames_autocorr(feats) if feats.shape[1] >= 2 else feats
+    rows = eng.extract_host(np.ascontiguousarray(y_padded, dtype=np.float32), [0, len(y_padded)],
+                            base | nv.AC_NO_PAD)
     return np.ascontiguousarray(rows.T, dtype=np.float64)
 
 
 def fix_edge_frames_autocorr(autocorr_features, zero_threshold=1e-7):
     """reference :105-113 -- a near-silent first/last frame copies its neighbour."""
-    if zero_threshold != 1e-7:
-        raise NotImplementedError("the CUDA path implements zero_threshold=1e-7 only")
     x = np.asarray(autocorr_features)
-    out = _generic_engine().post(np.ascontiguousarray(x.T, dtype=np.float32), nv.POST_EDGEFIX)
+    eng = _generic_engine()
+    if zero_threshold != 1e-7:
+        eng.set_edge_zero_threshold(zero_threshold)
+    try:
+        out = eng.post(np.ascontiguousarray(x.T, dtype=np.float32), nv.POST_EDGEFIX)
+    finally:
+        if zero_threshold != 1e-7:
+            eng.set_edge_zero_threshold(1e-7)
     return out.T.astype(x.dtype if x.dtype in (np.float32, np.float64) else np.float32, copy=False)
 
 

@@ -112,11 +112,17 @@ def fix_edge_frames(ac, zero_threshold=1e-7):
     return ac
 
 
-def autocorr_block(y, sr, frame_length, hop_length, num_lags=187):
-    """extract_features_utils.py:54-102 (defaults: reflect pad, no trimming) -> (187, T) float64."""
+def autocorr_block(y, sr, frame_length, hop_length, num_lags=187, pad_signal=True,
+                   padding_mode="reflect", trim_padded=False):
+    """extract_features_utils.py:54-102 -> (187, T) float64.  Defaults = the reference's only call
+    (:119-121: reflect pad, no trimming); the three knobs follow :56-61 and :67-74."""
     lr = _librosa()
-    padded = np.pad(y, pad_width=frame_length // 2, mode="reflect")            # :57-59
+    pad = frame_length // 2
+    padded = np.pad(y, pad_width=pad, mode=padding_mode) if pad_signal else y  # :56-61
     cols = lr.util.frame(padded, frame_length=frame_length, hop_length=hop_length)  # :64
+    if pad_signal and trim_padded:                                            # :67-74
+        start = np.arange(cols.shape[1]) * hop_length
+        cols = cols[:, np.where((start >= pad) & (start + frame_length <= len(y) + pad))[0]]
     cols = cols - np.mean(cols, axis=0, keepdims=True)                        # :76
     cols = cols * np.hanning(frame_length)[:, np.newaxis]                      # :79-80 (-> float64)
     zero_lag = frame_length - 1

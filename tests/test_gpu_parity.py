@@ -2,12 +2,14 @@
 vectors.  Tolerances (float32 device arithmetic vs the reference's float64/float32 mix):
 
 * frame / row counts, alignment, zero patterns: bit-exact;
-* MFCC, delta, delta-delta columns (0..68, CMVN'd, range about +-5):   max-abs <= 1e-3
+* MFCC columns (0..22, CMVN'd, range about +-5):                       max-abs <= 1e-4
+* delta, delta-delta columns (23..68, range about +-0.7):              max-abs <= 2e-5
 * autocorrelation columns (69..255, range [-1, 1]):                    max-abs <= 2e-5
 * collect_features augmentation in float64: bit-exact (same IEEE operation order as NumPy).
 
-The measured errors are far smaller (see profiles/parity_r01.md); the bounds leave room for libm /
-accumulation-order differences between hosts.
+Measured (profiles/parity_r01.md, profiles/parity_r02.md): 2.9e-5 / 3.9e-6 / 3.4e-6, so the bounds sit
+3-6x above the measurement - tight enough that a 2-product operand split (2e-4 on the MFCC block, 3e-5 on
+the autocorrelation block) fails them.
 """
 import io
 
@@ -18,7 +20,8 @@ from neurosync_trainer_lite_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-TOL_MFCC = 1e-3
+TOL_MFCC = 1e-4
+TOL_DELTA = 2e-5
 TOL_AC = 2e-5
 SHORT = ["voiced_2s_16k", "gated_1s5_88k", "noise_0s7_88k", "voiced_1s_44k1_oddF",
          "voiced_0s6_22k05_oddF"]
@@ -65,6 +68,9 @@ def check_rows(got, want, n_mfcc_cols=69, tol_mfcc=TOL_MFCC, tol_ac=TOL_AC):
     if n_mfcc_cols:
         err = np.abs(got[:, :n_mfcc_cols] - want[:, :n_mfcc_cols]).max()
         assert err <= tol_mfcc, f"MFCC block max-abs error {err:.3e} > {tol_mfcc}"
+    if n_mfcc_cols == 69:     # the default layout: delta / delta-delta columns have their own, tighter bound
+        err = np.abs(got[:, 23:69] - want[:, 23:69]).max()
+        assert err <= TOL_DELTA, f"delta block max-abs error {err:.3e} > {TOL_DELTA}"
     if got.shape[1] > n_mfcc_cols:
         err = np.abs(got[:, n_mfcc_cols:] - want[:, n_mfcc_cols:]).max()
         assert err <= tol_ac, f"autocorr block max-abs error {err:.3e} > {tol_ac}"

@@ -1,0 +1,176 @@
+"""GPU parity, round-2 additions: the non-default autocorrelation knobs, every clip of a C2-scale batch
+against the oracle, pageable vs pinned host buffers, back-to-back stream-ordered calls.
+
+Tolerances as in test_gpu_parity.py (MFCC 1e-4, delta 2e-5, autocorrelation 2e-5; bit-exact where stated)."""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+from neurosync_trainer_lite_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_MFCC, TOL_DELTA, TOL_AC = 1e-4, 2e-5, 2e-5
+
+
+@pytest.fixture(scope="module")
+def nv():
+    import __graft_entry__ as g
+    g.build_library()
+    from neurosync_trainer_lite_b200 import _native
+    if _native.lib.nsf_device_count() < 1:
+        pytest.fail("GPU tests need an sm_100 device (the library has no CPU path)")
+    return _native
+
+
+@pytest.fixture(scope="module")
+def engine(nv):
+    from neurosync_trainer_lite_b200 import engine
+    return engine
+
+
+@pytest.fixture(scope="module")
+def efu(nv):
+    from neurosync_trainer_lite_b200.utils.audio.extraction import extract_features_utils
+    return extract_features_utils
+
+
+# ---- extract_overlapping_autocorr(pad_signal, padding_mode, trim_padded), fix_edge(zero_threshold) -------
+KNOBS = {
+    "nopad": dict(pad_signal=False),
+    "constant": dict(padding_mode="constant"),
+    "edge": dict(padding_mode="edge"),
+    "symmetric": dict(padding_mode="symmetric"),
+    "trim": dict(trim_padded=True),
+    "edge_trim": dict(padding_mode="edge", trim_padded=True),
+}
+
+
+@pytest.mark.parametrize("clip", ["a", "b"])
+@pytest.mark.parametrize("knob", sorted(KNOBS))
+def test_autocorr_knobs_match_reference_golden(clip, knob, golden, efu, oracle):
+    g = golden("autocorr_knobs")
+    y, sr = g[f"{clip}_y"], int(g[f"{clip}_sr"])
+    F, H = oracle.frame_params(sr)
+    got = efu.extract_overlapping_autocorr(y, sr, F, H, **KNOBS[knob])
+    want = g[f"{clip}_{knob}"]
+    assert got.shape == want.shape and got.dtype == np.float64     # frame counts bit-exact
+    assert np.abs(got - want).max() <= TOL_AC
+
+
+def test_autocorr_constant_padding_triggers_the_edge_fix(golden, efu):
+    g = golden("autocorr_knobs")
+    got = efu.extract_overlapping_autocorr(g["c_y"], 88200, 1470, 735, padding_mode="constant")
+    assert got.shape == g["c_constant"].shape
+    assert np.array_equal(got[:, 0], got[:, 1])                    # frame 0 was all-zero and took frame 1
+    assert np.abs(got - g["c_constant"]).max() <= TOL_AC
+
+
+def test_fix_edge_zero_threshold(golden, efu):
+    g = golden("autocorr_knobs")
+    got = efu.fix_edge_frames_autocorr(g["thr_in"].copy(), zero_threshold=0.5)
+    assert np.allclose(got, g["thr_out"], rtol=0, atol=1e-7)       # float32 round trip of float64 values
+    assert np.array_equal(got[:, 0], got[:, 1])
+    # and the default threshold leaves this matrix alone
+    same = efu.fix_edge_frames_autocorr(g["thr_in"].copy())
+    assert np.allclose(same, g["thr_in"], rtol=0, atol=1e-7)
+
+
+def test_no_pad_flag_needs_autocorr_only(engine, nv):
+    eng = engine.get_engine(88200, 1470, 735)
+    y = synth.synth_clip(0.3, 88200, seed=1)
+    with pytest.raises(nv.NsfError) as e:
+        eng.extract_host(y, [0, len(y)], nv.AC_NO_PAD)
+    assert e.value.status == nv.ERR_UNSUPPORTED
+
+
+# ---- every clip of a C2-scale batch against the oracle -----------------------------------------------------
+def _oracle_clip(args):
+    kind, seed, seconds = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import feature_oracle as fo
+    y = synth.synth_clip(seconds, 88200, seed=seed, kind=kind)
+    return fo.extract_and_combine_features(y, 88200, 1470, 735)
+
+
+def test_every_clip_of_a_c2_scale_batch_matches_the_oracle(engine):
+    """BASELINE configs[1] at full size: 60 clips x 30 s @ 88.2 kHz in ONE batch; EVERY clip is compared with
+    the CPU oracle (all three signal kinds; the oracle runs on a process pool, ~1.5 core-seconds per clip)."""
+    kinds = ("voiced", "noise", "gated")
+    jobs = [(kinds[i % 3], 200 + i, 30.0) for i in range(60)]
+    clips = [synth.synth_clip(s, 88200, seed=seed, kind=k) for k, seed, s in jobs]
+    eng = engine.get_engine(88200, 1470, 735)
+    packed, off = engine.pack_clips(clips)
+    rows = eng.extract_host(packed, off)
+    roff = eng.row_offsets(off)
+    assert rows.shape == (60 * 1801, 256)
+    env = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    os.environ.update(OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    try:
+        with mp.get_context("spawn").Pool(min(os.cpu_count() or 1, 32)) as pool:
+            want = pool.map(_oracle_clip, jobs, chunksize=1)
+    finally:
+        for k, v in env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    worst = np.zeros(3)
+    for i, w in enumerate(want):
+        got = rows[roff[i]:roff[i + 1]]
+        assert got.shape == w.shape == (1801, 256)
+        d = np.abs(got - w)
+        worst = np.maximum(worst, [d[:, :23].max(), d[:, 23:69].max(), d[:, 69:].max()])
+    assert worst[0] <= TOL_MFCC and worst[1] <= TOL_DELTA and worst[2] <= TOL_AC, worst
+
+
+# ---- host-buffer pipeline: pageable (staged) == pinned (direct DMA), bit for bit ------------------------------
+def test_pageable_and_pinned_host_buffers_give_identical_rows(engine, nv):
+    eng = engine.get_engine(88200, 1470, 735)
+    clips = [synth.synth_clip(s, 88200, seed=40 + i, kind=k)
+             for i, (s, k) in enumerate([(3.0, "voiced"), (95.0, "noise"), (0.4, "gated"), (70.0, "voiced"),
+                                         (2.0, "noise")])]              # 170 s: several pipeline groups
+    packed, off = engine.pack_clips(clips)
+    rows = int(eng.row_offsets(off)[-1])
+    pin_in, pin_out = engine.PinnedBuffer(packed.nbytes), engine.PinnedBuffer(rows * 256 * 4)
+    h_in = pin_in.view(np.float32, packed.shape)
+    h_in[:] = packed
+    h_out = pin_out.view(np.float32, (rows, 256))
+    eng.extract_host(h_in, off, 0, out=h_out)
+    paged, y_paged = eng.extract_host(packed, off, nv.PEAK_NORMALIZE, want_y=True)
+    pinned_norm = eng.extract_host(h_in, off, nv.PEAK_NORMALIZE)
+    assert np.array_equal(paged, pinned_norm)
+    assert np.array_equal(eng.extract_host(packed, off, 0), h_out)
+    assert np.array_equal(y_paged, eng.normalize_host(packed, off))
+    # int16 PCM, pageable
+    p16 = synth.to_int16_pcm(packed)
+    a = eng.extract_host(p16, off, nv.PEAK_NORMALIZE)
+    pin16 = engine.PinnedBuffer(p16.nbytes)
+    h16 = pin16.view(np.int16, p16.shape)
+    h16[:] = p16
+    assert np.array_equal(a, eng.extract_host(h16, off, nv.PEAK_NORMALIZE))
+
+
+def test_back_to_back_device_calls_do_not_share_descriptor_staging(engine, oracle):
+    """Twenty stream-ordered nsf_extract_batch calls with DIFFERENT batch geometries are queued without any
+    host synchronisation in between (the descriptor ring has 8 entries); every result must be its own."""
+    import torch
+    eng = engine.get_engine(88200, 1470, 735)
+    dev = torch.device("cuda", eng.device)
+    lens = [int(0.25 * 88200) + 777 * i for i in range(20)]
+    ys = [synth.synth_clip(n / 88200.0, 88200, seed=60 + i, kind="voiced")[:n] for i, n in enumerate(lens)]
+    pcm = [torch.from_numpy(y).to(dev) for y in ys]
+    outs = []
+    torch.cuda.synchronize(dev)
+    for i, p in enumerate(pcm):
+        out, ws = eng.extract_device(p, [0, len(ys[i])])
+        outs.append((out, ws))
+    torch.cuda.synchronize(dev)
+    for i in (0, 7, 8, 9, 19):
+        want = oracle.extract_and_combine_features(ys[i], 88200, 1470, 735)
+        got = outs[i][0].cpu().numpy()
+        assert got.shape == want.shape
+        d = np.abs(got - want)
+        assert d[:, :23].max() <= TOL_MFCC and d[:, 23:69].max() <= TOL_DELTA and d[:, 69:].max() <= TOL_AC

@@ -145,3 +145,19 @@ def test_windowing_kats(golden, oracle):
     np.testing.assert_array_equal(ex[-1][0], k["window_n300_last_a"])
     np.testing.assert_array_equal(ex[-1][0], ex[-2][0])  # the duplicated last window
     assert len(oracle.window_examples(ra[:256], rf[:256])) == int(k["window_n256_count"]) == 129
+
+
+@pytest.mark.parametrize("knob,kw", [("nopad", dict(pad_signal=False)), ("constant", dict(padding_mode="constant")),
+                                     ("edge", dict(padding_mode="edge")), ("symmetric", dict(padding_mode="symmetric")),
+                                     ("trim", dict(trim_padded=True)),
+                                     ("edge_trim", dict(padding_mode="edge", trim_padded=True))])
+def test_autocorr_knobs_restatement_is_bit_identical_to_the_reference_vectors(knob, kw, golden, oracle):
+    """tests/golden/autocorr_knobs.npz comes from the reference's own extract_overlapping_autocorr
+    (oracle/make_golden_knobs.py); the restatement must reproduce every knob setting bit for bit."""
+    g = golden("autocorr_knobs")
+    for clip in ("a", "b"):
+        y, sr = g[f"{clip}_y"], int(g[f"{clip}_sr"])
+        F, H = oracle.frame_params(sr)
+        got = oracle.autocorr_block(y, sr, F, H, **kw)
+        assert got.dtype == np.float64 and np.array_equal(got, g[f"{clip}_{knob}"])
+    assert np.array_equal(oracle.fix_edge_frames(g["thr_in"].copy(), zero_threshold=0.5), g["thr_out"])
