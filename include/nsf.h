@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NSF_ABI_VERSION 1
+#define NSF_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NSF_API __attribute__((visibility("default")))
@@ -208,12 +208,15 @@ NSF_API nsf_status nsf_collect_host(nsf_ctx* ctx, int32_t dtype, const void* aud
  * up, only augmented rows come back.  float32 throughout (the training format, dataset/dataset.py:75); the
  * float64 bit-exact arithmetic of the reference remains available through nsf_collect_host.  Clip i owns
  * samples [clip_offsets[i], clip_offsets[i+1]) of pcm and rows [facial_offsets[i], facial_offsets[i+1]) of
- * facial; outputs are packed at the prefix sum of nsf_collect_rows(nsf_feature_rows(..), facial rows, ..). */
+ * facial; outputs are packed at the prefix sum of nsf_collect_rows(nsf_feature_rows(..), facial rows, ..).
+ * features_host (optional, [sum R_i x cols] float32) also receives the un-augmented feature rows - what
+ * collect_features writes to its audio_features.csv cache (data_processing.py:115-120). */
 NSF_API nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format,
                                             const int64_t* clip_offsets_host, int32_t n_clips, uint32_t flags,
                                             const float* facial_host, int32_t facial_cols,
                                             const int64_t* facial_offsets_host, uint32_t collect_flags,
-                                            int32_t blend_frames, float* out_audio_host, float* out_facial_host);
+                                            int32_t blend_frames, float* out_audio_host, float* out_facial_host,
+                                            float* features_host /* optional */);
 
 /* ---- stand-alone array helpers of the reference API, on HOST arrays --------------------------
  * Row-wise helpers of dataset/data_processing.py (float32 or float64, the reference's exact

@@ -84,7 +84,8 @@ _SIGS = {
                                  _vp, _vp, _i64p]),
     "nsf_collect_host": (_i32, [_vp, _i32, _vp, _i32, _i64p, _vp, _i32, _i64p, _i32, _u32, _i32, _vp,
                                 _vp]),
-    "nsf_extract_collect_host": (_i32, [_vp, _vp, _i32, _i64p, _i32, _u32, _vp, _i32, _i64p, _u32, _i32, _vp, _vp]),
+    "nsf_extract_collect_host": (_i32, [_vp, _vp, _i32, _i64p, _i32, _u32, _vp, _i32, _i64p, _u32, _i32, _vp, _vp,
+                                        _vp]),
     "nsf_rows_host": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "nsf_post_host": (_i32, [_vp, _vp, _i64, _i32, _u32, _vp]),
     "nsf_resample_len": (_i64, [_i64, _i32, _i32]),

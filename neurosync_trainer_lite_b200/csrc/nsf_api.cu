@@ -1010,7 +1010,7 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
                                     const int64_t* clip_offsets, int32_t n_clips, uint32_t flags,
                                     const float* facial_host, int32_t facial_cols, const int64_t* f_off,
                                     uint32_t collect_flags, int32_t blend_frames, float* out_audio_host,
-                                    float* out_facial_host) {
+                                    float* out_facial_host, float* features_host) {
   if (!ctx || !pcm_host || !clip_offsets || !facial_host || !f_off || !out_audio_host || !out_facial_host ||
       n_clips <= 0 || facial_cols <= 0) {
     set_error("nsf_extract_collect_host: NULL argument"); return NSF_ERR_BAD_ARG;
@@ -1080,6 +1080,9 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
                                  sl->col_f.ptr);
     if (n < 0) { set_error(cuda_msg("launch_collect", cudaGetLastError())); return NSF_ERR_CUDA; }
     ctx->launches += n;
+    if (features_host)   // the un-augmented rows as well (what collect_features caches as audio_features.csv)
+      NSF_CUDA(cudaMemcpyAsync(features_host + all.row_off[first] * cols, sl->out.ptr,
+                               static_cast<size_t>(rows) * cols * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
     NSF_CUDA(cudaMemcpyAsync(out_audio_host + o_all[first] * cols, sl->col_a.ptr,
                              static_cast<size_t>(orows) * cols * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
     NSF_CUDA(cudaMemcpyAsync(out_facial_host + o_all[first] * facial_cols, sl->col_f.ptr,

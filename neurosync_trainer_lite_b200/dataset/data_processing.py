@@ -7,8 +7,12 @@ augmentation - centre-trim, fast ``[::2]``, slow ``interpolate_slower`` (+ ``smo
 ``stack_with_blend`` - as one ``nsf_collect_host`` call in float64, bit-identical to the NumPy
 arithmetic of the reference (same operation order, IEEE add/mul, no FMA contraction).
 
-``load_data_batched`` is the B200-first builder: all clips of a dataset in one extraction batch and
-one collect batch, optionally sharded by clip over ranks (``shard.py``).
+``load_data`` keeps the reference signature but builds the whole dataset in ONE pipelined device pass
+(``load_data_batched``): the folders are scanned first, every take without a feature cache is read straight
+into a page-locked int16 arena, ``nsf_extract_collect_host`` turns PCM + facial rows into augmented rows
+without the feature rows ever leaving the GPU, and the examples are float32 views of the page-locked result
+(``dataset/dataset.py:75`` casts to float32 anyway).  ``process_folder`` / ``collect_features`` remain the
+per-take float64 route, bit-identical to the reference's NumPy arithmetic.
 """
 import os
 
@@ -36,7 +40,16 @@ def _rows64(a):
 
 
 def load_data(root_dir, sr, processed_folders):
-    """reference :10-26 -- ``os.listdir`` order, skips (and records) processed folders."""
+    """reference :10-26 -- examples in ``os.listdir`` order, skips (and records) processed folders.
+
+    Same folder scan, cache files, ``collect_features`` defaults and ``facial[:, :61] *= 100`` as the
+    reference's loop over ``process_folder``, executed as one batched pass (see ``load_data_batched``);
+    examples are float32.  ``load_data_per_folder`` is the literal folder-by-folder loop (float64)."""
+    return load_data_batched(root_dir, sr, processed_folders)[0]
+
+
+def load_data_per_folder(root_dir, sr, processed_folders):
+    """The reference's loop verbatim: one ``process_folder`` (float64, bit-exact arithmetic) per folder."""
     examples = []
     for folder in os.listdir(root_dir):
         folder_path = os.path.join(root_dir, folder)
@@ -199,24 +212,89 @@ def collect_batch(audio_rows, facial_rows, include_fast=True, include_slow=False
                             blend_frames)
 
 
+def _pcm16_payload(path, sr):
+    """(byte offset, sample count) of the data chunk when ``path`` is a mono PCM16 RIFF/WAVE file at ``sr`` -
+    the format ffmpeg writes for the takes (utils/video/mov_extraction.py:50-57) - else None."""
+    import struct
+    try:
+        with open(path, "rb") as fh:
+            head = fh.read(12)
+            if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+                return None
+            fmt, pos = None, 12
+            while True:
+                hdr = fh.read(8)
+                if len(hdr) < 8:
+                    return None
+                tag, size = hdr[:4], struct.unpack("<I", hdr[4:])[0]
+                if tag == b"fmt ":
+                    fmt = struct.unpack("<HHIIHH", fh.read(16))
+                    fh.seek(pos + 8 + size + (size & 1))
+                elif tag == b"data":
+                    if fmt is None or fmt[0] != 1 or fmt[1] != 1 or fmt[5] != 16 or fmt[2] != sr:
+                        return None
+                    avail = os.path.getsize(path) - (pos + 8)
+                    return pos + 8, min(size, max(avail, 0)) // 2
+                else:
+                    fh.seek(pos + 8 + size + (size & 1))
+                pos += 8 + size + (size & 1)
+    except OSError:
+        return None
+
+
+def _read_into(path, offset, dst):
+    with open(path, "rb", buffering=0) as fh:
+        fh.seek(offset)
+        view = memoryview(dst).cast("B")
+        got = 0
+        while got < len(view):
+            n = fh.readinto(view[got:])
+            if not n:
+                raise OSError(f"short read from {path}")
+            got += n
+
+
+def _facial_rows(path, dtype):
+    return np.ascontiguousarray(pd.read_csv(path).drop(columns=COLUMNS_TO_DROP).values, dtype=dtype)   # :123
+
+
+last_timing = {}     # phase -> seconds of the most recent load_data_batched call (bench.py reports it)
+
+
 def load_data_batched(root_dir, sr, processed_folders, include_fast=True, include_slow=False,
                       blend_boundaries=True, blend_frames=30, rank=0, world=1, cache_format=None,
-                      device=None):
-    """``load_data`` (reference :10-26) for a whole dataset at once - the B200-first builder.
+                      device=None, dtype=np.float32, io_threads=None):
+    """``load_data`` (reference :10-26) for a whole dataset in one pipelined device pass.
 
-    Same folder scan, caches, facial handling and ``(audio_features, facial_data)`` examples in
-    ``os.listdir`` order as ``load_data`` + ``process_folder`` + ``collect_features``, but every take
-    without a cache goes through ONE batched extraction call (int16 PCM up, peak normalisation on the
-    device) and all takes through ONE batched float64 augmentation call.  With ``world > 1`` the
-    takes are split by clip over ranks (``shard.lpt_partition``); each rank returns the examples of
-    its own takes together with their positions in the full list: ``(examples, indices)``.
-    """
+    Returns ``(examples, indices)``: ``(audio_features, facial_data)`` pairs in ``os.listdir`` order (what
+    ``load_data`` + ``process_folder`` + ``collect_features`` produce, including the cache files, the
+    ``processed_folders`` updates and ``facial[:, :61] *= 100``) and the position of each example in the
+    full take list.  With ``world > 1`` the takes are split by clip over ranks (``shard.lpt_partition``
+    on the size of each take's SOURCE file, which exists identically for every rank before anything is
+    extracted); a rank only touches - and only runs ffmpeg for - its own takes.
+
+    ``dtype=np.float32`` (default, the training format): takes without a feature cache are read straight
+    into page-locked int16 memory by a thread pool, go through ``nsf_extract_collect_host`` (features and
+    augmentation fused, rows never leave the device in between) and come back as float32 views of one
+    page-locked array; cached takes are augmented by one float32 ``nsf_collect_host`` call.
+    ``dtype=np.float64``: extraction batched, augmentation through the float64 kernel - bit-identical to
+    the per-folder builder.  A take shorter than 9 frames raises ``TypeError`` exactly where the
+    reference does (``len(None)``, :143)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
     from .. import shard
     from ..utils.audio.extraction.extract_features import MIN_FRAMES
-    from ..utils.audio.load_audio import decode_for_path
+    from ..utils.audio.load_audio import REFERENCE_RATE, decode_for_path
 
+    t_start = time.perf_counter()
+    timing = {}
     cache_format = cache_format or os.environ.get("NSF_FEATURE_CACHE", "csv")
-    takes = []                      # (folder, audio_path | None, csv_cache, facial_csv)
+    if cache_format not in ("csv", "npy", "both"):
+        raise ValueError("cache_format must be 'csv', 'npy' or 'both'")
+    if dtype not in (np.float32, np.float64):
+        raise ValueError("dtype must be numpy.float32 or numpy.float64")
+    takes = []                      # (folder, source audio/video, wav, cache_csv, facial_csv, folder_path)
     for folder in os.listdir(root_dir):
         folder_path = os.path.join(root_dir, folder)
         if not os.path.isdir(folder_path) or folder in processed_folders:
@@ -227,59 +305,159 @@ def load_data_batched(root_dir, sr, processed_folders, include_fast=True, includ
                                                    os.path.exists(_binary_cache_path(cache_csv)))
         if not (facial_csv and (video or wav or have_cache)):
             continue
-        audio_path = get_audio(video, wav, folder_path) if (video or wav) else None
-        if not (audio_path or have_cache):
-            continue
-        takes.append((folder, audio_path, cache_csv, facial_csv, have_cache))
-    # partition by audio size, independent of which caches exist (ranks must agree while caches appear)
-    weights = [max(1, os.path.getsize(t[1])) if t[1] and os.path.exists(t[1]) else 1 for t in takes]
-    mine = shard.lpt_partition(weights, world)[rank] if world > 1 else list(range(len(takes)))
+        takes.append((folder, video, wav, cache_csv, facial_csv, folder_path))
+    # partition on files every rank sees identically BEFORE any rank extracts audio (never on audio.wav, which
+    # another rank may be writing): the take's video, else its wav, else its cache
+    def weight(t):
+        for cand in (t[1], t[2], t[3]):
+            if cand and os.path.exists(cand):
+                return max(1, os.path.getsize(cand))
+        return 1
+    mine = shard.lpt_partition([weight(t) for t in takes], world)[rank] if world > 1 else list(range(len(takes)))
+    timing["scan"] = time.perf_counter() - t_start
 
-    f_len, h_len = _engine.frame_params(88200)          # file-path mode always lands at 88.2 kHz
-    eng = _engine.get_engine(88200, f_len, h_len, device=device)
-    audio_rows, todo, pcms = {}, [], []
-    for i in mine:
-        folder, audio_path, cache_csv, facial_csv, have_cache = takes[i]
-        if os.path.exists(cache_csv):
-            audio_rows[i] = pd.read_csv(cache_csv).values
-        elif have_cache:
-            audio_rows[i] = np.load(_binary_cache_path(cache_csv)).astype(np.float64)
-        else:
-            pcm, _ = decode_for_path(audio_path, sr)
-            n = eng.plan.guard_frames(len(pcm))
-            if n < MIN_FRAMES:
-                print(f"Audio file is too short: {n} frames, required: {MIN_FRAMES} frames")
-                continue
-            todo.append(i)
-            pcms.append(pcm)
-    if todo:
-        if not all(p.dtype == pcms[0].dtype for p in pcms):
-            pcms = [p if p.dtype == np.float32 else p.astype(np.float32) / np.float32(32768) for p in pcms]
-        packed, off = _engine.pack_clips(pcms, dtype=pcms[0].dtype)
-        rows = eng.extract_host(packed, off, nv.PEAK_NORMALIZE)
-        roff = eng.row_offsets(off)
-        for k, i in enumerate(todo):
-            feats = rows[roff[k]:roff[k + 1]].astype(np.float64)
-            audio_rows[i] = feats
-            cache_csv = takes[i][2]
+    f_len, h_len = _engine.frame_params(REFERENCE_RATE)     # file-path mode always lands at 88.2 kHz
+    eng = _engine.get_engine(REFERENCE_RATE, f_len, h_len, device=device)
+    threads = io_threads or min(16, os.cpu_count() or 1)
+    pool = ThreadPoolExecutor(max_workers=threads)
+    try:
+        # ---- which takes need extraction; where their audio is -------------------------------------------
+        t0 = time.perf_counter()
+        cached, todo = {}, []            # take -> rows | (take, audio_path)
+        for i in mine:
+            folder, video, wav, cache_csv, facial_csv, folder_path = takes[i]
+            if os.path.exists(cache_csv):                                      # :112-114
+                print(f"Loading audio features from {cache_csv}")
+                cached[i] = pool.submit(lambda p=cache_csv: pd.read_csv(p).values)
+            elif cache_format != "csv" and os.path.exists(_binary_cache_path(cache_csv)):
+                print(f"Loading audio features from {_binary_cache_path(cache_csv)}")
+                cached[i] = pool.submit(np.load, _binary_cache_path(cache_csv))
+            else:
+                audio_path = get_audio(video, wav, folder_path) if (video or wav) else None
+                if not audio_path:
+                    continue                                                   # process_folder returns (None, None)
+                print(f"Extracting audio features from {audio_path}")
+                todo.append((i, audio_path))
+        todo_set = {j for j, _ in todo}
+        keep = [i for i in mine if i in cached or i in todo_set]
+        facial_jobs = {i: pool.submit(_facial_rows, takes[i][4], dtype) for i in keep}
+
+        # ---- PCM of the takes to extract: mono PCM16 files at 88.2 kHz are read straight into page-locked
+        # int16 memory (2 bytes per sample over PCIe); anything else is decoded / resampled to float32 ----------
+        n_rows = {}
+        pcm_arena = pcm = off = None
+        if todo:
+            info = [_pcm16_payload(p, REFERENCE_RATE) if sr == REFERENCE_RATE else None for _, p in todo]
+            fast = all(x is not None for x in info)
+            if fast:
+                lens = [n for _, n in info]
+            else:
+                decoded = list(pool.map(lambda tp: _as_float32(decode_for_path(tp[1], sr)[0]), todo))
+                lens = [len(d) for d in decoded]
+            for (i, _), n in zip(todo, lens):
+                g = eng.plan.guard_frames(n)
+                if g < MIN_FRAMES:                                             # extract_features.py:16-20 -> :143
+                    print(f"Audio file is too short: {g} frames, required: {MIN_FRAMES} frames")
+                    raise TypeError("object of type 'NoneType' has no len()")
+            off = np.zeros(len(todo) + 1, dtype=np.int64)
+            np.cumsum(lens, out=off[1:])
+            item = 2 if fast else 4
+            pcm_arena = _engine.PinnedBuffer(int(off[-1]) * item)
+            pcm = pcm_arena.view(np.int16 if fast else np.float32, (int(off[-1]),))
+            if fast:
+                for (_, p) in todo:
+                    print(f"Loaded audio file '{p}' with sample rate {REFERENCE_RATE}")
+                list(pool.map(lambda k: _read_into(todo[k][1], info[k][0], pcm[off[k]:off[k + 1]]), range(len(todo))))
+            else:
+                for k, d in enumerate(decoded):
+                    pcm[off[k]:off[k + 1]] = d
+                del decoded
+            roff = eng.row_offsets(off)
+            for k, (i, _) in enumerate(todo):
+                n_rows[i] = int(roff[k + 1] - roff[k])
+        timing["read_audio"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        facial = {i: j.result() for i, j in facial_jobs.items()}
+        cached = {i: j.result() for i, j in cached.items()}
+        timing["facial_csv_wait"] = time.perf_counter() - t0
+
+        # ---- device pass ------------------------------------------------------------------------------------
+        t0 = time.perf_counter()
+        results = {}                    # take -> (audio rows, facial rows)
+        feats_by_take = {}
+        kw = dict(include_fast=include_fast, include_slow=include_slow, blend_boundaries=blend_boundaries,
+                  blend_frames=blend_frames)
+        augment = include_fast or include_slow
+        if todo:
+            order = [i for i, _ in todo]
+            f_off = np.zeros(len(order) + 1, dtype=np.int64)
+            np.cumsum([len(facial[i]) for i in order], out=f_off[1:])
+            if dtype == np.float32 and augment and all(n_rows[i] and len(facial[i]) for i in order):
+                f_cols = facial[order[0]].shape[1]
+                fac_arena = _engine.PinnedBuffer(int(f_off[-1]) * f_cols * 4)
+                fac = fac_arena.view(np.float32, (int(f_off[-1]), f_cols))
+                for k, i in enumerate(order):
+                    fac[f_off[k]:f_off[k + 1]] = facial[i]
+                o_off = eng.collect_rows(roff, f_off, **kw)
+                out_arena = _engine.PinnedBuffer(int(o_off[-1]) * (256 + fac.shape[1]) * 4 + int(roff[-1]) * 256 * 4)
+                out_a = out_arena.view(np.float32, (int(o_off[-1]), 256))
+                out_f = out_arena.view(np.float32, (int(o_off[-1]), fac.shape[1]), offset=out_a.nbytes)
+                feats = out_arena.view(np.float32, (int(roff[-1]), 256), offset=out_a.nbytes + out_f.nbytes)
+                eng.extract_collect_host(pcm, off, fac, f_off, nv.PEAK_NORMALIZE, out_audio=out_a, out_facial=out_f,
+                                         features_out=feats, **kw)
+                for k, i in enumerate(order):
+                    results[i] = (out_a[o_off[k]:o_off[k + 1]], out_f[o_off[k]:o_off[k + 1]])
+                    feats_by_take[i] = feats[roff[k]:roff[k + 1]]
+            else:
+                rows = eng.extract_host(pcm, off, nv.PEAK_NORMALIZE)
+                for k, i in enumerate(order):
+                    feats_by_take[i] = rows[roff[k]:roff[k + 1]]
+                    cached[i] = feats_by_take[i]
+        if cached:
+            order = sorted(cached)
+            rows_in = [np.ascontiguousarray(cached[i], dtype=dtype) for i in order]
+            if augment and all(len(r) for r in rows_in) and all(len(facial[i]) for i in order):
+                a_off = np.zeros(len(order) + 1, dtype=np.int64)
+                np.cumsum([len(r) for r in rows_in], out=a_off[1:])
+                f_off = np.zeros(len(order) + 1, dtype=np.int64)
+                np.cumsum([len(facial[i]) for i in order], out=f_off[1:])
+                out_a, out_f, o_off = eng.collect_host(np.concatenate(rows_in, axis=0), a_off,
+                                                       np.concatenate([facial[i] for i in order], axis=0), f_off, **kw)
+                for k, i in enumerate(order):
+                    results[i] = (out_a[o_off[k]:o_off[k + 1]], out_f[o_off[k]:o_off[k + 1]])
+            else:
+                for r, i in zip(rows_in, order):
+                    results[i] = tuple(np.array(x) for x in collect_arrays(r, facial[i], **kw))
+        timing["device"] = time.perf_counter() - t0
+
+        # ---- side effects: feature caches (:115-120), facial scaling (:68), processed_folders (:24) ---------
+        t0 = time.perf_counter()
+        def write_cache(i):
+            cache_csv, f = takes[i][3], feats_by_take[i]
             if cache_format in ("csv", "both"):
-                pd.DataFrame(feats).to_csv(cache_csv, index=False)
+                pd.DataFrame(np.asarray(f, dtype=np.float64)).to_csv(cache_csv, index=False)
+                print(f"Audio features saved to {cache_csv}")
             if cache_format in ("npy", "both"):
-                np.save(_binary_cache_path(cache_csv), feats.astype(np.float32))
-    order = [i for i in mine if i in audio_rows]
-    if not order:
-        return ([], []) if world > 1 else []
-    facial = [pd.read_csv(takes[i][3]).drop(columns=COLUMNS_TO_DROP).values.astype(np.float64) for i in order]
-    out_a, out_f, o_off = eng.collect_host(
-        np.concatenate([audio_rows[i] for i in order], axis=0),
-        np.concatenate([[0], np.cumsum([len(audio_rows[i]) for i in order])]),
-        np.concatenate(facial, axis=0), np.concatenate([[0], np.cumsum([len(f) for f in facial])]),
-        include_fast, include_slow, blend_boundaries, blend_frames)
-    examples = []
-    for k, i in enumerate(order):
-        a = out_a[o_off[k]:o_off[k + 1]]
-        f = out_f[o_off[k]:o_off[k + 1]].copy()
+                np.save(_binary_cache_path(cache_csv), np.asarray(f, dtype=np.float32))
+                print(f"Audio features saved to {_binary_cache_path(cache_csv)}")
+        list(pool.map(write_cache, list(feats_by_take)))
+        timing["write_cache"] = time.perf_counter() - t0
+    finally:
+        pool.shutdown(wait=True)
+    examples, indices = [], []
+    for i in mine:
+        if i not in results:
+            continue
+        a, f = results[i]
         f[:, :61] *= 100                                                   # process_folder :68
         examples.append((a, f))
+        indices.append(i)
         processed_folders.add(takes[i][0])
-    return (examples, order) if world > 1 else examples
+    timing["total"] = time.perf_counter() - t_start
+    last_timing.clear()
+    last_timing.update(timing)
+    return examples, indices
+
+
+def _as_float32(pcm):
+    return pcm if pcm.dtype == np.float32 else pcm.astype(np.float32) / np.float32(32768)

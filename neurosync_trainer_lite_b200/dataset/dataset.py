@@ -4,7 +4,9 @@
 ``collate_fn`` contracts: item ``i`` is ``(float32[128, 256], float32[128, 61])``.  The difference
 is memory: the reference materialises every stride-1 window (``process_example`` :58-98, the source
 of its 128-256 GB host-RAM advice); here each clip's rows are stored once as float32 and a window is
-a zero-copy ``narrow`` view produced at ``__getitem__`` time.  The duplicated, reflected last window
+produced at ``__getitem__`` time: an independent tensor by default (what the reference hands out, safe
+for in-place augmentation), or - ``config['zero_copy_windows'] = True`` - a read-only-by-contract
+``narrow`` view that shares the clip's storage with the 127 windows overlapping it.  The duplicated, reflected last window
 the reference appends when ``N % 128 != 0`` (:77-96) and its failure for ``N < 128`` are preserved.
 Pure host-side indexing - no arithmetic - so it needs no kernel.
 """
@@ -92,6 +94,9 @@ class AudioFacialDataset(Dataset):
         self.sr = config['sr']
         self.frame_rate = config['frame_rate']
         self.micro_batch_size = config['micro_batch_size']
+        # False (default): items are independent copies, as in the reference.  True: items are views into the
+        # clip's rows - no copy, but modifying one in place corrupts every overlapping window
+        self.zero_copy_windows = bool(config.get('zero_copy_windows', False))
         self.processed_folders = set()
         self.clips = []
         self._starts = [0]
@@ -117,7 +122,10 @@ class AudioFacialDataset(Dataset):
         if not 0 <= idx < len(self):
             raise IndexError(idx)
         c = int(np.searchsorted(self._starts, idx, side="right")) - 1
-        return self.clips[c].get(idx - self._starts[c])
+        a, f = self.clips[c].get(idx - self._starts[c])
+        if getattr(self, "zero_copy_windows", False):
+            return a, f
+        return a.clone(), f.clone()
 
     @staticmethod
     def collate_fn(batch):
@@ -129,4 +137,4 @@ class AudioFacialDataset(Dataset):
     def process_example(self, audio_features, facial_data):
         """reference :58-98 -- kept for API parity: the explicit list of windows of ONE clip."""
         clip = _WindowedClip(audio_features, facial_data, self.micro_batch_size)
-        return [clip.get(i) for i in range(len(clip))]
+        return [tuple(t.clone() for t in clip.get(i)) for i in range(len(clip))]

@@ -28,32 +28,44 @@ def frame_params(sr):
     return f, nv.lib.nsf_hop_length(f)
 
 
+class _HostBlock:
+    """Owner of one cudaHostAlloc allocation: frees it when the last array viewing it is gone."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr is not None and self.ptr.value:
+                nv.lib.nsf_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 class PinnedBuffer:
-    """Page-locked host array (cudaHostAlloc through the C ABI) exposed as a NumPy array."""
+    """Page-locked host memory (cudaHostAlloc through the C ABI) exposed as NumPy arrays.
+
+    The allocation is owned by the ctypes block every view is built on, so arrays handed to callers
+    (e.g. the dataset examples of ``load_data``) stay valid after the ``PinnedBuffer`` object itself
+    is dropped; the memory is released when the last view dies."""
 
     def __init__(self, nbytes):
         p = C.c_void_p()
         nv.check(nv.lib.nsf_host_alloc(C.byref(p), int(max(nbytes, 1))))
-        self._ptr = p
         self.nbytes = int(nbytes)
+        self.address = p.value
         self._raw = (C.c_char * max(self.nbytes, 1)).from_address(p.value)
+        self._raw._block = _HostBlock(p)
 
-    def view(self, dtype, shape):
+    def view(self, dtype, shape, offset=0):
         count = int(np.prod(shape))
-        arr = np.frombuffer(self._raw, dtype=dtype, count=count)
+        arr = np.frombuffer(self._raw, dtype=dtype, count=count, offset=int(offset))
         return arr.reshape(shape)
 
     def close(self):
-        if self._ptr is not None and self._ptr.value:
-            self._raw = None
-            nv.lib.nsf_host_free(self._ptr)
-            self._ptr = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        """Drop this object's reference; the memory goes when no view is left."""
+        self._raw = None
 
 
 class Plan:
@@ -288,10 +300,11 @@ class Engine:
 
     def extract_collect_host(self, pcm, offsets, facial, facial_offsets, flags=0, include_fast=True,
                              include_slow=False, blend_boundaries=True, blend_frames=30, out_audio=None,
-                             out_facial=None):
+                             out_facial=None, features_out=None):
         """Features of a batch of clips AND their ``collect_features`` augmentation in one pipelined pass
         (``nsf_extract_collect_host``): the feature rows stay on the device between the two steps.
-        float32 in (facial) and out; returns (audio rows, facial rows, output row offsets)."""
+        float32 in (facial) and out; returns (audio rows, facial rows, output row offsets).
+        ``features_out`` (optional ``[sum R_i, cols]`` float32) also receives the un-augmented rows."""
         pcm = np.ascontiguousarray(pcm)
         fmt = self._pcm_format(pcm)
         facial = np.ascontiguousarray(facial, dtype=np.float32)
@@ -307,10 +320,14 @@ class Engine:
             out_facial = np.empty((n_out, facial.shape[1]), dtype=np.float32)
         assert out_audio.shape == (n_out, cols) and out_facial.shape == (n_out, facial.shape[1])
         cflags = self.collect_flags(include_fast, include_slow, blend_boundaries)
+        if features_out is not None:
+            n_rows = int(self.row_offsets(off, flags)[-1])
+            assert features_out.dtype == np.float32 and features_out.shape == (n_rows, cols)
         with self._lock:
             nv.check(nv.lib.nsf_extract_collect_host(self.handle, nv.ptr(pcm), fmt, off_p, len(off) - 1, flags,
                                                      nv.ptr(facial), facial.shape[1], f_p, cflags,
-                                                     int(blend_frames), nv.ptr(out_audio), nv.ptr(out_facial)))
+                                                     int(blend_frames), nv.ptr(out_audio), nv.ptr(out_facial),
+                                                     nv.ptr(features_out)))
         return out_audio, out_facial, o_off
 
     def collect_host(self, audio, audio_offsets, facial, facial_offsets, include_fast=True,

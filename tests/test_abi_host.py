@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported(nv):
     for name in sorted(declared):
         assert hasattr(nv.lib, name), f"{name} declared in nsf.h but not exported by libnsf.so"
     assert declared == set(nv.EXPORTED), declared ^ set(nv.EXPORTED)
-    assert nv.lib.nsf_abi_version() == 1
+    assert nv.lib.nsf_abi_version() == 2
 
 
 @pytest.mark.parametrize("sr", [88200, 16000, 44100, 22050, 48000, 8000, 96000, 11025, 32000])

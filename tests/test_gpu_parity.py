@@ -372,10 +372,14 @@ def test_collect_features_with_csv_plumbing(tmp_path, dp, oracle):
     np.testing.assert_allclose(a4, a3, rtol=0, atol=1e-6)                   # float32 cache
     np.testing.assert_allclose(a3, a, rtol=0, atol=1e-12)
     done = set()
-    ex = dp.load_data(str(tmp_path / "data"), 88200, done)                  # dataset builder on top
+    ex = dp.load_data_per_folder(str(tmp_path / "data"), 88200, done)       # the reference's loop, float64
     assert len(ex) == 1 and done == {"take_001"}
     np.testing.assert_allclose(ex[0][0], a, rtol=0, atol=1e-12)
     np.testing.assert_allclose(ex[0][1], wf * 100, rtol=1e-15, atol=0)      # facial[:, :61] *= 100
+    ex32 = dp.load_data(str(tmp_path / "data"), 88200, set())               # batched float32 builder, CSV cache hit
+    assert len(ex32) == 1 and ex32[0][0].dtype == np.float32
+    np.testing.assert_allclose(ex32[0][0], a, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(ex32[0][1], wf * 100, rtol=3e-7, atol=0)
 
 
 def test_batched_dataset_builder_equals_per_folder_builder(tmp_path, dp):
@@ -391,24 +395,52 @@ def test_batched_dataset_builder_equals_per_folder_builder(tmp_path, dp):
             (take / "audio.wav").write_bytes(synth.wav_bytes(synth.to_int16_pcm(0.8 * y), 88200))
             pd.DataFrame(np.hstack([np.zeros((rows, 2)), synth.synth_facial(rows, seed=k)]),
                          columns=cols).to_csv(take / f"t{k}_iPhone_cal.csv", index=False)
-    ref = dp.load_data(str(tmp_path / "a"), 88200, set())
+    ref = dp.load_data_per_folder(str(tmp_path / "a"), 88200, set())       # process_folder per take, float64
     done = set()
-    got = dp.load_data_batched(str(tmp_path / "b"), 88200, done)
-    assert len(ref) == len(got) == 3 and len(done) == 3
-    # os.listdir order is the same for both roots (same names), so examples pair up
+    got, order = dp.load_data_batched(str(tmp_path / "b"), 88200, done, dtype=np.float64)
+    assert len(ref) == len(got) == 3 and len(done) == 3 and order == [0, 1, 2]
+    # os.listdir order is the same for both roots (same names), so examples pair up; the float64 mode runs the
+    # same float64 augmentation kernel on the same float32 features: bit-identical
     for (ra, rf), (ga, gf) in zip(ref, got):
-        assert ra.shape == ga.shape and rf.shape == gf.shape
-        np.testing.assert_allclose(ga, ra, rtol=0, atol=1e-12)
+        assert ra.shape == ga.shape and rf.shape == gf.shape and ga.dtype == np.float64
+        np.testing.assert_array_equal(ga, ra)
         np.testing.assert_array_equal(gf, rf)
-    # sharded over two "ranks": union of the shards == the full list, positions returned
+    # default float32 mode = what load_data() returns: fused extract + collect from page-locked int16 PCM
     for p in (tmp_path / "b").glob("*/audio_features.csv"):
         p.unlink()
-    parts = [dp.load_data_batched(str(tmp_path / "b"), 88200, set(), rank=r, world=2) for r in range(2)]
+    done32 = set()
+    got32 = dp.load_data(str(tmp_path / "b"), 88200, done32)
+    assert len(got32) == 3 and len(done32) == 3
+    assert all((tmp_path / "b" / f"take_{k:03d}" / "audio_features.csv").exists() for k in range(3))   # cache side effect
+    for (ra, rf), (ga, gf) in zip(ref, got32):
+        assert ga.dtype == np.float32 and gf.dtype == np.float32 and ra.shape == ga.shape and rf.shape == gf.shape
+        np.testing.assert_allclose(ga, ra, rtol=0, atol=2e-6)     # float32 cross-fades of values in about +-5
+        np.testing.assert_allclose(gf, rf, rtol=3e-7, atol=1e-5)
+    # the cache written by the float32 builder holds the un-augmented rows the per-folder builder cached
+    import pandas as pd2
+    ca = pd2.read_csv(tmp_path / "a" / "take_001" / "audio_features.csv").values
+    cb = pd2.read_csv(tmp_path / "b" / "take_001" / "audio_features.csv").values
+    np.testing.assert_array_equal(ca, cb)
+    # sharded over two "ranks": union of the shards == the full list, positions returned; a rank touches only
+    # its own takes
+    for p in (tmp_path / "b").glob("*/audio_features.csv"):
+        p.unlink()
+    parts = [dp.load_data_batched(str(tmp_path / "b"), 88200, set(), rank=r, world=2, dtype=np.float64)
+             for r in range(2)]
     seen = sorted(i for _, idx in parts for i in idx)
     assert seen == [0, 1, 2]
     for ex, idx in parts:
         for (ga, gf), i in zip(ex, idx):
-            np.testing.assert_allclose(ga, ref[i][0], rtol=0, atol=1e-12)
+            np.testing.assert_array_equal(ga, ref[i][0])
+    # a take under 9 frames fails where the reference fails (TypeError from len(None))
+    short = tmp_path / "c" / "take_000"
+    short.mkdir(parents=True)
+    (short / "audio.wav").write_bytes(synth.wav_bytes(np.zeros(5000, np.int16), 88200))
+    pd.DataFrame(np.zeros((10, 63)), columns=cols).to_csv(short / "s_iPhone_cal.csv", index=False)
+    with pytest.raises(TypeError):
+        dp.load_data(str(tmp_path / "c"), 88200, set())
+    with pytest.raises(TypeError):
+        dp.load_data_per_folder(str(tmp_path / "c"), 88200, set())
 
 
 def test_dataset_windows_match_reference_semantics(golden, nv):
