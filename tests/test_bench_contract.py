@@ -61,8 +61,13 @@ def test_bench_workload_table_and_algorithmic_counts():
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    assert set(bench.WORKLOADS) == {"c2", "c3", "c4", "c5"} and set(bench.COLLECT) == {"c3", "c4"}
-    alg = bench.algorithmic(88200, 1470, 735, 384, 768)
+    assert set(bench.WORKLOADS) == {"c2", "c3", "c4", "c5"}
+    assert {n for n, w in bench.WORKLOADS.items() if w["collect"]} == {"c3", "c4"}
+    # configs[2] and [4] are split over the ranks (strong), c2 / c4 carry a fixed batch per rank
+    assert bench.DEFAULT_SCALING == {"c2": "weak", "c3": "strong", "c4": "weak", "c5": "strong"}
+    # the math libraries are pinned before NumPy is imported by the module (children of the CPU pool inherit it)
+    assert all(os.environ.get(k) == "1" for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"))
+    alg = bench.algorithmic(88200, 1470, 735, 384)
     # per hop-frame at 88.2 kHz
     assert alg["stft_gemm"][1] == 4327680 and alg["autocorr"][1] == 517564
     assert alg["stft_gemm"][0] == alg["autocorr"][0] == "tensor" and alg["fold"][0] == "hbm"
