@@ -433,7 +433,9 @@ def measure_workload(name, scaling, steps, warmup, D, rank, world, local_rank, d
             acc[k] = acc.get(k, 0.0) + v / reps
     eng.set_profiling(False)
     if col:                                            # the augmentation kernel on its own (CUDA events, same stream)
+        reps = 10
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
         c0.record(stream)
         for _ in range(reps):
             eng.collect_device(out, col["a_off"], col["facial"], col["f_off"], out_audio=col["out_a"],
@@ -754,7 +756,7 @@ def api_e2e(D, rank, world, local_rank, steps):
                 "phases_ms": {k: round(v * 1e3, 2) for k, v in phases.items()},
                 "what_is_inside": "folder scan, WAV payloads read into page-locked memory by a thread pool, facial "
                                   "CSVs parsed by pandas (thread pool), fused extract + collect on the device, "
-                                  "feature caches written (.npy), examples returned as float32 views"}
+                                  "feature caches written (.npy), examples returned as float32 arrays"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
         os.environ.pop("NSF_FEATURE_CACHE", None)

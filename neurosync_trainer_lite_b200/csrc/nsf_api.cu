@@ -2,6 +2,7 @@
 // host-buffer (H2D -> kernels -> D2H) pipeline.  See include/nsf.h for the contract.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -134,7 +135,16 @@ struct PinnedArena {
 constexpr int kSlots = 3;
 constexpr int64_t kGroupSamples = int64_t(24) << 20;       // ~96 MB of float32 PCM per in-flight group
 constexpr int64_t kFirstGroupSamples = int64_t(6) << 20;   // groups 0 and 1
-inline int64_t group_budget(int turn) { return turn < 2 ? kFirstGroupSamples : kGroupSamples; }
+// NSF_GROUP_MI / NSF_FIRST_MI (Mi samples) override the two budgets for pipeline experiments
+inline int64_t env_mi(const char* name, int64_t dflt) {
+  const char* v = std::getenv(name);
+  const long n = v ? std::atol(v) : 0;
+  return n > 0 ? (int64_t(n) << 20) : dflt;
+}
+inline int64_t group_budget(int turn) {
+  static const int64_t big = env_mi("NSF_GROUP_MI", kGroupSamples), first = env_mi("NSF_FIRST_MI", kFirstGroupSamples);
+  return turn < 2 ? first : big;
+}
 
 struct Slot {  // one in-flight clip group of the host pipeline
   cudaStream_t stream = nullptr;
@@ -143,9 +153,9 @@ struct Slot {  // one in-flight clip group of the host pipeline
   cudaEvent_t done = nullptr;
   // pageable callers: the group's PCM is gathered into `stage_in` (pinned) before its upload and its rows
   // come back through `stage_out` (pinned); `pending_*` describe the copy-out owed to the caller's buffers
-  PinnedArena stage_in, stage_out, stage_aux;
+  PinnedArena stage_in, stage_out, stage_aux, stage_fac, stage_feat;
   struct CopyOut { void* dst; const void* src; size_t bytes; size_t dst_pitch, src_pitch, width; int64_t rows; };
-  CopyOut pending[3];
+  CopyOut pending[4];
   int n_pending = 0;
 };
 
@@ -317,8 +327,15 @@ nsf_status desc_acquire(nsf_ctx* ctx, size_t bytes, DescEntry** out) {
   DescEntry& d = ctx->desc[ctx->desc_next];
   ctx->desc_next = (ctx->desc_next + 1) % kDescRing;
   if (d.pending) { NSF_CUDA(cudaEventSynchronize(d.copied)); d.pending = false; }
-  const nsf_status st = d.mem.reserve(bytes);
-  if (st != NSF_OK) return st;
+  if (bytes > d.mem.bytes) {
+    // a larger batch geometry than any seen so far: grow EVERY entry now (cudaHostAlloc synchronises the
+    // device), so that the following calls of the same size find their entries ready
+    for (auto& e : ctx->desc) {
+      if (e.pending) { NSF_CUDA(cudaEventSynchronize(e.copied)); e.pending = false; }
+      const nsf_status st = e.mem.reserve(bytes);
+      if (st != NSF_OK) return st;
+    }
+  }
   *out = &d;
   return NSF_OK;
 }
@@ -468,8 +485,9 @@ nsf_status nsf_ctx_create(const nsf_plan* plan, int32_t device, nsf_ctx** out_ct
   nsf_status st = upload_tables(ctx);
   if (st != NSF_OK) { nsf_ctx_destroy(ctx); return st; }
   for (auto& d : ctx->desc) {
-    if (cudaEventCreateWithFlags(&d.copied, cudaEventDisableTiming) != cudaSuccess) {
-      set_error("cudaEventCreate failed"); nsf_ctx_destroy(ctx); return NSF_ERR_CUDA;
+    if (cudaEventCreateWithFlags(&d.copied, cudaEventDisableTiming) != cudaSuccess ||
+        d.mem.reserve(size_t(48) << 10) != NSF_OK) {      // room for ~2000 clips per call before the ring grows
+      set_error("descriptor ring setup failed"); nsf_ctx_destroy(ctx); return NSF_ERR_CUDA;
     }
   }
   // opt-in shared-memory limits of every kernel, once per device: no launch path touches function attributes
@@ -494,7 +512,7 @@ void nsf_ctx_destroy(nsf_ctx* ctx) {
     if (s.done) cudaEventDestroy(s.done);
     s.pcm.release(); s.out.release(); s.work.release(); s.ynorm.release();
     s.fac_in.release(); s.col_a.release(); s.col_f.release(); s.col_desc.release();
-    s.stage_in.release(); s.stage_out.release(); s.stage_aux.release();
+    s.stage_in.release(); s.stage_out.release(); s.stage_aux.release(); s.stage_fac.release(); s.stage_feat.release();
   }
   for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
   for (auto& d : ctx->desc) {
@@ -1026,7 +1044,12 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
   for (int i = 0; i <= n_clips; ++i) a_rows[i] = all.row_off[i];
   if ((st = collect_offsets(a_rows.data(), f_off, n_clips, collect_flags, blend_frames, nullptr, &o_all)) != NSF_OK) return st;
   NSF_CUDA(cudaSetDevice(ctx->device));
+  for (auto& sl : ctx->slot) sl.n_pending = 0;
   const size_t esz = pcm_format == NSF_PCM_I16 ? 2 : 4;
+  // pageable caller buffers are staged through the slot's pinned arenas (see nsf_extract_host)
+  const bool pcm_dma = dma_reachable(pcm_host), fac_dma = dma_reachable(facial_host);
+  const bool oa_dma = dma_reachable(out_audio_host), of_dma = dma_reachable(out_facial_host);
+  const bool ft_dma = features_host ? dma_reachable(features_host) : true;
   int first = 0, turn = 0;
   while (first < n_clips) {
     int last = first;
@@ -1038,7 +1061,7 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
     const int gn = last - first;
     Slot* sl = &ctx->slot[turn % kSlots];
     if ((st = ensure_slot(sl)) != NSF_OK) return st;
-    NSF_CUDA(cudaStreamSynchronize(sl->stream));      // the slot's previous group has fully drained
+    if ((st = drain_slot(sl)) != NSF_OK) return st;   // the slot's previous group has fully drained
     const int64_t rows = all.row_off[last] - all.row_off[first];
     const int64_t frows = f_off[last] - f_off[first];
     const int64_t orows = o_all[last] - o_all[first];
@@ -1052,9 +1075,20 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
     if ((st = sl->col_f.reserve(static_cast<size_t>(orows) * facial_cols * sizeof(float))) != NSF_OK) return st;
     if ((st = sl->col_desc.reserve(3 * n1 * sizeof(int64_t))) != NSF_OK) return st;
     const char* src = static_cast<const char*>(pcm_host) + clip_offsets[first] * esz;
+    if (!pcm_dma) {
+      if ((st = sl->stage_in.reserve(samples * esz)) != NSF_OK) return st;
+      host_copy(sl->stage_in.ptr, src, samples * esz);
+      src = static_cast<const char*>(sl->stage_in.ptr);
+    }
     NSF_CUDA(cudaMemcpyAsync(sl->pcm.ptr, src, samples * esz, cudaMemcpyHostToDevice, sl->stream));
-    NSF_CUDA(cudaMemcpyAsync(sl->fac_in.ptr, facial_host + f_off[first] * facial_cols,
-                             static_cast<size_t>(frows) * facial_cols * sizeof(float), cudaMemcpyHostToDevice, sl->stream));
+    const size_t fac_bytes = static_cast<size_t>(frows) * facial_cols * sizeof(float);
+    const float* fsrc = facial_host + f_off[first] * facial_cols;
+    if (!fac_dma) {
+      if ((st = sl->stage_fac.reserve(fac_bytes)) != NSF_OK) return st;
+      host_copy(sl->stage_fac.ptr, fsrc, fac_bytes);
+      fsrc = static_cast<const float*>(sl->stage_fac.ptr);
+    }
+    NSF_CUDA(cudaMemcpyAsync(sl->fac_in.ptr, fsrc, fac_bytes, cudaMemcpyHostToDevice, sl->stream));
     // collect descriptors of this group (relative offsets) through the guarded pinned staging buffer.  Staged
     // BEFORE the extraction kernels are enqueued: the next wait on the staging buffer then ends as soon as this
     // group's uploads have run, so the host can start the next group's upload while these kernels execute
@@ -1080,18 +1114,27 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
                                  sl->col_f.ptr);
     if (n < 0) { set_error(cuda_msg("launch_collect", cudaGetLastError())); return NSF_ERR_CUDA; }
     ctx->launches += n;
-    if (features_host)   // the un-augmented rows as well (what collect_features caches as audio_features.csv)
-      NSF_CUDA(cudaMemcpyAsync(features_host + all.row_off[first] * cols, sl->out.ptr,
-                               static_cast<size_t>(rows) * cols * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
-    NSF_CUDA(cudaMemcpyAsync(out_audio_host + o_all[first] * cols, sl->col_a.ptr,
-                             static_cast<size_t>(orows) * cols * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
-    NSF_CUDA(cudaMemcpyAsync(out_facial_host + o_all[first] * facial_cols, sl->col_f.ptr,
-                             static_cast<size_t>(orows) * facial_cols * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+    // downloads: straight into page-locked caller memory, else through a pinned stage + host copy at drain time
+    auto download = [&](void* dst, const void* dev, size_t bytes, bool dma, PinnedArena* stage) -> nsf_status {
+      if (dma) { NSF_CUDA(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, sl->stream)); return NSF_OK; }
+      const nsf_status r = stage->reserve(bytes);
+      if (r != NSF_OK) return r;
+      NSF_CUDA(cudaMemcpyAsync(stage->ptr, dev, bytes, cudaMemcpyDeviceToHost, sl->stream));
+      sl->pending[sl->n_pending++] = Slot::CopyOut{dst, stage->ptr, bytes, 0, 0, 0, 1};
+      return NSF_OK;
+    };
+    if (features_host &&   // the un-augmented rows as well (what collect_features caches as audio_features.csv)
+        (st = download(features_host + all.row_off[first] * cols, sl->out.ptr,
+                       static_cast<size_t>(rows) * cols * sizeof(float), ft_dma, &sl->stage_feat)) != NSF_OK) return st;
+    if ((st = download(out_audio_host + o_all[first] * cols, sl->col_a.ptr,
+                       static_cast<size_t>(orows) * cols * sizeof(float), oa_dma, &sl->stage_out)) != NSF_OK) return st;
+    if ((st = download(out_facial_host + o_all[first] * facial_cols, sl->col_f.ptr,
+                       static_cast<size_t>(orows) * facial_cols * sizeof(float), of_dma, &sl->stage_aux)) != NSF_OK) return st;
     first = last;
     ++turn;
   }
   for (auto& sl : ctx->slot)
-    if (sl.stream) NSF_CUDA(cudaStreamSynchronize(sl.stream));
+    if (sl.stream && (st = drain_slot(&sl)) != NSF_OK) return st;
   return NSF_OK;
 }
 

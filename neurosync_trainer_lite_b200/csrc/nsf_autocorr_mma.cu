@@ -20,6 +20,8 @@
 // r[lag] / r[0].
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "nsf.h"
 #include "nsf_device_utils.cuh"
 #include "nsf_kernels.cuh"
@@ -309,6 +311,162 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   __syncwarp();
 }
 
+// The same lags with HALF the shared-memory traffic for the A operand and no B history (kExact kernels: the number
+// of K-blocks is a compile-time constant and the loop is fully unrolled, so every register index below is static).
+//
+// Rows 8..15 of the A fragment of K-block b, H(b) = X(16 b + 64 + k + 8 r) (r = 0..7), are rows 0..7 of block b + 4.
+// So only H is ever loaded - ONE ldmatrix.x4 per K-block brings {hi k0-7, hi k8-15, lo k0-7, lo k8-15} - and
+//     tile 0 (lags   0..127):  A = [H(b-4) ; H(b)  ]   x   B(b)
+//     tile 1 (lags 64..191):   A = [H(b)   ; H(b+4)]   x   B(b)      (rows 8..15 = lags 128..191 are kept)
+// both against the CURRENT block's B fragments: 8 shared-memory wavefronts per K-block (4 for H, 4 for B) instead
+// of 12, ten live H fragments in a statically indexed ring, and the products reach every accumulator in the same
+// order as in am_mma (bit-identical results).  H(b) is identically zero from block kBlocks - 4 on (samples beyond
+// 16 kBlocks are the zero padding), which also removes tile 1's last four blocks.
+template <int kBlocks>
+__device__ __forceinline__ void am_mma_ring(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
+  static_assert(kBlocks % 4 == 0 && kBlocks >= 12, "K-blocks come in groups of four");
+  const int g = lane >> 2, tq = lane & 3;
+  const int mi = lane >> 3, mr = lane & 7;
+  const uint32_t lo_delta = 2u * static_cast<uint32_t>(geo.len);
+  // this lane's ldmatrix row of H(0); H(b) lies 32 bytes per block further (negative b: the frame's first rows)
+  const uint32_t sa0 = am_smem_u32(copies) + 2u * static_cast<uint32_t>(kFrontMargin + 64 + 8 * mr + (mi & 1) * 8) +
+                       static_cast<uint32_t>(mi >> 1) * lo_delta;
+  const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
+  const uint32_t* E_lo = E_hi + geo.len / 2;
+  const uint32_t* O_hi = E_lo + geo.len / 2;
+  const uint32_t* O_lo = O_hi + geo.len / 2;
+  const int boff = kFrontMargin + 2 * tq - g - (g & 1);
+  const uint32_t* Bh = ((g & 1) ? O_hi : E_hi) + boff / 2;
+  const uint32_t* Bl = ((g & 1) ? O_lo : E_lo) + boff / 2;
+  float d0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d0x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float d1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  constexpr int kRing = 10;                 // H(b-4) .. H(b+5): slot of H(b) = (b + 4) % kRing
+  uint32_t H[kRing][4];
+#pragma unroll
+  for (int b = -4; b <= 4; ++b) ldsm_x4(sa0 + static_cast<uint32_t>(32 * b), H[(b + 4) % kRing]);
+  uint32_t B[2][4];
+  B[0][0] = Bh[0]; B[0][1] = Bh[4]; B[0][2] = Bl[0]; B[0][3] = Bl[4];
+#pragma unroll
+  for (int b = 0; b < kBlocks; ++b) {
+    // one block ahead: H(b + 5) into the slot H(b - 5) has just left, B(b + 1) into the other B set
+    if (b + 5 < kBlocks - 4) {
+      ldsm_x4(sa0 + static_cast<uint32_t>(32 * (b + 5)), H[(b + 9) % kRing]);
+    } else {
+      H[(b + 9) % kRing][0] = H[(b + 9) % kRing][1] = H[(b + 9) % kRing][2] = H[(b + 9) % kRing][3] = 0u;
+    }
+    if (b + 1 < kBlocks) {
+      B[(b + 1) & 1][0] = Bh[8 * (b + 1)]; B[(b + 1) & 1][1] = Bh[8 * (b + 1) + 4];
+      B[(b + 1) & 1][2] = Bl[8 * (b + 1)]; B[(b + 1) & 1][3] = Bl[8 * (b + 1) + 4];
+    }
+    const uint32_t(&lo4)[4] = H[b % kRing];          // H(b - 4): rows 0..7 of tile 0
+    const uint32_t(&mid)[4] = H[(b + 4) % kRing];    // H(b):     rows 8..15 of tile 0, rows 0..7 of tile 1
+    const uint32_t(&hi4)[4] = H[(b + 8) % kRing];    // H(b + 4): rows 8..15 of tile 1
+    const uint32_t(&cur)[4] = B[b & 1];              // {b0 hi, b1 hi, b0 lo, b1 lo}
+    const bool tile1 = b < kBlocks - 4;              // compile-time after unrolling
+    mma_16816(d0x, lo4[0], mid[0], lo4[1], mid[1], cur[2], cur[3]);
+    if (tile1) mma_16816(d1x, mid[0], hi4[0], mid[1], hi4[1], cur[2], cur[3]);
+    mma_16816(d0, lo4[0], mid[0], lo4[1], mid[1], cur[0], cur[1]);
+    if (tile1) mma_16816(d1, mid[0], hi4[0], mid[1], hi4[1], cur[0], cur[1]);
+    mma_16816(d0x, lo4[2], mid[2], lo4[3], mid[3], cur[0], cur[1]);
+    if (tile1) mma_16816(d1x, mid[2], hi4[2], mid[3], hi4[3], cur[0], cur[1]);
+  }
+  val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];
+  val[4] = d1[2] + d1x[2]; val[5] = d1[3] + d1x[3];
+  const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
+  if (r0 != 0.0f) {
+    const float inv = __fdiv_rn(1.0f, r0);
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) val[v] *= inv;
+  }
+  __syncwarp();
+}
+
+// Third formulation: the loop structure of am_mma (one A fragment per K-block used for BOTH tiles, tile 1 against
+// the B fragments of four blocks earlier) with each half of the A fragment loaded ONCE.  The blocks b, b+4, b+8, ...
+// share one register quad per split part: the rows new to block b, H(b), are written alternately to positions
+// (a0, a2) and (a1, a3) while the half that entered four blocks earlier stays where it is.  In the blocks where the
+// new rows sit in (a0, a2) the MMA sees the two row halves exchanged, so those blocks accumulate into a second set
+// of accumulators whose row halves are exchanged back when the sets are added.  The new rows arrive as four plain
+// 32-bit loads (one conflict-free wavefront each) that write their quad positions directly - an ldmatrix.x4 would
+// deliver them in four CONSECUTIVE registers and cost four moves per block.  Per K-block: 4 A loads + 4 B loads (8
+// wavefronts) + 6 MMAs; am_mma needs 12 wavefronts, am_mma_ring ~20 register moves.  The products of a lag are summed in two groups here, so results differ from am_mma in the last bits.
+// 32-bit shared-memory load the compiler may not move across the (volatile) MMAs: the unrolled loop keeps exactly
+// the prefetch distance written below instead of hoisting dozens of loads and spilling.
+__device__ __forceinline__ uint32_t am_lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
+template <int kBlocks>
+__device__ __forceinline__ void am_mma_alt(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
+  static_assert(kBlocks % 4 == 0 && kBlocks >= 12, "K-blocks come in groups of four");
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t lo_delta = 2u * static_cast<uint32_t>(geo.len);   // E_lo - E_hi (and O_lo - O_hi) in bytes
+  // H(b) register of lane (g, tq): the pair X(16 b + 64 + 8 g + 2 tq [+ 8]), a 32-bit word of the E copy; the 32
+  // lanes of a load read 32 consecutive words (conflict-free), and every load writes its quad position directly
+  const uint32_t sA = am_smem_u32(copies) + 2u * static_cast<uint32_t>(kFrontMargin + 64 + 8 * g + 2 * tq);  // + 32 b; k 8..15: + 16
+  const int boff = kFrontMargin + 2 * tq - g - (g & 1);
+  const uint32_t sB = am_smem_u32(copies) + ((g & 1) ? 4u * static_cast<uint32_t>(geo.len) : 0u) + 2u * static_cast<uint32_t>(boff);
+  // accumulators [set][tile]: set 0 = row halves in place (new rows in a1, a3), set 1 = exchanged
+  float d[2][2][4], dx[2][2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) d[a][t][c] = dx[a][t][c] = 0.0f;
+  uint32_t Qh[4][4], Ql[4][4];      // per residue class b & 3: the A fragment quads of the hi and lo parts
+  uint32_t Bf[6][4];                // B fragments of blocks b-4 .. b+1 {b0 hi, b1 hi, b0 lo, b1 lo} (static ring)
+  auto load_block = [&](int b) {    // H(b) into its quad positions, B(b) into its ring slot (b: compile-time constant)
+    const int r = b & 3;
+    const int p0 = ((b >> 2) & 1) ? 1 : 0;        // groups 0, 2, 4, ...: (a0, a2); groups 1, 3, ...: (a1, a3)
+    const uint32_t a = sA + static_cast<uint32_t>(32 * b);
+    Qh[r][p0] = am_lds32(a); Qh[r][p0 + 2] = am_lds32(a + 16u);
+    Ql[r][p0] = am_lds32(a + lo_delta); Ql[r][p0 + 2] = am_lds32(a + lo_delta + 16u);
+    const uint32_t q = sB + static_cast<uint32_t>(32 * b);
+    Bf[b % 6][0] = am_lds32(q); Bf[b % 6][1] = am_lds32(q + 16u);
+    Bf[b % 6][2] = am_lds32(q + lo_delta); Bf[b % 6][3] = am_lds32(q + lo_delta + 16u);
+  };
+  // prologue: H(-4..-1), the frame's first rows, enter at (a1, a3) - as if an "in place" group had loaded them
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint32_t a = sA - static_cast<uint32_t>(32 * (4 - r));
+    Qh[r][1] = am_lds32(a); Qh[r][3] = am_lds32(a + 16u);
+    Ql[r][1] = am_lds32(a + lo_delta); Ql[r][3] = am_lds32(a + lo_delta + 16u);
+  }
+  load_block(0);
+#pragma unroll
+  for (int b = 0; b < kBlocks; ++b) {
+    const int r = b & 3;
+    const int set = ((b >> 2) & 1) ^ 1;           // new rows in (a0, a2) -> the exchanged set
+    // one block ahead: the quad positions and the ring slot written here were last read by block b - 3 / b - 5
+    if (b + 1 < kBlocks) load_block(b + 1);
+    const uint32_t(&cur)[4] = Bf[b % 6];
+    const uint32_t(&old)[4] = Bf[(b + 2) % 6];    // block b - 4
+    mma_16816(dx[set][0], Qh[r][0], Qh[r][1], Qh[r][2], Qh[r][3], cur[2], cur[3]);
+    if (b >= 4) mma_16816(dx[set][1], Qh[r][0], Qh[r][1], Qh[r][2], Qh[r][3], old[2], old[3]);
+    mma_16816(d[set][0], Qh[r][0], Qh[r][1], Qh[r][2], Qh[r][3], cur[0], cur[1]);
+    if (b >= 4) mma_16816(d[set][1], Qh[r][0], Qh[r][1], Qh[r][2], Qh[r][3], old[0], old[1]);
+    mma_16816(dx[set][0], Ql[r][0], Ql[r][1], Ql[r][2], Ql[r][3], cur[0], cur[1]);
+    if (b >= 4) mma_16816(dx[set][1], Ql[r][0], Ql[r][1], Ql[r][2], Ql[r][3], old[0], old[1]);
+  }
+  // set 0: c0, c1 = lags base, base + 1 (rows 0..7), c2, c3 = base + 64, + 65; set 1 has the halves exchanged
+  val[0] = (d[0][0][0] + dx[0][0][0]) + (d[1][0][2] + dx[1][0][2]);
+  val[1] = (d[0][0][1] + dx[0][0][1]) + (d[1][0][3] + dx[1][0][3]);
+  val[2] = (d[0][0][2] + dx[0][0][2]) + (d[1][0][0] + dx[1][0][0]);
+  val[3] = (d[0][0][3] + dx[0][0][3]) + (d[1][0][1] + dx[1][0][1]);
+  val[4] = (d[0][1][2] + dx[0][1][2]) + (d[1][1][0] + dx[1][1][0]);     // tile 1: base + 128, + 129
+  val[5] = (d[0][1][3] + dx[0][1][3]) + (d[1][1][1] + dx[1][1][1]);
+  const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
+  if (r0 != 0.0f) {
+    const float inv = __fdiv_rn(1.0f, r0);
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) val[v] *= inv;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane, int n_lags, float thr) {
   bool small = true;
 #pragma unroll
@@ -346,8 +504,13 @@ __device__ __forceinline__ void am_bar_wait(uint64_t* bar, uint32_t parity) {
 // consumer warp runs nothing but the MMA loop (plus the cheap normalise / pair-mean / store), so the
 // tensor pipe is fed continuously while memory latency and the fp32->fp16 conversion hide behind it.
 constexpr int kAmPairs = 4;
+constexpr int kDefaultLoop = 1;   // see k_autocorr_mma: which MMA loop the exact-size kernels run by default
 
-template <int kIters, bool kExact>
+// kLoop (exact-size kernels only; NSF_AC_LOOP=legacy|ring|alt picks one at run time for A/B timing):
+//   1  am_mma       A through two ldmatrix.x4 per block, B history in registers (round 1)
+//   2  am_mma_ring  A halves loaded once into a ring, no B history; bit-identical to am_mma
+//   0  am_mma_alt   A halves loaded once into alternating quad positions, two accumulator sets
+template <int kIters, bool kExact, int kLoop = 1>
 __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables t, BatchView b,
                                                                    const float* __restrict__ y, bool reduce,
                                                                    float* __restrict__ out, int64_t out_ld,
@@ -421,12 +584,16 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
         const int64_t tf = tf0 + f;
         float val[kVals];
         am_bar_wait(full + buf, (it >> 1) & 1u);
-        am_mma(copies, geo, lane, val);
+        if constexpr (kExact && kLoop == 0) am_mma_alt<4 * kIters>(copies, geo, lane, val);
+        else if constexpr (kExact && kLoop == 2) am_mma_ring<4 * kIters>(copies, geo, lane, val);
+        else am_mma(copies, geo, lane, val);
         // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
         // rare, so the consumer refills the buffer it still owns itself
         if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
           am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
-          am_mma(copies, geo, lane, val);
+          if constexpr (kExact && kLoop == 0) am_mma_alt<4 * kIters>(copies, geo, lane, val);
+          else if constexpr (kExact && kLoop == 2) am_mma_ring<4 * kIters>(copies, geo, lane, val);
+          else am_mma(copies, geo, lane, val);
         }
         __syncwarp();
         if (lane == 0) am_bar_arrive(empty + buf);
@@ -470,8 +637,15 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
     kernel<<<static_cast<int>(grid), pairs * 64, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   };
-  if (iters == 23) return go(k_autocorr_mma<23, true>);   // 88.2 kHz: F = 1470
-  if (iters == 5) return go(k_autocorr_mma<5, true>);     // 16 kHz: F = 266
+  static const int loop = [] {
+    const char* v = std::getenv("NSF_AC_LOOP");
+    if (!v) return kDefaultLoop;
+    return v[0] == 'a' ? 0 : (v[0] == 'r' ? 2 : 1);
+  }();
+  if (iters == 23)   // 88.2 kHz: F = 1470
+    return loop == 0 ? go(k_autocorr_mma<23, true, 0>) : (loop == 2 ? go(k_autocorr_mma<23, true, 2>) : go(k_autocorr_mma<23, true, 1>));
+  if (iters == 5)    // 16 kHz: F = 266
+    return loop == 0 ? go(k_autocorr_mma<5, true, 0>) : (loop == 2 ? go(k_autocorr_mma<5, true, 2>) : go(k_autocorr_mma<5, true, 1>));
   if (iters <= 6) return go(k_autocorr_mma<6, false>);    // F <= 382   (22.05 kHz: 367)
   if (iters <= 12) return go(k_autocorr_mma<12, false>);  // F <= 766   (44.1 kHz: 735)
   if (iters <= 24) return go(k_autocorr_mma<24, false>);  // F <= 1534  (48 kHz: 800)
@@ -486,7 +660,9 @@ bool init_autocorr_mma_attributes() {
   auto set = [&](auto kernel) {
     ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess;
   };
-  set(k_autocorr_mma<23, true>); set(k_autocorr_mma<5, true>); set(k_autocorr_mma<6, false>);
+  set(k_autocorr_mma<23, true, 0>); set(k_autocorr_mma<5, true, 0>); set(k_autocorr_mma<6, false>);
+  set(k_autocorr_mma<23, true, 1>); set(k_autocorr_mma<5, true, 1>);
+  set(k_autocorr_mma<23, true, 2>); set(k_autocorr_mma<5, true, 2>);
   set(k_autocorr_mma<12, false>); set(k_autocorr_mma<24, false>); set(k_autocorr_mma<40, false>);
   set(k_autocorr_mma<66, false>);
   return ok;

@@ -10,8 +10,8 @@ arithmetic of the reference (same operation order, IEEE add/mul, no FMA contract
 ``load_data`` keeps the reference signature but builds the whole dataset in ONE pipelined device pass
 (``load_data_batched``): the folders are scanned first, every take without a feature cache is read straight
 into a page-locked int16 arena, ``nsf_extract_collect_host`` turns PCM + facial rows into augmented rows
-without the feature rows ever leaving the GPU, and the examples are float32 views of the page-locked result
-(``dataset/dataset.py:75`` casts to float32 anyway).  ``process_folder`` / ``collect_features`` remain the
+without the feature rows ever leaving the GPU, and the examples are float32 (``dataset/dataset.py:75`` casts to
+float32 anyway).  ``process_folder`` / ``collect_features`` remain the
 per-take float64 route, bit-identical to the reference's NumPy arithmetic.
 """
 import os
@@ -275,8 +275,7 @@ def load_data_batched(root_dir, sr, processed_folders, include_fast=True, includ
 
     ``dtype=np.float32`` (default, the training format): takes without a feature cache are read straight
     into page-locked int16 memory by a thread pool, go through ``nsf_extract_collect_host`` (features and
-    augmentation fused, rows never leave the device in between) and come back as float32 views of one
-    page-locked array; cached takes are augmented by one float32 ``nsf_collect_host`` call.
+    augmentation fused, rows never leave the device in between) and come back as float32 arrays; cached takes are augmented by one float32 ``nsf_collect_host`` call.
     ``dtype=np.float64``: extraction batched, augmentation through the float64 kernel - bit-identical to
     the per-folder builder.  A take shorter than 9 frames raises ``TypeError`` exactly where the
     reference does (``len(None)``, :143)."""
@@ -362,7 +361,7 @@ def load_data_batched(root_dir, sr, processed_folders, include_fast=True, includ
             off = np.zeros(len(todo) + 1, dtype=np.int64)
             np.cumsum(lens, out=off[1:])
             item = 2 if fast else 4
-            pcm_arena = _engine.PinnedBuffer(int(off[-1]) * item)
+            pcm_arena = _engine.scratch_pinned("dataset_pcm", int(off[-1]) * item)   # library-owned, reused
             pcm = pcm_arena.view(np.int16 if fast else np.float32, (int(off[-1]),))
             if fast:
                 for (_, p) in todo:
@@ -394,15 +393,16 @@ def load_data_batched(root_dir, sr, processed_folders, include_fast=True, includ
             np.cumsum([len(facial[i]) for i in order], out=f_off[1:])
             if dtype == np.float32 and augment and all(n_rows[i] and len(facial[i]) for i in order):
                 f_cols = facial[order[0]].shape[1]
-                fac_arena = _engine.PinnedBuffer(int(f_off[-1]) * f_cols * 4)
+                fac_arena = _engine.scratch_pinned("dataset_facial", int(f_off[-1]) * f_cols * 4)
                 fac = fac_arena.view(np.float32, (int(f_off[-1]), f_cols))
                 for k, i in enumerate(order):
                     fac[f_off[k]:f_off[k + 1]] = facial[i]
                 o_off = eng.collect_rows(roff, f_off, **kw)
-                out_arena = _engine.PinnedBuffer(int(o_off[-1]) * (256 + fac.shape[1]) * 4 + int(roff[-1]) * 256 * 4)
-                out_a = out_arena.view(np.float32, (int(o_off[-1]), 256))
-                out_f = out_arena.view(np.float32, (int(o_off[-1]), fac.shape[1]), offset=out_a.nbytes)
-                feats = out_arena.view(np.float32, (int(roff[-1]), 256), offset=out_a.nbytes + out_f.nbytes)
+                # results go to ordinary (pageable) arrays the caller owns: the library stages the downloads through
+                # its own page-locked arenas, which costs a host copy but not a cudaHostAlloc of ~300 MB per call
+                out_a = np.empty((int(o_off[-1]), 256), dtype=np.float32)
+                out_f = np.empty((int(o_off[-1]), f_cols), dtype=np.float32)
+                feats = np.empty((int(roff[-1]), 256), dtype=np.float32)
                 eng.extract_collect_host(pcm, off, fac, f_off, nv.PEAK_NORMALIZE, out_audio=out_a, out_facial=out_f,
                                          features_out=feats, **kw)
                 for k, i in enumerate(order):

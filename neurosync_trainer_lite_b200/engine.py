@@ -68,6 +68,19 @@ class PinnedBuffer:
         self._raw = None
 
 
+_scratch = {}
+
+
+def scratch_pinned(tag, nbytes):
+    """Grow-only page-locked scratch buffer kept for the life of the process (library-owned staging for the
+    dataset builders: cudaHostAlloc costs ~1 ms per MB, far more than filling the buffer).  The caller must be
+    done with the previous contents of ``tag`` - views handed out earlier alias the same memory."""
+    buf = _scratch.get(tag)
+    if buf is None or buf.nbytes < nbytes:
+        _scratch[tag] = buf = PinnedBuffer(int(nbytes * 1.25) + 4096)
+    return buf
+
+
 class Plan:
     """Constant tables for one (sr, F, H) geometry.  Pure host object: usable without a GPU."""
 
