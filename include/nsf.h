@@ -247,6 +247,24 @@ NSF_API nsf_status nsf_rows_host(nsf_ctx* ctx, int32_t op, int32_t dtype, const 
 NSF_API nsf_status nsf_post_host(nsf_ctx* ctx, const float* in_host, int64_t n_frames, int32_t channels,
                                  uint32_t post_flags, float* out_host);
 
+/* ---- inference-side chunker --------------------------------------------------------------------------
+ * The consumer of the feature rows at inference / validation time, process_audio_features
+ * (utils/audio/processing/audio_processing.py:50-112): `frame`-row chunks every frame - overlap rows, the last
+ * ones completed by reflection (pad_audio_chunk :14-23), decoded by the caller's model, cross-faded over `overlap`
+ * rows (blend_chunks :33-48), trimmed to n_rows and `[:, :61] /= 100` (:103).  Device-resident and stream-ordered:
+ * feature rows from nsf_extract_batch never leave the GPU between extraction and the model.
+ *   nsf_chunk_count   number of chunks the reference's while loop produces (0 for an invalid geometry)
+ *   nsf_chunk_gather  rows_dev [n_rows x cols] (row pitch ld) -> chunks_dev [n_chunks x frame x cols]
+ *   nsf_chunk_blend   decoded_dev [n_chunks x frame x out_cols] -> out_dev [n_rows x out_cols]; the first
+ *                     scale_cols columns are divided by `divisor`.  float32 arithmetic in NumPy's order (bit-identical
+ *                     to the reference given the same decoded chunks).  NSF_ERR_UNSUPPORTED when 2 * overlap > frame. */
+NSF_API int64_t nsf_chunk_count(int64_t n_rows, int32_t frame, int32_t overlap);
+NSF_API nsf_status nsf_chunk_gather(nsf_ctx* ctx, void* cuda_stream, const float* rows_dev, int64_t n_rows, int32_t cols,
+                                    int64_t ld, int32_t frame, int32_t overlap, float* chunks_dev);
+NSF_API nsf_status nsf_chunk_blend(nsf_ctx* ctx, void* cuda_stream, const float* decoded_dev, int64_t n_rows,
+                                   int32_t out_cols, int32_t frame, int32_t overlap, int32_t scale_cols, float divisor,
+                                   float* out_dev);
+
 /* ---- sample-rate conversion ------------------------------------------------------------------------
  * The resampling half of the loaders: `librosa.resample(y, orig_sr=sr, target_sr=88200)` of
  * load_and_preprocess_audio (utils/audio/load_audio.py:8-10) and the `sr=` conversion inside
@@ -263,8 +281,23 @@ NSF_API nsf_status nsf_post_host(nsf_ctx* ctx, const float* in_host, int64_t n_f
  *                       up / down / n_pre_pad / n_pre_remove (all optional) describe the polyphase
  *                       indexing  out[j] = sum_n h[(j + n_pre_remove) down - n_pre_pad - n up] x[n].
  *                       Runs without a GPU.
- *   nsf_resample_host   host PCM (float32 or int16) -> host float32 at target_sr, through the device. */
+ *   nsf_resample_host   host PCM (float32 or int16) -> host float32 at target_sr, through the device.
+ *
+ * Two filter designs share the polyphase kernel (same indexing, different taps); the context option
+ * NSF_OPT_RESAMPLE_QUALITY picks the one nsf_resample_host applies (default NSF_RESAMPLE_HQ):
+ *   NSF_RESAMPLE_POLY  the scipy.signal.resample_poly design above (Kaiser beta 5, ~60 dB; pinned to scipy);
+ *   NSF_RESAMPLE_HQ    band-limited windowed sinc, 64 zero crossings, roll-off 0.9476, Kaiser beta 14.77 (> 140 dB):
+ *                      out[m] = sum_n x[n] g((n/down - m/up) f), f = min(up, down) rolloff, the arithmetic of
+ *                      torchaudio.functional.resample(resampling_method="sinc_interp_kaiser") with those
+ *                      parameters (pinned to torchaudio).  Same class as the reference's soxr_hq: what lies above
+ *                      the input band ends below the 80 dB floor of the dB stage, so the features agree with any
+ *                      high-quality resampler up to the transition band (profiles/parity_r02.md). */
+#define NSF_RESAMPLE_POLY 0
+#define NSF_RESAMPLE_HQ 1
+#define NSF_OPT_RESAMPLE_QUALITY 1
 NSF_API int64_t nsf_resample_len(int64_t n_in, int32_t orig_sr, int32_t target_sr);
+NSF_API int64_t nsf_resample_design_q(int32_t orig_sr, int32_t target_sr, int32_t quality, double* taps, int64_t capacity,
+                                      int32_t* up, int32_t* down, int32_t* n_pre_pad, int32_t* n_pre_remove);
 NSF_API int64_t nsf_resample_design(int32_t orig_sr, int32_t target_sr, double* taps, int64_t capacity,
                                     int32_t* up, int32_t* down, int32_t* n_pre_pad, int32_t* n_pre_remove);
 NSF_API nsf_status nsf_resample_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_format, int64_t n_in,

@@ -26,6 +26,8 @@ F32, F64 = 0, 1
 TABLE_MEL, TABLE_DCT, TABLE_HANN_SYM, TABLE_HANN_PER = 0, 1, 2, 3
 ROWS_INTERP_SLOWER, ROWS_SMOOTH, ROWS_BLEND_STACK = 0, 1, 2
 OPT_EDGE_ZERO_THRESHOLD = 0
+OPT_RESAMPLE_QUALITY = 1
+RESAMPLE_POLY, RESAMPLE_HQ = 0, 1
 POST_EDGEFIX, POST_CMVN, POST_DELTAS, POST_REDUCE = 0x1, 0x2, 0x4, 0x8
 STAGE_NAMES = ("peak_normalize", "fold", "stft_gemm", "mel_db", "dct_stats", "cmvn_delta_reduce",
                "autocorr", "post")
@@ -88,8 +90,12 @@ _SIGS = {
                                         _vp]),
     "nsf_rows_host": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "nsf_post_host": (_i32, [_vp, _vp, _i64, _i32, _u32, _vp]),
+    "nsf_chunk_count": (_i64, [_i64, _i32, _i32]),
+    "nsf_chunk_gather": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _i32, _i32, _vp]),
+    "nsf_chunk_blend": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, C.c_float, _vp]),
     "nsf_resample_len": (_i64, [_i64, _i32, _i32]),
     "nsf_resample_design": (_i64, [_i32, _i32, _f64p, _i64, _i32p, _i32p, _i32p, _i32p]),
+    "nsf_resample_design_q": (_i64, [_i32, _i32, _i32, _f64p, _i64, _i32p, _i32p, _i32p, _i32p]),
     "nsf_resample_host": (_i32, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i64]),
     "nsf_launch_count": (_i64, [_vp]),
     "nsf_set_profiling": (None, [_vp, _i32]),

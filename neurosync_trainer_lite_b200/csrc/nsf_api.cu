@@ -131,9 +131,11 @@ struct PinnedArena {
 // Host pipeline: clip groups rotate over three slots (stream + arenas each), so the upload of group g+1, the
 // kernels of group g and the download of group g-1 overlap without the upload engine ever waiting for a
 // download to release its slot.  The first groups are small (the pipeline fills after a short upload instead of
-// a 96 MB one), later groups carry up to 24 Mi samples.
+// a large one), later groups carry up to 8 Mi samples: measured on C2 (r2_ab.jsonl) 8 / 16 / 24 / 32 Mi give
+// 6.5 / 7.0 / 7.1 / 7.1 ms per int16 step against a bare-copy ceiling of 6.1 ms - the tail (kernels + download of
+// the LAST group) and the bubble before the first kernels shrink with the group.
 constexpr int kSlots = 3;
-constexpr int64_t kGroupSamples = int64_t(24) << 20;       // ~96 MB of float32 PCM per in-flight group
+constexpr int64_t kGroupSamples = int64_t(8) << 20;        // ~32 MB of float32 PCM per in-flight group
 constexpr int64_t kFirstGroupSamples = int64_t(6) << 20;   // groups 0 and 1
 // NSF_GROUP_MI / NSF_FIRST_MI (Mi samples) override the two budgets for pipeline experiments
 inline int64_t env_mi(const char* name, int64_t dflt) {
@@ -189,6 +191,7 @@ struct nsf_ctx {
   int desc_next = 0;
   nsf::HostDesc hd_batch, hd_all;   // scratch of nsf_extract_batch / the host pipelines
   float edge_zero_threshold = 1e-7f;   // fix_edge_frames_autocorr(zero_threshold=1e-7)
+  int resample_quality = NSF_RESAMPLE_HQ;
   nsf::Slot slot[nsf::kSlots];
   int64_t launches = 0;
   bool profiling = false;
@@ -455,6 +458,10 @@ nsf_status nsf_ctx_set_option(nsf_ctx* ctx, int32_t option, double value) {
       if (!(value >= 0.0)) { set_error("zero_threshold must be >= 0"); return NSF_ERR_BAD_ARG; }
       ctx->edge_zero_threshold = static_cast<float>(value);
       ctx->tables.edge_thr = ctx->edge_zero_threshold;
+      return NSF_OK;
+    case NSF_OPT_RESAMPLE_QUALITY:
+      if (value != NSF_RESAMPLE_POLY && value != NSF_RESAMPLE_HQ) { set_error("unknown resample quality"); return NSF_ERR_BAD_ARG; }
+      ctx->resample_quality = static_cast<int>(value);
       return NSF_OK;
     default:
       set_error("nsf_ctx_set_option: unknown option");
@@ -893,7 +900,10 @@ nsf_status nsf_resample_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_for
   if (!ctx || !pcm_host || !out_host || n_in <= 0) { set_error("nsf_resample_host: NULL argument or empty input"); return NSF_ERR_BAD_ARG; }
   if (pcm_format != NSF_PCM_F32 && pcm_format != NSF_PCM_I16) { set_error("unknown pcm_format"); return NSF_ERR_BAD_ARG; }
   ResampleDesign d;
-  if (!design_resampler(orig_sr, target_sr, &d)) { set_error("nsf_resample_host: rates must be positive"); return NSF_ERR_BAD_ARG; }
+  if (!(ctx->resample_quality == NSF_RESAMPLE_HQ ? design_resampler_hq(orig_sr, target_sr, &d)
+                                                 : design_resampler(orig_sr, target_sr, &d))) {
+    set_error("nsf_resample_host: rates must be positive"); return NSF_ERR_BAD_ARG;
+  }
   const int64_t n_out = nsf_resample_len(n_in, orig_sr, target_sr);
   if (out_capacity < n_out) { set_error("nsf_resample_host: out_capacity < nsf_resample_len()"); return NSF_ERR_BAD_ARG; }
   NSF_CUDA(cudaSetDevice(ctx->device));
@@ -1135,6 +1145,59 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
   }
   for (auto& sl : ctx->slot)
     if (sl.stream && (st = drain_slot(&sl)) != NSF_OK) return st;
+  return NSF_OK;
+}
+
+// ---- inference-side chunker ---------------------------------------------------------------------------
+int64_t nsf_chunk_count(int64_t n_rows, int32_t frame, int32_t overlap) {
+  if (n_rows <= 0 || frame <= 0 || overlap < 0 || overlap >= frame) return 0;
+  const int64_t stride = frame - overlap;
+  return (n_rows + stride - 1) / stride;            // starts 0, stride, 2 stride, ... while start < n_rows
+}
+
+// The reference blends every new chunk into the LAST `n` rows of what it has accumulated; the kernels assume those
+// are the rows the chunk starts at, which holds whenever frame - overlap >= overlap (and in every other geometry
+// this walk accepts).  Returns false for a geometry where the reference's own bookkeeping shifts rows.
+static bool chunk_geometry_aligned(int64_t n_rows, int32_t frame, int32_t overlap) {
+  const int64_t stride = frame - overlap, n_chunks = nsf_chunk_count(n_rows, frame, overlap);
+  int64_t acc = std::min<int64_t>(frame, n_rows);
+  for (int64_t k = 1; k < n_chunks; ++k) {
+    const int64_t s = k * stride, len_k = std::min<int64_t>(frame, n_rows - s);
+    const int64_t n = std::min<int64_t>(std::min<int64_t>(overlap, acc), len_k);
+    if (acc - n != s) return false;
+    if (k + 1 < n_chunks && (k + 1) * stride < s + n) return false;   // cross-fade zones must not overlap
+    acc += len_k - n;
+  }
+  return acc == n_rows;
+}
+
+nsf_status nsf_chunk_gather(nsf_ctx* ctx, void* cuda_stream, const float* rows_dev, int64_t n_rows, int32_t cols,
+                            int64_t ld, int32_t frame, int32_t overlap, float* chunks_dev) {
+  if (!ctx || !rows_dev || !chunks_dev || cols <= 0 || ld < cols) { set_error("nsf_chunk_gather: bad argument"); return NSF_ERR_BAD_ARG; }
+  const int64_t n_chunks = nsf_chunk_count(n_rows, frame, overlap);
+  if (n_chunks <= 0) { set_error("nsf_chunk_gather: need n_rows > 0 and 0 <= overlap < frame"); return NSF_ERR_BAD_ARG; }
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  const int n = launch_chunk_gather(static_cast<cudaStream_t>(cuda_stream), rows_dev, n_rows, cols, ld, frame, overlap, n_chunks, chunks_dev);
+  if (n < 0) { set_error(cuda_msg("launch_chunk_gather", cudaGetLastError())); return NSF_ERR_CUDA; }
+  ctx->launches += n;
+  return NSF_OK;
+}
+
+nsf_status nsf_chunk_blend(nsf_ctx* ctx, void* cuda_stream, const float* decoded_dev, int64_t n_rows, int32_t out_cols,
+                           int32_t frame, int32_t overlap, int32_t scale_cols, float divisor, float* out_dev) {
+  if (!ctx || !decoded_dev || !out_dev || out_cols <= 0 || scale_cols < 0) { set_error("nsf_chunk_blend: bad argument"); return NSF_ERR_BAD_ARG; }
+  const int64_t n_chunks = nsf_chunk_count(n_rows, frame, overlap);
+  if (n_chunks <= 0) { set_error("nsf_chunk_blend: need n_rows > 0 and 0 <= overlap < frame"); return NSF_ERR_BAD_ARG; }
+  if (scale_cols > 0 && divisor == 0.0f) { set_error("nsf_chunk_blend: divisor is zero"); return NSF_ERR_BAD_ARG; }
+  if (!chunk_geometry_aligned(n_rows, frame, overlap)) {
+    set_error("nsf_chunk_blend: overlap larger than half a chunk shifts rows in the reference's bookkeeping; not implemented");
+    return NSF_ERR_UNSUPPORTED;
+  }
+  NSF_CUDA(cudaSetDevice(ctx->device));
+  const int n = launch_chunk_blend(static_cast<cudaStream_t>(cuda_stream), decoded_dev, n_rows, out_cols, frame, overlap, n_chunks,
+                                   scale_cols, divisor, out_dev);
+  if (n < 0) { set_error(cuda_msg("launch_chunk_blend", cudaGetLastError())); return NSF_ERR_CUDA; }
+  ctx->launches += n;
   return NSF_OK;
 }
 

@@ -236,6 +236,12 @@ __device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&r)[4]) {
 }
 
 // The MMA half: normalised lags of the frame currently held in `copies` into val[0..5] (see lag_of).
+// kSplitAcc: the two cross products of a tile (hi.lo, lo.hi) go to SEPARATE accumulators, so that each of the six
+// MMAs of a K-block continues its own chain and an accumulator is touched once per block.  ncu (round 2, source
+// page of the round-1 loop): 44 % of the HMMA stall samples are fixed-latency waits on the accumulator that two of
+// the six MMAs share at a distance of two or three MMAs - shorter than the HMMA latency whenever the second MMA
+// warp of the scheduler is not ready to fill the gap.
+template <bool kSplitAcc>
 __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
   const int g = lane >> 2, tq = lane & 3;
   const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
@@ -260,6 +266,7 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   // (hi.hi) and the two cross products go to separate accumulators: four independent MMA chains.
   float d0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d0x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   float d1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float d0y[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1y[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // lo.hi products when kSplitAcc
   // B fragments of the last 4 K-blocks: two register sets used alternately (a group of four blocks
   // loads into one set while tile 1 reads the other), so no fragment is ever copied
   uint32_t bp[4][4], bq[4][4];                // [slot][b0h, b1h, b0l, b1l]
@@ -284,8 +291,8 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
       mma_16816(d1x, ah[0], ah[1], ah[2], ah[3], old[q][2], old[q][3]);
       mma_16816(d0, ah[0], ah[1], ah[2], ah[3], cur[q][0], cur[q][1]);
       mma_16816(d1, ah[0], ah[1], ah[2], ah[3], old[q][0], old[q][1]);
-      mma_16816(d0x, al[0], al[1], al[2], al[3], cur[q][0], cur[q][1]);
-      mma_16816(d1x, al[0], al[1], al[2], al[3], old[q][0], old[q][1]);
+      mma_16816(kSplitAcc ? d0y : d0x, al[0], al[1], al[2], al[3], cur[q][0], cur[q][1]);
+      mma_16816(kSplitAcc ? d1y : d1x, al[0], al[1], al[2], al[3], old[q][0], old[q][1]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { ah[i] = nh[i]; al[i] = nl[i]; }
     }
@@ -300,6 +307,10 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   }
   if (left) group(pb_h, pb_l, bp, bq);   // nblk4 is a multiple of 4
   // tile 0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  tile 1: c2,c3 = base+128, base+129.
+  if (kSplitAcc) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { d0x[c] += d0y[c]; d1x[c] += d1y[c]; }
+  }
   val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];
   val[4] = d1[2] + d1x[2]; val[5] = d1[3] + d1x[3];
   const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
@@ -504,12 +515,14 @@ __device__ __forceinline__ void am_bar_wait(uint64_t* bar, uint32_t parity) {
 // consumer warp runs nothing but the MMA loop (plus the cheap normalise / pair-mean / store), so the
 // tensor pipe is fed continuously while memory latency and the fp32->fp16 conversion hide behind it.
 constexpr int kAmPairs = 4;
-constexpr int kDefaultLoop = 1;   // see k_autocorr_mma: which MMA loop the exact-size kernels run by default
+constexpr int kDefaultLoop = 1;
+constexpr bool kDefaultSym = true;    // which kernel runs by default for the exact-size frames (see k_autocorr_sym)   // see k_autocorr_mma: which MMA loop the exact-size kernels run by default
 
 // kLoop (exact-size kernels only; NSF_AC_LOOP=legacy|ring|alt picks one at run time for A/B timing):
 //   1  am_mma       A through two ldmatrix.x4 per block, B history in registers (round 1)
 //   2  am_mma_ring  A halves loaded once into a ring, no B history; bit-identical to am_mma
 //   0  am_mma_alt   A halves loaded once into alternating quad positions, two accumulator sets
+//   3  am_mma<true> the round-1 loop with one accumulator per MMA of a K-block (six independent chains)
 template <int kIters, bool kExact, int kLoop = 1>
 __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables t, BatchView b,
                                                                    const float* __restrict__ y, bool reduce,
@@ -586,14 +599,14 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
         am_bar_wait(full + buf, (it >> 1) & 1u);
         if constexpr (kExact && kLoop == 0) am_mma_alt<4 * kIters>(copies, geo, lane, val);
         else if constexpr (kExact && kLoop == 2) am_mma_ring<4 * kIters>(copies, geo, lane, val);
-        else am_mma(copies, geo, lane, val);
+        else am_mma<kLoop == 3>(copies, geo, lane, val);
         // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
         // rare, so the consumer refills the buffer it still owns itself
         if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
           am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
           if constexpr (kExact && kLoop == 0) am_mma_alt<4 * kIters>(copies, geo, lane, val);
           else if constexpr (kExact && kLoop == 2) am_mma_ring<4 * kIters>(copies, geo, lane, val);
-          else am_mma(copies, geo, lane, val);
+          else am_mma<kLoop == 3>(copies, geo, lane, val);
         }
         __syncwarp();
         if (lane == 0) am_bar_arrive(empty + buf);
@@ -609,6 +622,97 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Symmetric kernel: every warp stages AND multiplies its own frames (one frame buffer per warp, no mbarriers).
+// The warp-specialised kernel above keeps two MMA warps per scheduler busy and two producer warps idle two thirds of
+// the time (ncu, round 2: 25 % of all stall samples are producers spinning on `empty`), and whenever both MMA warps
+// of a scheduler wait for a fragment or a hand-off at the same moment the tensor pipe idles (67 % active).  Here the
+// same sixteen warps per SM all issue MMAs, each in its own phase of the stage / multiply cycle, so on average
+// two to three warps per scheduler have MMAs ready while the others convert their next frame.  Same shared-memory
+// footprint (sixteen frame buffers per SM), same registers, same arithmetic in the same order: bit-identical rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSymWarps = 8;       // per block, two blocks per SM
+
+template <int kIters, bool kExact>
+__global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables t, BatchView b,
+                                                                    const float* __restrict__ y, bool reduce,
+                                                                    float* __restrict__ out, int64_t out_ld, int col0) {
+  extern __shared__ __align__(16) __half s_am[];
+  const AmGeom geo = am_geom(t.F);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = static_cast<int>(blockDim.x >> 5);
+  __half* copies = s_am + static_cast<size_t>(warp) * 4 * geo.len;
+  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(n_warps) * 4 * geo.len);
+  const int n_it = (t.F / 2 + 1 + 31) / 32;
+  for (int n = threadIdx.x; n < 64 * n_it; n += blockDim.x) hann[n] = n < t.F ? __ldg(t.hann_sym + n) : 0.0f;
+  // zero once: the margins are never written again, the frame region is rewritten per frame
+  for (int i = lane; i < 4 * geo.len / 2; i += 32) reinterpret_cast<uint32_t*>(copies)[i] = 0u;
+  __syncthreads();
+  const int64_t n_warps_total = static_cast<int64_t>(gridDim.x) * n_warps;
+  const int64_t chunk = (b.total_rows + n_warps_total - 1) / n_warps_total;
+  const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * n_warps + warp) * chunk;
+  const int64_t r_end = min(r_begin + chunk, b.total_rows);
+  int64_t base = 0, len = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
+  for (int64_t r = r_begin; r < r_end; ++r) {
+    if (r >= clip_row_end) {
+      const int clip = find_segment(b.row_off, b.n_clips, r);
+      base = __ldg(b.clip_off + clip);
+      len = __ldg(b.clip_off + clip + 1) - base;
+      T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
+      clip_row0 = __ldg(b.row_off + clip);
+      clip_row_end = __ldg(b.row_off + clip + 1);
+    }
+    const int64_t lr = r - clip_row0;
+    const int64_t tf0 = reduce ? 2 * lr : lr;
+    const int n_frames = (reduce && tf0 + 1 < T) ? 2 : 1;   // odd T: the last row passes through
+    float acc[kVals];
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
+    for (int f = 0; f < n_frames; ++f) {
+      const int64_t tf = tf0 + f;
+      const AmSrc src = am_src(t, b, y, base, len, tf, n_it);
+      if (src.fast) {
+        float v0[kIters], v1[kIters];
+        am_issue_fast<kIters, kExact>(src.clip + src.first, n_it, lane, v0, v1);
+        am_process<kIters, kExact>(t, hann, n_it, v0, v1, copies, geo, lane, nullptr);
+      } else {
+        am_fill_simple(t, hann, src, copies, geo, lane);
+      }                                                   // both end with __syncwarp
+      float val[kVals];
+      am_mma<false>(copies, geo, lane, val);              // ends with __syncwarp: the buffer may be rewritten
+      if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
+        am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
+        am_mma<false>(copies, geo, lane, val);
+      }
+#pragma unroll
+      for (int v = 0; v < kVals; ++v) acc[v] += val[v];
+    }
+    const float wgt = n_frames == 2 ? 0.5f : 1.0f;
+    float* o = out + r * out_ld + col0;
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) {
+      const int lag = lag_of(lane, v);
+      if (lag >= 1 && lag <= t.n_lags) o[lag - 1] = acc[v] * wgt;
+    }
+  }
+}
+
+// launch of the symmetric kernel; returns 0 when it does not apply (frame buffers too large), -1 on error
+template <typename Launch>
+int am_launch_sym(const BatchView& b, const AmGeom& geo, size_t hann_bytes, Launch&& launch) {
+  int warps = kSymWarps;
+  size_t smem = 0;
+  for (; warps >= 2; warps -= 2) {
+    smem = static_cast<size_t>(warps) * 4 * geo.len * sizeof(__half) + hann_bytes;
+    if (smem <= 110 * 1024) break;            // two blocks per SM
+  }
+  if (warps < 2) return 0;
+  int64_t grid = (b.total_rows + warps - 1) / warps;
+  if (grid > static_cast<int64_t>(kSmCount) * 2) grid = static_cast<int64_t>(kSmCount) * 2;
+  if (grid < 1) grid = 1;
+  return launch(static_cast<int>(grid), warps * 32, smem);
 }
 
 }  // namespace
@@ -633,6 +737,19 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   int64_t grid = (b.total_rows + pairs - 1) / pairs;
   if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
   if (grid < 1) grid = 1;
+  // NSF_AC_KERNEL=pairs|sym picks the warp-specialised or the symmetric kernel (A/B timing; same results)
+  static const bool use_sym = [] {
+    const char* v = std::getenv("NSF_AC_KERNEL");
+    return v ? v[0] == 's' : kDefaultSym;
+  }();
+  if (use_sym && (iters == 23 || iters == 5)) {
+    const int rc = am_launch_sym(b, geo, hann_bytes, [&](int g, int threads, size_t bytes) {
+      if (iters == 23) k_autocorr_sym<23, true><<<g, threads, bytes, s>>>(t, b, y, reduce, out, out_ld, col0);
+      else k_autocorr_sym<5, true><<<g, threads, bytes, s>>>(t, b, y, reduce, out, out_ld, col0);
+      return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    });
+    if (rc != 0) return rc;
+  }
   auto go = [&](auto kernel) {
     kernel<<<static_cast<int>(grid), pairs * 64, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -640,12 +757,14 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   static const int loop = [] {
     const char* v = std::getenv("NSF_AC_LOOP");
     if (!v) return kDefaultLoop;
-    return v[0] == 'a' ? 0 : (v[0] == 'r' ? 2 : 1);
+    return v[0] == 'a' ? 0 : (v[0] == 'r' ? 2 : (v[0] == 's' ? 3 : 1));      // alt | ring | split | legacy
   }();
   if (iters == 23)   // 88.2 kHz: F = 1470
-    return loop == 0 ? go(k_autocorr_mma<23, true, 0>) : (loop == 2 ? go(k_autocorr_mma<23, true, 2>) : go(k_autocorr_mma<23, true, 1>));
+    return loop == 0 ? go(k_autocorr_mma<23, true, 0>) : loop == 2 ? go(k_autocorr_mma<23, true, 2>)
+         : loop == 3 ? go(k_autocorr_mma<23, true, 3>) : go(k_autocorr_mma<23, true, 1>);
   if (iters == 5)    // 16 kHz: F = 266
-    return loop == 0 ? go(k_autocorr_mma<5, true, 0>) : (loop == 2 ? go(k_autocorr_mma<5, true, 2>) : go(k_autocorr_mma<5, true, 1>));
+    return loop == 0 ? go(k_autocorr_mma<5, true, 0>) : loop == 2 ? go(k_autocorr_mma<5, true, 2>)
+         : loop == 3 ? go(k_autocorr_mma<5, true, 3>) : go(k_autocorr_mma<5, true, 1>);
   if (iters <= 6) return go(k_autocorr_mma<6, false>);    // F <= 382   (22.05 kHz: 367)
   if (iters <= 12) return go(k_autocorr_mma<12, false>);  // F <= 766   (44.1 kHz: 735)
   if (iters <= 24) return go(k_autocorr_mma<24, false>);  // F <= 1534  (48 kHz: 800)
@@ -663,6 +782,8 @@ bool init_autocorr_mma_attributes() {
   set(k_autocorr_mma<23, true, 0>); set(k_autocorr_mma<5, true, 0>); set(k_autocorr_mma<6, false>);
   set(k_autocorr_mma<23, true, 1>); set(k_autocorr_mma<5, true, 1>);
   set(k_autocorr_mma<23, true, 2>); set(k_autocorr_mma<5, true, 2>);
+  set(k_autocorr_mma<23, true, 3>); set(k_autocorr_mma<5, true, 3>);
+  set(k_autocorr_sym<23, true>); set(k_autocorr_sym<5, true>);
   set(k_autocorr_mma<12, false>); set(k_autocorr_mma<24, false>); set(k_autocorr_mma<40, false>);
   set(k_autocorr_mma<66, false>);
   return ok;

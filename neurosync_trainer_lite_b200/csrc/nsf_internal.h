@@ -54,7 +54,8 @@ struct ResampleDesign {
   int up = 1, down = 1, half_len = 0, n_pre_pad = 0, n_pre_remove = 0;
   std::vector<double> h;   // 2 half_len + 1 taps, scaled by `up`
 };
-bool design_resampler(int orig_sr, int target_sr, ResampleDesign* d);
+bool design_resampler(int orig_sr, int target_sr, ResampleDesign* d);      // NSF_RESAMPLE_POLY
+bool design_resampler_hq(int orig_sr, int target_sr, ResampleDesign* d);   // NSF_RESAMPLE_HQ
 nsf_status build_plan(int sr, int F, int H, int n_mfcc, int n_mels, int n_lags, Plan* plan);
 
 // Python-style floor division for the guard (extract_features.py:16)

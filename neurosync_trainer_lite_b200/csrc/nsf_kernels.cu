@@ -1232,6 +1232,69 @@ __global__ void __launch_bounds__(256) k_edge_fix(float* __restrict__ d, int64_t
   }
 }
 
+// ---- inference-side chunker (utils/audio/processing/audio_processing.py:14-23, 33-48, 50-112) ---------------
+// Chunk k covers feature rows [k stride, k stride + frame), stride = frame - overlap; a chunk that runs past the
+// last row is completed with np.pad(..., mode='reflect') of ITS OWN rows (period 2 m - 2 for m valid rows, a single
+// row repeats).  One thread per (chunk row, float4 of columns): pure data movement.
+__global__ void __launch_bounds__(256) k_chunk_gather(const float* __restrict__ rows, int64_t n_rows, int cols, int64_t ld,
+                                                      int frame, int stride, int64_t n_chunks, float* __restrict__ out) {
+  const int64_t total = n_chunks * frame * cols;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(e % cols);
+    const int64_t cr = e / cols;
+    const int j = static_cast<int>(cr % frame);
+    const int64_t k = cr / frame;
+    const int64_t s = k * stride;
+    const int64_t m = min(static_cast<int64_t>(frame), n_rows - s);     // valid rows of this chunk (>= 1)
+    int64_t idx = j;
+    if (idx >= m) {
+      if (m == 1) idx = 0;
+      else {
+        const int64_t period = 2 * m - 2;
+        idx %= period;
+        if (idx >= m) idx = period - idx;
+      }
+    }
+    out[e] = __ldg(rows + (s + idx) * ld + c);
+  }
+}
+
+// Output row r of process_audio_features: the decoded rows of the chunks that cover r, folded in chunk order with
+// blend_chunks' cross-fade  (1 - i/n) * accumulated + (i/n) * chunk[i]  (the Python-float weights rounded to float32
+// first, separate multiply and add - NumPy's arithmetic), then `[:, :scale_cols] /= divisor`.
+__global__ void __launch_bounds__(256) k_chunk_blend(const float* __restrict__ dec, int64_t n_rows, int cols, int frame,
+                                                     int stride, int overlap, int64_t n_chunks, int scale_cols,
+                                                     float divisor, float* __restrict__ out) {
+  const int64_t total = n_rows * cols;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(e % cols);
+    const int64_t r = e / cols;
+    int64_t k_hi = r / stride;
+    if (k_hi > n_chunks - 1) k_hi = n_chunks - 1;
+    int64_t k_lo = r - frame + 1 <= 0 ? 0 : (r - frame + 1 + stride - 1) / stride;
+    float v = __ldg(dec + (k_lo * frame + (r - k_lo * stride)) * cols + c);
+    for (int64_t k = k_lo + 1; k <= k_hi; ++k) {
+      const int64_t s = k * stride;
+      const int64_t len_k = min(static_cast<int64_t>(frame), n_rows - s);
+      const int64_t l_prev = min(n_rows, s - stride + frame);           // rows accumulated before chunk k
+      const int64_t n = min(min(static_cast<int64_t>(overlap), l_prev), len_k);
+      const int64_t i = r - s;                                          // l_prev - n == s (checked on the host)
+      const float x = __ldg(dec + (k * frame + i) * cols + c);
+      if (i < n) {
+        const double alpha = static_cast<double>(i) / static_cast<double>(n);
+        const float w1 = static_cast<float>(1.0 - alpha), w2 = static_cast<float>(alpha);
+        v = __fadd_rn(__fmul_rn(w1, v), __fmul_rn(w2, x));
+      } else {
+        v = x;
+      }
+    }
+    if (c < scale_cols) v = __fdiv_rn(v, divisor);
+    out[e] = v;
+  }
+}
+
 int grid_for(int64_t items, int per_block, int max_blocks) {
   int64_t g = (items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -1433,6 +1496,22 @@ int launch_col_stats(cudaStream_t s, const float* in, int64_t T, int C, double* 
 
 int launch_edge_fix(cudaStream_t s, float* data, int64_t T, int C, float zero_threshold) {
   k_edge_fix<<<1, 256, 0, s>>>(data, T, C, zero_threshold);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_chunk_gather(cudaStream_t s, const float* rows, int64_t n_rows, int cols, int64_t ld, int frame, int overlap,
+                        int64_t n_chunks, float* out) {
+  const int grid = grid_for(n_chunks * frame * cols, 256, kSmCount * 8);
+  k_chunk_gather<<<grid, 256, 0, s>>>(rows, n_rows, cols, ld, frame, frame - overlap, n_chunks, out);
+  NSF_CHECK_LAUNCH();
+  return 1;
+}
+
+int launch_chunk_blend(cudaStream_t s, const float* decoded, int64_t n_rows, int cols, int frame, int overlap,
+                       int64_t n_chunks, int scale_cols, float divisor, float* out) {
+  const int grid = grid_for(n_rows * cols, 256, kSmCount * 8);
+  k_chunk_blend<<<grid, 256, 0, s>>>(decoded, n_rows, cols, frame, frame - overlap, overlap, n_chunks, scale_cols, divisor, out);
   NSF_CHECK_LAUNCH();
   return 1;
 }

@@ -111,6 +111,13 @@ int launch_resample(cudaStream_t s, const void* pcm, int pcm_format, int64_t n_i
 int launch_col_stats(cudaStream_t s, const float* in, int64_t T, int C, double* sum, double* sumsq);
 int launch_edge_fix(cudaStream_t s, float* data, int64_t T, int C, float zero_threshold);
 
+// inference-side chunker: chunks [n_chunks][frame][cols] out of feature rows (reflect-completed tail), and the
+// cross-faded reassembly of the decoded chunks [n_chunks][frame][cols] into [n_rows][cols]
+int launch_chunk_gather(cudaStream_t s, const float* rows, int64_t n_rows, int cols, int64_t ld, int frame, int overlap,
+                        int64_t n_chunks, float* out);
+int launch_chunk_blend(cudaStream_t s, const float* decoded, int64_t n_rows, int cols, int frame, int overlap,
+                       int64_t n_chunks, int scale_cols, float divisor, float* out);
+
 // One-time (per device) cudaFuncSetAttribute calls of each translation unit; nsf_ctx_create runs them so that no
 // launch path touches function attributes.
 bool init_kernel_attributes();        // nsf_kernels.cu

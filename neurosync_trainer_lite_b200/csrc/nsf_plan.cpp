@@ -268,6 +268,40 @@ double bessel_i0(double x) {
 // scipy.signal.resample_poly(x, up, down): h = up * firwin(2 half_len + 1, 1/max(up,down), window=('kaiser', 5.0)),
 // half_len = 10 max(up, down); h is front-padded with n_pre_pad = down - half_len % down zeros so that the
 // output sample j is upfirdn output j + n_pre_remove, n_pre_remove = (half_len + n_pre_pad) / down.
+//
+// quality NSF_RESAMPLE_HQ (what the loaders use): the band-limited windowed-sinc interpolator with the "kaiser_best"
+// parameters - 64 zero crossings, roll-off 0.9475937167399596, Kaiser beta 14.769656459379492 (stop band below
+// -140 dB) - evaluated exactly like torchaudio.functional.resample(..., resampling_method="sinc_interp_kaiser"):
+//     out[m] = sum_n x[n] g((n / down - m / up) f),  f = min(up, down) * rolloff,
+//     g(t) = (f / down) sinc(t) I0(beta sqrt(1 - (t / 64)^2)) / I0(beta)   for |t| <= 64, else 0.
+// The reference resamples with soxr_hq (not reproducible here); this design shares its class - linear phase, pass
+// band to ~0.91-0.95 of the lower Nyquist, > 120 dB rejection - so what lies above the input's band ends far
+// below the 80 dB floor of the dB stage, which the 60 dB Kaiser(5) design of scipy.signal.resample_poly does not.
+bool design_resampler_hq(int orig_sr, int target_sr, ResampleDesign* d) {
+  if (orig_sr <= 0 || target_sr <= 0) return false;
+  const int g = gcd_int(target_sr, orig_sr);
+  d->up = target_sr / g;
+  d->down = orig_sr / g;
+  const double width = 64.0, rolloff = 0.9475937167399596, beta = 14.769656459379492;
+  const double pi = 3.14159265358979323846264338327950288;
+  const double f = (d->up < d->down ? d->up : d->down) * rolloff;
+  const double per_tap = f / (static_cast<double>(d->up) * d->down);     // |t| of the tap at distance 1
+  d->half_len = static_cast<int>(std::floor(width / per_tap));
+  const int n = 2 * d->half_len + 1;
+  d->h.assign(n, 0.0);
+  const double i0b = bessel_i0(beta), scale = f / d->down;
+  for (int i = 0; i < n; ++i) {
+    const double t = (i - d->half_len) * per_tap;
+    const double r = t / width;
+    const double win = bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / i0b;
+    const double arg = pi * t;
+    d->h[i] = scale * (t == 0.0 ? 1.0 : std::sin(arg) / arg) * win;
+  }
+  d->n_pre_pad = d->down - d->half_len % d->down;
+  d->n_pre_remove = (d->half_len + d->n_pre_pad) / d->down;
+  return true;
+}
+
 bool design_resampler(int orig_sr, int target_sr, ResampleDesign* d) {
   if (orig_sr <= 0 || target_sr <= 0) return false;
   const int g = gcd_int(target_sr, orig_sr);
@@ -447,8 +481,16 @@ int64_t nsf_resample_len(int64_t n_in, int32_t orig_sr, int32_t target_sr) {
 
 int64_t nsf_resample_design(int32_t orig_sr, int32_t target_sr, double* taps, int64_t capacity, int32_t* up,
                             int32_t* down, int32_t* n_pre_pad, int32_t* n_pre_remove) {
+  return nsf_resample_design_q(orig_sr, target_sr, NSF_RESAMPLE_POLY, taps, capacity, up, down, n_pre_pad, n_pre_remove);
+}
+
+int64_t nsf_resample_design_q(int32_t orig_sr, int32_t target_sr, int32_t quality, double* taps, int64_t capacity,
+                              int32_t* up, int32_t* down, int32_t* n_pre_pad, int32_t* n_pre_remove) {
   nsf::ResampleDesign d;
-  if (!nsf::design_resampler(orig_sr, target_sr, &d)) { nsf::set_error("nsf_resample_design: rates must be positive"); return 0; }
+  if (quality != NSF_RESAMPLE_POLY && quality != NSF_RESAMPLE_HQ) { nsf::set_error("nsf_resample_design_q: unknown quality"); return 0; }
+  const bool ok = quality == NSF_RESAMPLE_HQ ? nsf::design_resampler_hq(orig_sr, target_sr, &d)
+                                             : nsf::design_resampler(orig_sr, target_sr, &d);
+  if (!ok) { nsf::set_error("nsf_resample_design: rates must be positive"); return 0; }
   if (up) *up = d.up;
   if (down) *down = d.down;
   if (n_pre_pad) *n_pre_pad = d.n_pre_pad;

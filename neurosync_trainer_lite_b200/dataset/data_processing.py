@@ -255,7 +255,21 @@ def _read_into(path, offset, dst):
 
 
 def _facial_rows(path, dtype):
-    return np.ascontiguousarray(pd.read_csv(path).drop(columns=COLUMNS_TO_DROP).values, dtype=dtype)   # :123
+    """The facial CSV minus Timecode / BlendshapeCount (:123).  float64: pandas' default parser, value for value
+    what the reference reads.  float32 (training format): Arrow's multi-threaded reader, 4x faster per file and
+    free of the GIL - its correctly rounded float64 values differ from pandas' fast parser by at most one ulp,
+    which the cast to float32 absorbs."""
+    if dtype == np.float32:
+        try:
+            import pyarrow.csv as pacsv
+            table = pacsv.read_csv(path).drop_columns(COLUMNS_TO_DROP)
+            out = np.empty((table.num_rows, table.num_columns), dtype=np.float32)
+            for j, col in enumerate(table.columns):
+                out[:, j] = col.to_numpy()
+            return out
+        except Exception:      # noqa: BLE001 - anything Arrow cannot type as numbers goes the reference's way
+            pass
+    return np.ascontiguousarray(pd.read_csv(path).drop(columns=COLUMNS_TO_DROP).values, dtype=dtype)
 
 
 last_timing = {}     # phase -> seconds of the most recent load_data_batched call (bench.py reports it)
@@ -339,7 +353,7 @@ def load_data_batched(root_dir, sr, processed_folders, include_fast=True, includ
                 todo.append((i, audio_path))
         todo_set = {j for j, _ in todo}
         keep = [i for i in mine if i in cached or i in todo_set]
-        facial_jobs = {i: pool.submit(_facial_rows, takes[i][4], dtype) for i in keep}
+        facial_jobs = {}
 
         # ---- PCM of the takes to extract: mono PCM16 files at 88.2 kHz are read straight into page-locked
         # int16 memory (2 bytes per sample over PCIe); anything else is decoded / resampled to float32 ----------
@@ -366,7 +380,10 @@ def load_data_batched(root_dir, sr, processed_folders, include_fast=True, includ
             if fast:
                 for (_, p) in todo:
                     print(f"Loaded audio file '{p}' with sample rate {REFERENCE_RATE}")
-                list(pool.map(lambda k: _read_into(todo[k][1], info[k][0], pcm[off[k]:off[k + 1]]), range(len(todo))))
+                reads = [pool.submit(_read_into, todo[k][1], info[k][0], pcm[off[k]:off[k + 1]]) for k in range(len(todo))]
+                facial_jobs = {i: pool.submit(_facial_rows, takes[i][4], dtype) for i in keep}   # queued behind the reads
+                for r in reads:
+                    r.result()
             else:
                 for k, d in enumerate(decoded):
                     pcm[off[k]:off[k + 1]] = d
@@ -376,6 +393,9 @@ def load_data_batched(root_dir, sr, processed_folders, include_fast=True, includ
                 n_rows[i] = int(roff[k + 1] - roff[k])
         timing["read_audio"] = time.perf_counter() - t0
         t0 = time.perf_counter()
+        for i in keep:
+            if i not in facial_jobs:
+                facial_jobs[i] = pool.submit(_facial_rows, takes[i][4], dtype)
         facial = {i: j.result() for i, j in facial_jobs.items()}
         cached = {i: j.result() for i, j in cached.items()}
         timing["facial_csv_wait"] = time.perf_counter() - t0

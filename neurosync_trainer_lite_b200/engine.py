@@ -220,10 +220,14 @@ class Engine:
                                                nv.ptr(y), None))
         return y
 
-    def resample_host(self, pcm, orig_sr, target_sr):
+    def resample_host(self, pcm, orig_sr, target_sr, quality="hq"):
         """``librosa.resample(y, orig_sr=, target_sr=)`` stand-in on the device (load_audio.py:8-10):
-        rational polyphase filter, scipy.signal.resample_poly arithmetic (see include/nsf.h) ->
-        float32 host array of ``nsf_resample_len`` samples."""
+        rational polyphase filter -> float32 host array of ``nsf_resample_len`` samples.  ``quality``:
+        "hq" = band-limited windowed sinc (64 zero crossings, Kaiser beta 14.77; torchaudio's
+        sinc_interp_kaiser arithmetic, the class of the reference's soxr_hq), "poly" = the
+        scipy.signal.resample_poly design (see include/nsf.h)."""
+        q = {"hq": nv.RESAMPLE_HQ, "poly": nv.RESAMPLE_POLY}[quality]
+        nv.check(nv.lib.nsf_ctx_set_option(self.handle, nv.OPT_RESAMPLE_QUALITY, float(q)))
         pcm = np.ascontiguousarray(pcm)
         fmt = self._pcm_format(pcm)
         n_out = int(nv.lib.nsf_resample_len(len(pcm), int(orig_sr), int(target_sr)))

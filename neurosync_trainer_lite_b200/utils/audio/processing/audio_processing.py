@@ -12,9 +12,15 @@ Same names, arguments and results as the reference.  Two things differ in *how* 
 * the cross-fade is one broadcast expression per chunk boundary instead of a Python loop over rows
   (same float32 arithmetic: ``(1 - i/n) * a + (i/n) * b``).
 
-This is host orchestration around a user-supplied model: there is no kernel here and nothing for the
-C ABI to replace; the feature rows themselves come from ``extract_audio_features``.
+On a CUDA device the chunker is device-resident: the feature rows - a CUDA tensor
+straight from ``Engine.extract_device``, or host rows uploaded once - are cut into the ``[n_chunks, frame, 256]``
+batch by ``nsf_chunk_gather`` (reflect-completed tail included), go through the model as one batch, and
+``nsf_chunk_blend`` reassembles the decoded chunks with the reference's cross-fade arithmetic and the final
+``[:, :61] /= 100``; one device-to-host copy at the end (none with ``return_tensor=True``).  With the model on the
+CPU the NumPy route below runs, which chunk by chunk is bit-identical to the reference module.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -71,8 +77,59 @@ def blend_chunks(chunk1, chunk2, overlap):
     return np.vstack((blended_chunk, chunk2[actual_overlap:]))
 
 
+def process_audio_features_device(audio_features, model, device, config, return_tensor=False, stream=None):
+    """reference :50-112 with every row-wise step on the GPU (``device`` must be a CUDA device).
+
+    ``audio_features``: ``(num_frames, features)`` float rows - a CUDA tensor (e.g. the output of
+    ``Engine.extract_device``; not copied), a CPU tensor or a NumPy array (uploaded once).  Returns the
+    ``(num_frames, out)`` float32 result as a NumPy array, or as a CUDA tensor with ``return_tensor=True``."""
+    from .... import _native as nv
+    from .... import engine as _engine
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError("process_audio_features_device needs a CUDA device")
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    dev = torch.device("cuda", index)
+    frame_length = int(config['frame_size'])
+    overlap = int(config.get('overlap', 16))
+    rows = torch.as_tensor(audio_features)
+    rows = rows.to(device=dev, dtype=torch.float32)
+    if rows.dim() != 2 or rows.stride(1) != 1:
+        rows = rows.contiguous()
+    num_frames, num_features = rows.shape
+    n_chunks = int(nv.lib.nsf_chunk_count(num_frames, frame_length, overlap))
+    if n_chunks <= 0:
+        raise ValueError("need at least one feature row and 0 <= overlap < frame_size")
+    f_len, h_len = _engine.frame_params(88200)
+    eng = _engine.get_engine(88200, f_len, h_len, device=index)       # any context of that device will do
+    s = torch.cuda.current_stream(dev) if stream is None else stream
+    model.eval()
+    with torch.cuda.stream(s), torch.no_grad():
+        chunks = torch.empty((n_chunks, frame_length, num_features), dtype=torch.float32, device=dev)
+        nv.check(nv.lib.nsf_chunk_gather(eng.handle, C.c_void_p(s.cuda_stream), C.c_void_p(rows.data_ptr()), num_frames,
+                                         num_features, rows.stride(0), frame_length, overlap,
+                                         C.c_void_p(chunks.data_ptr())))
+        decoded = model.decoder(model.encoder(chunks)).to(torch.float32).contiguous()
+        out_cols = decoded.shape[-1]
+        out = torch.empty((num_frames, out_cols), dtype=torch.float32, device=dev)
+        nv.check(nv.lib.nsf_chunk_blend(eng.handle, C.c_void_p(s.cuda_stream), C.c_void_p(decoded.data_ptr()), num_frames,
+                                        out_cols, frame_length, overlap, min(61, out_cols), C.c_float(100.0),
+                                        C.c_void_p(out.data_ptr())))
+    if return_tensor:
+        return out
+    s.synchronize()
+    return out.cpu().numpy()
+
+
 def process_audio_features(audio_features, model, device, config, batched=True):
-    """reference :50-112.  ``audio_features``: ``(num_frames, 256)`` rows of ``extract_audio_features``."""
+    """reference :50-112.  ``audio_features``: ``(num_frames, 256)`` rows of ``extract_audio_features``.
+
+    On a CUDA ``device`` (and ``batched=True``) the device-resident route above runs; otherwise the host route
+    below, which with ``batched=False`` decodes chunk by chunk exactly like the reference."""
+    if batched and torch.device(device).type == "cuda":
+        return process_audio_features_device(audio_features, model, device, config)
+    if isinstance(audio_features, torch.Tensor):
+        audio_features = audio_features.detach().cpu().numpy()
     frame_length = config['frame_size']
     overlap = config.get('overlap', 16)
     num_features = audio_features.shape[1]

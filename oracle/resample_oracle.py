@@ -36,10 +36,35 @@ def design(orig_sr, target_sr):
     return up, down, half_len, n_pre_pad, (half_len + n_pre_pad) // down, h
 
 
-def resample(x, orig_sr, target_sr):
+HQ_WIDTH, HQ_ROLLOFF, HQ_BETA = 64.0, 0.9475937167399596, 14.769656459379492     # the "kaiser_best" parameters
+
+
+def design_hq(orig_sr, target_sr):
+    """The high-quality design (what the loaders use): band-limited windowed sinc
+
+        out[m] = sum_n x[n] g((n / down - m / up) f),  f = min(up, down) * rolloff,
+        g(t) = (f / down) sinc(t) I0(beta sqrt(1 - (t / 64)^2)) / I0(beta)  for |t| <= 64, else 0
+
+    i.e. torchaudio.functional.resample(..., lowpass_filter_width=64, rolloff=HQ_ROLLOFF,
+    resampling_method="sinc_interp_kaiser", beta=HQ_BETA), expressed as a symmetric FIR on the up*down grid
+    so that the polyphase indexing of ``resample`` applies unchanged.  ``tests/test_resample.py`` pins it to
+    torchaudio itself."""
+    g = gcd(int(orig_sr), int(target_sr))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    f = min(up, down) * HQ_ROLLOFF
+    per_tap = f / (float(up) * down)
+    half_len = int(np.floor(HQ_WIDTH / per_tap))
+    t = (np.arange(2 * half_len + 1, dtype=np.float64) - half_len) * per_tap
+    win = np.i0(HQ_BETA * np.sqrt(np.maximum(0.0, 1.0 - (t / HQ_WIDTH) ** 2))) / np.i0(HQ_BETA)
+    h = (f / down) * np.sinc(t) * win
+    n_pre_pad = down - half_len % down
+    return up, down, half_len, n_pre_pad, (half_len + n_pre_pad) // down, h
+
+
+def resample(x, orig_sr, target_sr, quality="poly"):
     """float64 polyphase resampling of a 1-D signal (direct evaluation of the sum above)."""
     x = np.asarray(x, dtype=np.float64)
-    up, down, half_len, n_pre_pad, n_pre_remove, h = design(orig_sr, target_sr)
+    up, down, half_len, n_pre_pad, n_pre_remove, h = (design_hq if quality == "hq" else design)(orig_sr, target_sr)
     n_in = len(x)
     n_out = (n_in * up) // down + ((n_in * up) % down != 0)
     out = np.zeros(n_out, dtype=np.float64)

@@ -104,3 +104,58 @@ def test_chunker_on_device_features():
     want = ap.process_audio_features(feats, ToyModel(), "cpu", cfg, batched=False)
     assert got.shape == (len(feats), 68)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,frame,overlap", CASES + [(230, 128, 16), (240, 128, 16), (1801, 128, 16), (1, 128, 16)])
+def test_device_resident_chunker_equals_host_chunker(n, frame, overlap):
+    """nsf_chunk_gather / nsf_chunk_blend against the host route: the gathered chunks are bit-identical to the
+    NumPy chunks (reflect-completed tails included), and given the SAME decoded chunks the cross-faded result is
+    bit-identical too (the reference's float32 arithmetic, separate multiply and add)."""
+    import ctypes as C
+
+    from neurosync_trainer_lite_b200 import _native as nv
+    from neurosync_trainer_lite_b200 import engine
+    feats = _features(n, seed=n).astype(np.float32)
+    cfg = {"frame_size": frame, "overlap": overlap}
+    dev = torch.device("cuda", 0)
+    eng = engine.get_engine(88200, 1470, 735, device=0)
+    n_chunks = int(nv.lib.nsf_chunk_count(n, frame, overlap))
+    starts = list(range(0, n, frame - overlap))
+    assert n_chunks == len(starts)
+    want_chunks = np.stack([ap.pad_audio_chunk(feats[s0:min(s0 + frame, n)], frame, 256) for s0 in starts])
+    rows = torch.from_numpy(feats).to(dev)
+    chunks = torch.empty((n_chunks, frame, 256), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    nv.check(nv.lib.nsf_chunk_gather(eng.handle, C.c_void_p(stream.cuda_stream), C.c_void_p(rows.data_ptr()), n, 256, 256,
+                                     frame, overlap, C.c_void_p(chunks.data_ptr())))
+    np.testing.assert_array_equal(chunks.cpu().numpy(), want_chunks)
+    # one set of decoded chunks for both blenders
+    model = ToyModel().to(dev)
+    with torch.no_grad():
+        decoded = model.decoder(model.encoder(chunks)).contiguous()
+    dec_h = decoded.cpu().numpy()
+    acc = []
+    for k, s0 in enumerate(starts):
+        part = dec_h[k][:min(s0 + frame, n) - s0]
+        acc = [ap.blend_chunks(acc.pop(), part, overlap)] if acc else [part]
+    want = np.concatenate(acc, axis=0)[:n].copy()
+    want[:, :61] /= 100
+    out = torch.empty((n, 68), dtype=torch.float32, device=dev)
+    nv.check(nv.lib.nsf_chunk_blend(eng.handle, C.c_void_p(stream.cuda_stream), C.c_void_p(decoded.data_ptr()), n, 68, frame,
+                                    overlap, 61, C.c_float(100.0), C.c_void_p(out.data_ptr())))
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    # and the public entry point end to end (same model, same batch -> same numbers)
+    got = ap.process_audio_features(feats, model, "cuda:0", cfg)
+    np.testing.assert_array_equal(got, want)
+    got_t = ap.process_audio_features_device(rows, model, dev, cfg, return_tensor=True)
+    assert got_t.is_cuda and torch.equal(got_t.cpu(), torch.from_numpy(want))
+
+
+@pytest.mark.gpu
+def test_chunker_rejects_overlap_beyond_half_a_chunk():
+    from neurosync_trainer_lite_b200 import _native as nv
+    feats = _features(300, seed=1).astype(np.float32)
+    with pytest.raises(nv.NsfError) as e:
+        ap.process_audio_features(feats, ToyModel().to("cuda:0"), "cuda:0", {"frame_size": 64, "overlap": 40})
+    assert e.value.status == nv.ERR_UNSUPPORTED
