@@ -262,7 +262,8 @@ def _facial_rows(path, dtype):
     if dtype == np.float32:
         try:
             import pyarrow.csv as pacsv
-            table = pacsv.read_csv(path).drop_columns(COLUMNS_TO_DROP)
+            # single-threaded parse: the caller's thread pool already runs one file per core, and Arrow drops the GIL
+            table = pacsv.read_csv(path, read_options=pacsv.ReadOptions(use_threads=False)).drop_columns(COLUMNS_TO_DROP)
             out = np.empty((table.num_rows, table.num_columns), dtype=np.float32)
             for j, col in enumerate(table.columns):
                 out[:, j] = col.to_numpy()
@@ -331,7 +332,7 @@ def load_data_batched(root_dir, sr, processed_folders, include_fast=True, includ
 
     f_len, h_len = _engine.frame_params(REFERENCE_RATE)     # file-path mode always lands at 88.2 kHz
     eng = _engine.get_engine(REFERENCE_RATE, f_len, h_len, device=device)
-    threads = io_threads or min(16, os.cpu_count() or 1)
+    threads = io_threads or min(32, len(os.sched_getaffinity(0)) or 1)
     pool = ThreadPoolExecutor(max_workers=threads)
     try:
         # ---- which takes need extraction; where their audio is -------------------------------------------
