@@ -762,6 +762,68 @@ def api_e2e(D, rank, world, local_rank, steps):
         os.environ.pop("NSF_FEATURE_CACHE", None)
 
 
+def run_single_process(args):
+    """BASELINE configs[3] as SURVEY.md section 8(d) states it: ONE process, one library context and one host thread
+    per GPU, every GPU downloading straight into its slice of ONE page-locked (rows, 256) host array.  End to end
+    only (host int16 PCM in, gathered augmented rows out); wall clock around the whole call."""
+    import __graft_entry__ as g
+    g.build_library()
+    import torch
+    from neurosync_trainer_lite_b200 import engine, shard, synth
+    n = args.gpus
+    if torch.cuda.device_count() < n:
+        raise RuntimeError(f"--single-process --gpus {n} needs {n} visible GPUs")
+    name = args.workload
+    w = WORKLOADS[name]
+    if not w["collect"]:
+        raise RuntimeError("--single-process runs the collect workloads (c3, c4)")
+    parts = [make_inputs(name, r, n, "weak") for r in range(n)]
+    packed = np.concatenate([p[0] for p in parts])
+    lens = np.concatenate([np.diff(p[1]) for p in parts])
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    n_clips = len(lens)
+    pcm16 = synth.to_int16_pcm(packed)
+    del packed, parts
+    pin_in = engine.PinnedBuffer(pcm16.nbytes)
+    h16 = pin_in.view(np.int16, pcm16.shape)
+    h16[:] = pcm16
+    del pcm16
+    facial = np.concatenate([synth.synth_facial(FACIAL_ROWS, seed=i % 6) for i in range(n_clips)]).astype(np.float32)
+    pin_f = engine.PinnedBuffer(facial.nbytes)
+    h_f = pin_f.view(np.float32, facial.shape)
+    h_f[:] = facial
+    f_off = np.arange(n_clips + 1, dtype=np.int64) * FACIAL_ROWS
+    from neurosync_trainer_lite_b200 import _native as nv
+    devices = list(range(n))
+    out_a = out_f = None
+    times = []
+    for it in range(max(args.warmup, 2) + args.steps):
+        t0 = time.perf_counter()
+        out_a, out_f, o_off = shard.extract_collect_multi_device(h16, off, h_f, f_off, devices, sr=w["sr"], flags=nv.PEAK_NORMALIZE,
+                                                                 out_audio=out_a, out_facial=out_f, **w["collect"])
+        if it >= max(args.warmup, 2):
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    audio_s = n_clips * w["seconds"]
+    filled = [bool(np.abs(out_a[o_off[c]:o_off[c] + 4]).sum() > 0) for c in range(0, n_clips, max(1, n_clips // (2 * n)))]
+    line = {
+        "metric": "audio_seconds_per_second", "value": audio_s / dt, "unit": "audio-s/s", "n_gpus": n, "steps": args.steps,
+        "warmup": max(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mode": "single-process, one thread + context per GPU",
+        "config": {"workload": w["desc"], "clips_total": n_clips, "audio_seconds_per_step": audio_s,
+                   "sharding": f"by clip, contiguous runs over {n} GPUs, no collective"},
+        "e2e": {"value": audio_s / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(h16.nbytes + h_f.nbytes),
+                "d2h_bytes_per_step": int(out_a.nbytes + out_f.nbytes), "ms_per_step": dt * 1e3,
+                "api": "shard.extract_collect_multi_device -> nsf_extract_collect_host per device (int16 PCM, page-locked)"},
+        "gathered_host_array": {"shape": list(out_a.shape), "bytes": int(out_a.nbytes + out_f.nbytes), "single_process": True,
+                                "backing": "one cudaHostAlloc(portable) array; each device DMAs its rows to its own offset",
+                                "all_slices_filled": all(filled)},
+        "gpu_launches": int(sum(engine.get_engine(w["sr"], w["F"], w["H"], device=d).launch_count() for d in devices)),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_native(args, rank, world, local_rank):
     import __graft_entry__ as g
     g.build_library()
@@ -858,12 +920,17 @@ def main():
                          "over the ranks.  Default: weak for c2 / c4, strong for c3 / c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the embedded c3 / c4 / c5 passes and the api_e2e leg")
+    ap.add_argument("--single-process", action="store_true",
+                    help="c3 / c4 end to end from ONE process driving --gpus N devices (one thread + context each) into one "
+                         "page-locked host array; run without torchrun")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_native(args, rank, world, local_rank)
 

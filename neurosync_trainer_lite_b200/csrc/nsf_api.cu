@@ -433,7 +433,8 @@ int32_t nsf_device_count(void) {
 
 nsf_status nsf_host_alloc(void** out_ptr, int64_t bytes) {
   if (!out_ptr || bytes <= 0) { set_error("nsf_host_alloc: bad argument"); return NSF_ERR_BAD_ARG; }
-  NSF_CUDA(cudaHostAlloc(out_ptr, static_cast<size_t>(bytes), cudaHostAllocDefault));
+  // portable: page-locked for every device of the process (one host array filled by several GPUs)
+  NSF_CUDA(cudaHostAlloc(out_ptr, static_cast<size_t>(bytes), cudaHostAllocPortable));
   return NSF_OK;
 }
 

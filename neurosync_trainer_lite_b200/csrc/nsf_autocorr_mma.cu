@@ -236,12 +236,11 @@ __device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&r)[4]) {
 }
 
 // The MMA half: normalised lags of the frame currently held in `copies` into val[0..5] (see lag_of).
-// kSplitAcc: the two cross products of a tile (hi.lo, lo.hi) go to SEPARATE accumulators, so that each of the six
-// MMAs of a K-block continues its own chain and an accumulator is touched once per block.  ncu (round 2, source
-// page of the round-1 loop): 44 % of the HMMA stall samples are fixed-latency waits on the accumulator that two of
-// the six MMAs share at a distance of two or three MMAs - shorter than the HMMA latency whenever the second MMA
-// warp of the scheduler is not ready to fill the gap.
-template <bool kSplitAcc>
+// Round 2 measured three re-formulations of this loop on B200 and kept none (gpurun logs
+// r2_ab / r2d / r2h): loading each half of the A fragment once - into a register ring (1.98 ms on C2: ~20 register
+// moves per K-block to assemble the fragment quads) or with plain 32-bit loads into alternating quad positions (8
+// instead of 12 shared-memory wavefronts per K-block, 1.30-1.38 ms: more load INSTRUCTIONS than two ldmatrix.x4) -
+// and one accumulator per MMA of a K-block (six chains instead of four: 1.282 vs 1.285 ms).  This loop: 1.25-1.29 ms.
 __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
   const int g = lane >> 2, tq = lane & 3;
   const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
@@ -266,7 +265,6 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   // (hi.hi) and the two cross products go to separate accumulators: four independent MMA chains.
   float d0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d0x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   float d1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  float d0y[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1y[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // lo.hi products when kSplitAcc
   // B fragments of the last 4 K-blocks: two register sets used alternately (a group of four blocks
   // loads into one set while tile 1 reads the other), so no fragment is ever copied
   uint32_t bp[4][4], bq[4][4];                // [slot][b0h, b1h, b0l, b1l]
@@ -291,8 +289,8 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
       mma_16816(d1x, ah[0], ah[1], ah[2], ah[3], old[q][2], old[q][3]);
       mma_16816(d0, ah[0], ah[1], ah[2], ah[3], cur[q][0], cur[q][1]);
       mma_16816(d1, ah[0], ah[1], ah[2], ah[3], old[q][0], old[q][1]);
-      mma_16816(kSplitAcc ? d0y : d0x, al[0], al[1], al[2], al[3], cur[q][0], cur[q][1]);
-      mma_16816(kSplitAcc ? d1y : d1x, al[0], al[1], al[2], al[3], old[q][0], old[q][1]);
+      mma_16816(d0x, al[0], al[1], al[2], al[3], cur[q][0], cur[q][1]);
+      mma_16816(d1x, al[0], al[1], al[2], al[3], old[q][0], old[q][1]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { ah[i] = nh[i]; al[i] = nl[i]; }
     }
@@ -307,168 +305,8 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   }
   if (left) group(pb_h, pb_l, bp, bq);   // nblk4 is a multiple of 4
   // tile 0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  tile 1: c2,c3 = base+128, base+129.
-  if (kSplitAcc) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { d0x[c] += d0y[c]; d1x[c] += d1y[c]; }
-  }
   val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];
   val[4] = d1[2] + d1x[2]; val[5] = d1[3] + d1x[3];
-  const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
-  if (r0 != 0.0f) {
-    const float inv = __fdiv_rn(1.0f, r0);
-#pragma unroll
-    for (int v = 0; v < kVals; ++v) val[v] *= inv;
-  }
-  __syncwarp();
-}
-
-// The same lags with HALF the shared-memory traffic for the A operand and no B history (kExact kernels: the number
-// of K-blocks is a compile-time constant and the loop is fully unrolled, so every register index below is static).
-//
-// Rows 8..15 of the A fragment of K-block b, H(b) = X(16 b + 64 + k + 8 r) (r = 0..7), are rows 0..7 of block b + 4.
-// So only H is ever loaded - ONE ldmatrix.x4 per K-block brings {hi k0-7, hi k8-15, lo k0-7, lo k8-15} - and
-//     tile 0 (lags   0..127):  A = [H(b-4) ; H(b)  ]   x   B(b)
-//     tile 1 (lags 64..191):   A = [H(b)   ; H(b+4)]   x   B(b)      (rows 8..15 = lags 128..191 are kept)
-// both against the CURRENT block's B fragments: 8 shared-memory wavefronts per K-block (4 for H, 4 for B) instead
-// of 12, ten live H fragments in a statically indexed ring, and the products reach every accumulator in the same
-// order as in am_mma (bit-identical results).  H(b) is identically zero from block kBlocks - 4 on (samples beyond
-// 16 kBlocks are the zero padding), which also removes tile 1's last four blocks.
-template <int kBlocks>
-__device__ __forceinline__ void am_mma_ring(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
-  static_assert(kBlocks % 4 == 0 && kBlocks >= 12, "K-blocks come in groups of four");
-  const int g = lane >> 2, tq = lane & 3;
-  const int mi = lane >> 3, mr = lane & 7;
-  const uint32_t lo_delta = 2u * static_cast<uint32_t>(geo.len);
-  // this lane's ldmatrix row of H(0); H(b) lies 32 bytes per block further (negative b: the frame's first rows)
-  const uint32_t sa0 = am_smem_u32(copies) + 2u * static_cast<uint32_t>(kFrontMargin + 64 + 8 * mr + (mi & 1) * 8) +
-                       static_cast<uint32_t>(mi >> 1) * lo_delta;
-  const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
-  const uint32_t* E_lo = E_hi + geo.len / 2;
-  const uint32_t* O_hi = E_lo + geo.len / 2;
-  const uint32_t* O_lo = O_hi + geo.len / 2;
-  const int boff = kFrontMargin + 2 * tq - g - (g & 1);
-  const uint32_t* Bh = ((g & 1) ? O_hi : E_hi) + boff / 2;
-  const uint32_t* Bl = ((g & 1) ? O_lo : E_lo) + boff / 2;
-  float d0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d0x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  float d1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d1x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  constexpr int kRing = 10;                 // H(b-4) .. H(b+5): slot of H(b) = (b + 4) % kRing
-  uint32_t H[kRing][4];
-#pragma unroll
-  for (int b = -4; b <= 4; ++b) ldsm_x4(sa0 + static_cast<uint32_t>(32 * b), H[(b + 4) % kRing]);
-  uint32_t B[2][4];
-  B[0][0] = Bh[0]; B[0][1] = Bh[4]; B[0][2] = Bl[0]; B[0][3] = Bl[4];
-#pragma unroll
-  for (int b = 0; b < kBlocks; ++b) {
-    // one block ahead: H(b + 5) into the slot H(b - 5) has just left, B(b + 1) into the other B set
-    if (b + 5 < kBlocks - 4) {
-      ldsm_x4(sa0 + static_cast<uint32_t>(32 * (b + 5)), H[(b + 9) % kRing]);
-    } else {
-      H[(b + 9) % kRing][0] = H[(b + 9) % kRing][1] = H[(b + 9) % kRing][2] = H[(b + 9) % kRing][3] = 0u;
-    }
-    if (b + 1 < kBlocks) {
-      B[(b + 1) & 1][0] = Bh[8 * (b + 1)]; B[(b + 1) & 1][1] = Bh[8 * (b + 1) + 4];
-      B[(b + 1) & 1][2] = Bl[8 * (b + 1)]; B[(b + 1) & 1][3] = Bl[8 * (b + 1) + 4];
-    }
-    const uint32_t(&lo4)[4] = H[b % kRing];          // H(b - 4): rows 0..7 of tile 0
-    const uint32_t(&mid)[4] = H[(b + 4) % kRing];    // H(b):     rows 8..15 of tile 0, rows 0..7 of tile 1
-    const uint32_t(&hi4)[4] = H[(b + 8) % kRing];    // H(b + 4): rows 8..15 of tile 1
-    const uint32_t(&cur)[4] = B[b & 1];              // {b0 hi, b1 hi, b0 lo, b1 lo}
-    const bool tile1 = b < kBlocks - 4;              // compile-time after unrolling
-    mma_16816(d0x, lo4[0], mid[0], lo4[1], mid[1], cur[2], cur[3]);
-    if (tile1) mma_16816(d1x, mid[0], hi4[0], mid[1], hi4[1], cur[2], cur[3]);
-    mma_16816(d0, lo4[0], mid[0], lo4[1], mid[1], cur[0], cur[1]);
-    if (tile1) mma_16816(d1, mid[0], hi4[0], mid[1], hi4[1], cur[0], cur[1]);
-    mma_16816(d0x, lo4[2], mid[2], lo4[3], mid[3], cur[0], cur[1]);
-    if (tile1) mma_16816(d1x, mid[2], hi4[2], mid[3], hi4[3], cur[0], cur[1]);
-  }
-  val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];
-  val[4] = d1[2] + d1x[2]; val[5] = d1[3] + d1x[3];
-  const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
-  if (r0 != 0.0f) {
-    const float inv = __fdiv_rn(1.0f, r0);
-#pragma unroll
-    for (int v = 0; v < kVals; ++v) val[v] *= inv;
-  }
-  __syncwarp();
-}
-
-// Third formulation: the loop structure of am_mma (one A fragment per K-block used for BOTH tiles, tile 1 against
-// the B fragments of four blocks earlier) with each half of the A fragment loaded ONCE.  The blocks b, b+4, b+8, ...
-// share one register quad per split part: the rows new to block b, H(b), are written alternately to positions
-// (a0, a2) and (a1, a3) while the half that entered four blocks earlier stays where it is.  In the blocks where the
-// new rows sit in (a0, a2) the MMA sees the two row halves exchanged, so those blocks accumulate into a second set
-// of accumulators whose row halves are exchanged back when the sets are added.  The new rows arrive as four plain
-// 32-bit loads (one conflict-free wavefront each) that write their quad positions directly - an ldmatrix.x4 would
-// deliver them in four CONSECUTIVE registers and cost four moves per block.  Per K-block: 4 A loads + 4 B loads (8
-// wavefronts) + 6 MMAs; am_mma needs 12 wavefronts, am_mma_ring ~20 register moves.  The products of a lag are summed in two groups here, so results differ from am_mma in the last bits.
-// 32-bit shared-memory load the compiler may not move across the (volatile) MMAs: the unrolled loop keeps exactly
-// the prefetch distance written below instead of hoisting dozens of loads and spilling.
-__device__ __forceinline__ uint32_t am_lds32(uint32_t saddr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr));
-  return v;
-}
-
-template <int kBlocks>
-__device__ __forceinline__ void am_mma_alt(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
-  static_assert(kBlocks % 4 == 0 && kBlocks >= 12, "K-blocks come in groups of four");
-  const int g = lane >> 2, tq = lane & 3;
-  const uint32_t lo_delta = 2u * static_cast<uint32_t>(geo.len);   // E_lo - E_hi (and O_lo - O_hi) in bytes
-  // H(b) register of lane (g, tq): the pair X(16 b + 64 + 8 g + 2 tq [+ 8]), a 32-bit word of the E copy; the 32
-  // lanes of a load read 32 consecutive words (conflict-free), and every load writes its quad position directly
-  const uint32_t sA = am_smem_u32(copies) + 2u * static_cast<uint32_t>(kFrontMargin + 64 + 8 * g + 2 * tq);  // + 32 b; k 8..15: + 16
-  const int boff = kFrontMargin + 2 * tq - g - (g & 1);
-  const uint32_t sB = am_smem_u32(copies) + ((g & 1) ? 4u * static_cast<uint32_t>(geo.len) : 0u) + 2u * static_cast<uint32_t>(boff);
-  // accumulators [set][tile]: set 0 = row halves in place (new rows in a1, a3), set 1 = exchanged
-  float d[2][2][4], dx[2][2][4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) d[a][t][c] = dx[a][t][c] = 0.0f;
-  uint32_t Qh[4][4], Ql[4][4];      // per residue class b & 3: the A fragment quads of the hi and lo parts
-  uint32_t Bf[6][4];                // B fragments of blocks b-4 .. b+1 {b0 hi, b1 hi, b0 lo, b1 lo} (static ring)
-  auto load_block = [&](int b) {    // H(b) into its quad positions, B(b) into its ring slot (b: compile-time constant)
-    const int r = b & 3;
-    const int p0 = ((b >> 2) & 1) ? 1 : 0;        // groups 0, 2, 4, ...: (a0, a2); groups 1, 3, ...: (a1, a3)
-    const uint32_t a = sA + static_cast<uint32_t>(32 * b);
-    Qh[r][p0] = am_lds32(a); Qh[r][p0 + 2] = am_lds32(a + 16u);
-    Ql[r][p0] = am_lds32(a + lo_delta); Ql[r][p0 + 2] = am_lds32(a + lo_delta + 16u);
-    const uint32_t q = sB + static_cast<uint32_t>(32 * b);
-    Bf[b % 6][0] = am_lds32(q); Bf[b % 6][1] = am_lds32(q + 16u);
-    Bf[b % 6][2] = am_lds32(q + lo_delta); Bf[b % 6][3] = am_lds32(q + lo_delta + 16u);
-  };
-  // prologue: H(-4..-1), the frame's first rows, enter at (a1, a3) - as if an "in place" group had loaded them
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const uint32_t a = sA - static_cast<uint32_t>(32 * (4 - r));
-    Qh[r][1] = am_lds32(a); Qh[r][3] = am_lds32(a + 16u);
-    Ql[r][1] = am_lds32(a + lo_delta); Ql[r][3] = am_lds32(a + lo_delta + 16u);
-  }
-  load_block(0);
-#pragma unroll
-  for (int b = 0; b < kBlocks; ++b) {
-    const int r = b & 3;
-    const int set = ((b >> 2) & 1) ^ 1;           // new rows in (a0, a2) -> the exchanged set
-    // one block ahead: the quad positions and the ring slot written here were last read by block b - 3 / b - 5
-    if (b + 1 < kBlocks) load_block(b + 1);
-    const uint32_t(&cur)[4] = Bf[b % 6];
-    const uint32_t(&old)[4] = Bf[(b + 2) % 6];    // block b - 4
-    mma_16816(dx[set][0], Qh[r][0], Qh[r][1], Qh[r][2], Qh[r][3], cur[2], cur[3]);
-    if (b >= 4) mma_16816(dx[set][1], Qh[r][0], Qh[r][1], Qh[r][2], Qh[r][3], old[2], old[3]);
-    mma_16816(d[set][0], Qh[r][0], Qh[r][1], Qh[r][2], Qh[r][3], cur[0], cur[1]);
-    if (b >= 4) mma_16816(d[set][1], Qh[r][0], Qh[r][1], Qh[r][2], Qh[r][3], old[0], old[1]);
-    mma_16816(dx[set][0], Ql[r][0], Ql[r][1], Ql[r][2], Ql[r][3], cur[0], cur[1]);
-    if (b >= 4) mma_16816(dx[set][1], Ql[r][0], Ql[r][1], Ql[r][2], Ql[r][3], old[0], old[1]);
-  }
-  // set 0: c0, c1 = lags base, base + 1 (rows 0..7), c2, c3 = base + 64, + 65; set 1 has the halves exchanged
-  val[0] = (d[0][0][0] + dx[0][0][0]) + (d[1][0][2] + dx[1][0][2]);
-  val[1] = (d[0][0][1] + dx[0][0][1]) + (d[1][0][3] + dx[1][0][3]);
-  val[2] = (d[0][0][2] + dx[0][0][2]) + (d[1][0][0] + dx[1][0][0]);
-  val[3] = (d[0][0][3] + dx[0][0][3]) + (d[1][0][1] + dx[1][0][1]);
-  val[4] = (d[0][1][2] + dx[0][1][2]) + (d[1][1][0] + dx[1][1][0]);     // tile 1: base + 128, + 129
-  val[5] = (d[0][1][3] + dx[0][1][3]) + (d[1][1][1] + dx[1][1][1]);
   const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
   if (r0 != 0.0f) {
     const float inv = __fdiv_rn(1.0f, r0);
@@ -514,16 +352,10 @@ __device__ __forceinline__ void am_bar_wait(uint64_t* bar, uint32_t parity) {
 // frame buffers.  The producer warp fetches, windows, scales and splits frame after frame; the
 // consumer warp runs nothing but the MMA loop (plus the cheap normalise / pair-mean / store), so the
 // tensor pipe is fed continuously while memory latency and the fp32->fp16 conversion hide behind it.
+// Round 2: this kernel is the alternative (NSF_AC_KERNEL=pairs); the symmetric kernel below is the product path.
 constexpr int kAmPairs = 4;
-constexpr int kDefaultLoop = 1;
-constexpr bool kDefaultSym = true;    // which kernel runs by default for the exact-size frames (see k_autocorr_sym)   // see k_autocorr_mma: which MMA loop the exact-size kernels run by default
 
-// kLoop (exact-size kernels only; NSF_AC_LOOP=legacy|ring|alt picks one at run time for A/B timing):
-//   1  am_mma       A through two ldmatrix.x4 per block, B history in registers (round 1)
-//   2  am_mma_ring  A halves loaded once into a ring, no B history; bit-identical to am_mma
-//   0  am_mma_alt   A halves loaded once into alternating quad positions, two accumulator sets
-//   3  am_mma<true> the round-1 loop with one accumulator per MMA of a K-block (six independent chains)
-template <int kIters, bool kExact, int kLoop = 1>
+template <int kIters, bool kExact>
 __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables t, BatchView b,
                                                                    const float* __restrict__ y, bool reduce,
                                                                    float* __restrict__ out, int64_t out_ld,
@@ -597,16 +429,12 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
         const int64_t tf = tf0 + f;
         float val[kVals];
         am_bar_wait(full + buf, (it >> 1) & 1u);
-        if constexpr (kExact && kLoop == 0) am_mma_alt<4 * kIters>(copies, geo, lane, val);
-        else if constexpr (kExact && kLoop == 2) am_mma_ring<4 * kIters>(copies, geo, lane, val);
-        else am_mma<kLoop == 3>(copies, geo, lane, val);
+        am_mma(copies, geo, lane, val);
         // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2);
         // rare, so the consumer refills the buffer it still owns itself
         if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
           am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
-          if constexpr (kExact && kLoop == 0) am_mma_alt<4 * kIters>(copies, geo, lane, val);
-          else if constexpr (kExact && kLoop == 2) am_mma_ring<4 * kIters>(copies, geo, lane, val);
-          else am_mma<kLoop == 3>(copies, geo, lane, val);
+          am_mma(copies, geo, lane, val);
         }
         __syncwarp();
         if (lane == 0) am_bar_arrive(empty + buf);
@@ -681,10 +509,10 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
         am_fill_simple(t, hann, src, copies, geo, lane);
       }                                                   // both end with __syncwarp
       float val[kVals];
-      am_mma<false>(copies, geo, lane, val);              // ends with __syncwarp: the buffer may be rewritten
+      am_mma(copies, geo, lane, val);                     // ends with __syncwarp: the buffer may be rewritten
       if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
         am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
-        am_mma<false>(copies, geo, lane, val);
+        am_mma(copies, geo, lane, val);
       }
 #pragma unroll
       for (int v = 0; v < kVals; ++v) acc[v] += val[v];
@@ -699,22 +527,6 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
   }
 }
 
-// launch of the symmetric kernel; returns 0 when it does not apply (frame buffers too large), -1 on error
-template <typename Launch>
-int am_launch_sym(const BatchView& b, const AmGeom& geo, size_t hann_bytes, Launch&& launch) {
-  int warps = kSymWarps;
-  size_t smem = 0;
-  for (; warps >= 2; warps -= 2) {
-    smem = static_cast<size_t>(warps) * 4 * geo.len * sizeof(__half) + hann_bytes;
-    if (smem <= 110 * 1024) break;            // two blocks per SM
-  }
-  if (warps < 2) return 0;
-  int64_t grid = (b.total_rows + warps - 1) / warps;
-  if (grid > static_cast<int64_t>(kSmCount) * 2) grid = static_cast<int64_t>(kSmCount) * 2;
-  if (grid < 1) grid = 1;
-  return launch(static_cast<int>(grid), warps * 32, smem);
-}
-
 }  // namespace
 
 int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
@@ -723,53 +535,56 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   if (t.n_lags > 191) return -1;
   const int iters = (t.F / 2 + 1 + 31) / 32;      // register-staging iterations the frame needs
   const size_t hann_bytes = static_cast<size_t>(64) * iters * sizeof(float);   // np.hanning(F), zero padded
-  // four (consumer, producer) pairs per block when their eight frame buffers fit twice per SM or at least
-  // once; long frames (F > ~1530, e.g. 96 kHz) run with three or two pairs per block
+  // NSF_AC_KERNEL=pairs selects the warp-specialised kernel of round 1 (A/B timing; bit-identical results)
+  static const bool use_pairs = [] {
+    const char* v = std::getenv("NSF_AC_KERNEL");
+    return v != nullptr && v[0] == 'p';
+  }();
+  // symmetric kernel: as many warps per block as fit twice per SM (eight up to F ~ 1530, fewer for long frames)
+  int warps = kSymWarps;
+  size_t sym_smem = 0;
+  for (; warps >= 1; --warps) {
+    sym_smem = static_cast<size_t>(warps) * 4 * geo.len * sizeof(__half) + hann_bytes;
+    if (sym_smem <= (warps > 2 ? 110 : 220) * 1024) break;      // long frames: one block per SM
+  }
+  // pairs kernel: four (consumer, producer) pairs per block when their eight frame buffers fit, else three or two
   int pairs = kAmPairs;
   size_t smem = 0;
   for (; pairs >= 1; --pairs) {
     smem = static_cast<size_t>(pairs) * 2 * 4 * geo.len * sizeof(__half) + hann_bytes;
     if (smem <= 220 * 1024) break;
   }
-  if (pairs < 1) return -1;
-  int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
-  int64_t grid = (b.total_rows + pairs - 1) / pairs;
-  if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
-  if (grid < 1) grid = 1;
-  // NSF_AC_KERNEL=pairs|sym picks the warp-specialised or the symmetric kernel (A/B timing; same results)
-  static const bool use_sym = [] {
-    const char* v = std::getenv("NSF_AC_KERNEL");
-    return v ? v[0] == 's' : kDefaultSym;
-  }();
-  if (use_sym && (iters == 23 || iters == 5)) {
-    const int rc = am_launch_sym(b, geo, hann_bytes, [&](int g, int threads, size_t bytes) {
-      if (iters == 23) k_autocorr_sym<23, true><<<g, threads, bytes, s>>>(t, b, y, reduce, out, out_ld, col0);
-      else k_autocorr_sym<5, true><<<g, threads, bytes, s>>>(t, b, y, reduce, out, out_ld, col0);
-      return cudaGetLastError() == cudaSuccess ? 1 : -1;
-    });
-    if (rc != 0) return rc;
+  if (warps < 1 && pairs < 1) return -1;
+  const bool sym = !use_pairs && warps >= 1;
+  int64_t grid;
+  int threads;
+  if (sym) {
+    const int per_sm = sym_smem <= 110 * 1024 ? 2 : 1;
+    grid = (b.total_rows + warps - 1) / warps;
+    if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
+    threads = warps * 32;
+    smem = sym_smem;
+  } else {
+    if (pairs < 1) return -1;
+    int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+    grid = (b.total_rows + pairs - 1) / pairs;
+    if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
+    threads = pairs * 64;
   }
-  auto go = [&](auto kernel) {
-    kernel<<<static_cast<int>(grid), pairs * 64, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+  if (grid < 1) grid = 1;
+  auto go = [&](auto k_sym, auto k_pairs) {
+    if (sym) k_sym<<<static_cast<int>(grid), threads, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+    else k_pairs<<<static_cast<int>(grid), threads, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   };
-  static const int loop = [] {
-    const char* v = std::getenv("NSF_AC_LOOP");
-    if (!v) return kDefaultLoop;
-    return v[0] == 'a' ? 0 : (v[0] == 'r' ? 2 : (v[0] == 's' ? 3 : 1));      // alt | ring | split | legacy
-  }();
-  if (iters == 23)   // 88.2 kHz: F = 1470
-    return loop == 0 ? go(k_autocorr_mma<23, true, 0>) : loop == 2 ? go(k_autocorr_mma<23, true, 2>)
-         : loop == 3 ? go(k_autocorr_mma<23, true, 3>) : go(k_autocorr_mma<23, true, 1>);
-  if (iters == 5)    // 16 kHz: F = 266
-    return loop == 0 ? go(k_autocorr_mma<5, true, 0>) : loop == 2 ? go(k_autocorr_mma<5, true, 2>)
-         : loop == 3 ? go(k_autocorr_mma<5, true, 3>) : go(k_autocorr_mma<5, true, 1>);
-  if (iters <= 6) return go(k_autocorr_mma<6, false>);    // F <= 382   (22.05 kHz: 367)
-  if (iters <= 12) return go(k_autocorr_mma<12, false>);  // F <= 766   (44.1 kHz: 735)
-  if (iters <= 24) return go(k_autocorr_mma<24, false>);  // F <= 1534  (48 kHz: 800)
-  if (iters <= 40) return go(k_autocorr_mma<40, false>);  // F <= 2558
-  return go(k_autocorr_mma<66, false>);                   // F <= 4096  (plan limit)
+  if (iters == 23) return go(k_autocorr_sym<23, true>, k_autocorr_mma<23, true>);    // 88.2 kHz: F = 1470
+  if (iters == 5) return go(k_autocorr_sym<5, true>, k_autocorr_mma<5, true>);      // 16 kHz: F = 266
+  if (iters <= 6) return go(k_autocorr_sym<6, false>, k_autocorr_mma<6, false>);    // F <= 382   (22.05 kHz: 367)
+  if (iters <= 12) return go(k_autocorr_sym<12, false>, k_autocorr_mma<12, false>); // F <= 766   (44.1 kHz: 735)
+  if (iters <= 24) return go(k_autocorr_sym<24, false>, k_autocorr_mma<24, false>); // F <= 1534  (48 kHz: 800)
+  if (iters <= 40) return go(k_autocorr_sym<40, false>, k_autocorr_mma<40, false>); // F <= 2558
+  return go(k_autocorr_sym<66, false>, k_autocorr_mma<66, false>);                  // F <= 4096  (plan limit)
 }
 
 // Opt-in shared-memory limit of every instantiation, once per device (called by nsf_ctx_create after
@@ -779,13 +594,12 @@ bool init_autocorr_mma_attributes() {
   auto set = [&](auto kernel) {
     ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess;
   };
-  set(k_autocorr_mma<23, true, 0>); set(k_autocorr_mma<5, true, 0>); set(k_autocorr_mma<6, false>);
-  set(k_autocorr_mma<23, true, 1>); set(k_autocorr_mma<5, true, 1>);
-  set(k_autocorr_mma<23, true, 2>); set(k_autocorr_mma<5, true, 2>);
-  set(k_autocorr_mma<23, true, 3>); set(k_autocorr_mma<5, true, 3>);
-  set(k_autocorr_sym<23, true>); set(k_autocorr_sym<5, true>);
+  set(k_autocorr_mma<23, true>); set(k_autocorr_mma<5, true>); set(k_autocorr_mma<6, false>);
   set(k_autocorr_mma<12, false>); set(k_autocorr_mma<24, false>); set(k_autocorr_mma<40, false>);
   set(k_autocorr_mma<66, false>);
+  set(k_autocorr_sym<23, true>); set(k_autocorr_sym<5, true>); set(k_autocorr_sym<6, false>);
+  set(k_autocorr_sym<12, false>); set(k_autocorr_sym<24, false>); set(k_autocorr_sym<40, false>);
+  set(k_autocorr_sym<66, false>);
   return ok;
 }
 

@@ -32,6 +32,70 @@ def lpt_partition(lengths, world):
     return [sorted(p) for p in parts]
 
 
+def block_partition(lengths, world):
+    """Contiguous split of the clip list into ``world`` runs of near-equal total length (each cut placed at the
+    clip boundary closest to its ideal position).  Every rank's rows then form ONE slice of the gathered array,
+    so a rank can download straight into it."""
+    lengths = np.asarray([int(n) for n in lengths], dtype=np.int64)
+    n = len(lengths)
+    cum = np.concatenate([[0], np.cumsum(lengths)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        i = int(np.searchsorted(cum, target))            # first boundary at or beyond the target
+        if i > 0 and target - cum[i - 1] <= cum[min(i, n)] - target:
+            i -= 1
+        cuts.append(min(max(i, cuts[-1]), n))
+    cuts.append(n)
+    return [list(range(cuts[r], cuts[r + 1])) for r in range(world)]
+
+
+def extract_collect_multi_device(pcm, offsets, facial, facial_offsets, devices, sr=88200, flags=0, include_fast=True,
+                                 include_slow=False, blend_boundaries=True, blend_frames=30, out_audio=None,
+                                 out_facial=None):
+    """Features + ``collect_features`` augmentation of one dataset on SEVERAL GPUs from ONE process: one thread and
+    one library context per device, every device working on a contiguous run of clips and downloading its rows
+    straight into its slice of ONE page-locked host array ("gather" = independent D2H
+    copies, no collective).  ``pcm`` / ``facial`` should be page-locked (``engine.PinnedBuffer``) for full speed.
+    Returns ``(audio rows, facial rows, output row offsets)`` in the input clip order."""
+    import threading
+
+    from . import engine as _engine
+    f_len, h_len = _engine.frame_params(sr)
+    off = np.asarray(offsets, dtype=np.int64)
+    f_off = np.asarray(facial_offsets, dtype=np.int64)
+    engines = [_engine.get_engine(sr, f_len, h_len, device=d) for d in devices]
+    kw = dict(include_fast=include_fast, include_slow=include_slow, blend_boundaries=blend_boundaries, blend_frames=blend_frames)
+    o_off = engines[0].collect_rows(engines[0].row_offsets(off, flags), f_off, **kw)
+    cols = engines[0].plan.feature_cols(flags)
+    n_out = int(o_off[-1])
+    if out_audio is None:
+        out_audio = _engine.PinnedBuffer(n_out * cols * 4).view(np.float32, (n_out, cols))
+    if out_facial is None:
+        out_facial = _engine.PinnedBuffer(n_out * facial.shape[1] * 4).view(np.float32, (n_out, facial.shape[1]))
+    parts = block_partition(np.diff(off), len(devices))
+    errors = []
+
+    def work(eng, idx):
+        try:
+            if not idx:
+                return
+            c0, c1 = idx[0], idx[-1] + 1
+            eng.extract_collect_host(pcm, off[c0:c1 + 1], facial, f_off[c0:c1 + 1], flags,
+                                     out_audio=out_audio[o_off[c0]:o_off[c1]], out_facial=out_facial[o_off[c0]:o_off[c1]], **kw)
+        except Exception as e:  # noqa: BLE001 - re-raised in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(e, p)) for e, p in zip(engines, parts)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out_audio, out_facial, o_off
+
+
 def row_layout(row_counts, parts):
     """Global row offsets (input order) and, per rank, the global row offset of each of its clips."""
     row_counts = np.asarray(row_counts, dtype=np.int64)

@@ -110,3 +110,12 @@ def test_assemble_handles_empty_ranks():
     want, woff = _fake_extract(clips)
     np.testing.assert_array_equal(rows, want)
     np.testing.assert_array_equal(off, woff)
+
+
+def test_block_partition_is_contiguous_and_balanced():
+    from neurosync_trainer_lite_b200 import shard
+    for lengths, world in (([5] * 60, 8), ([10, 1, 1, 1, 10, 3, 3], 3), ([1, 2, 3], 5), ([7], 2), ([3, 3, 3, 3], 4)):
+        parts = shard.block_partition(lengths, world)
+        assert len(parts) == world and sum(parts, []) == list(range(len(lengths)))      # contiguous, complete, ordered
+    loads = [sum(5 for _ in p) for p in shard.block_partition([5] * 60, 8)]
+    assert max(loads) - min(loads) <= 5
