@@ -555,9 +555,8 @@ def measure_workload(name, scaling, steps, warmup, D, rank, world, local_rank, d
     for k in kernels:
         ms = k["ms"] * 1e-3
         if k["kernel"] == "autocorr":
-            nblk = (Fr + 15) // 16
-            nblk4 = (nblk + 3) // 4 * 4
-            ex = frames * nblk4 * 6 * 4096 / ms / 1e12
+            nblk = (Fr + 15) // 16                      # K-blocks that hold samples (all-zero blocks are skipped)
+            ex = frames * nblk * 6 * 4096 / ms / 1e12
             # the lag products are a banded Toeplitz matrix-VECTOR product per frame (no operand shared between
             # frames), which only the warp-level HMMA pipe can fill: its measured peak is the relevant ceiling,
             # and the same FLOPs on the fp32 FMA pipe (the reference algorithm's pipe) are given for scale
@@ -855,11 +854,13 @@ def run_native(args, rank, world, local_rank):
     # DRAM bytes per launch from the newest committed `ncu --set full` capture (scripts/ncu_extract.py)
     traffic = {}
     import glob
-    tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_*.json")))
-    if tpaths:
-        with open(tpaths[-1]) as fh:
-            traffic = json.load(fh)
-        traffic["file"] = os.path.relpath(tpaths[-1], ROOT)
+    for tp in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_*.json")), reverse=True):
+        with open(tp) as fh:
+            cand = json.load(fh)
+        if cand.get("workload") == name:                  # newest capture of THIS workload
+            traffic = cand
+            traffic["file"] = os.path.relpath(tp, ROOT)
+            break
     top = main["kernels"][0]
     roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
                 "unit": top["unit"], "frac": top["frac"],

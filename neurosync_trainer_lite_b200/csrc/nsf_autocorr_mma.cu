@@ -35,10 +35,11 @@ constexpr int kFrontMargin = 16;   // halfs of zeros before X(0)  (B reads back 
 constexpr int kBackMargin = 160;   // halfs of zeros after the last K-block (the A prefetch of one block beyond reads up to +151)
 constexpr int kVals = 6;           // lags per thread that can be <= 191
 
-struct AmGeom { int nblk4; int len; };   // K-blocks (multiple of 4), halfs per copy
+struct AmGeom { int nblk; int nblk4; int len; };   // K-blocks that hold samples, rounded up to a multiple of 4, halfs per copy
 __host__ __device__ inline AmGeom am_geom(int F) {
   AmGeom g;
-  g.nblk4 = ((F + 15) / 16 + 3) / 4 * 4;
+  g.nblk = (F + 15) / 16;
+  g.nblk4 = (g.nblk + 3) / 4 * 4;
   g.len = kFrontMargin + 16 * g.nblk4 + kBackMargin;
   return g;
 }
@@ -275,9 +276,12 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   ldsm_x4(sa_h, ah);
   ldsm_x4(sa_h + lo_delta, al);
   // one group = 4 K-blocks; `cur` receives this group's B fragments, `old` holds the previous group's
-  auto group = [&](const uint32_t* pb_h, const uint32_t* pb_l, uint32_t (&cur)[4][4], const uint32_t (&old)[4][4]) {
+  // nq: blocks of the group that hold samples (4, or fewer in the frame's last group: blocks beyond the frame are
+  // all-zero A fragments, e.g. 3 of the 20 blocks at F = 266, and contribute nothing to either tile)
+  auto group = [&](const uint32_t* pb_h, const uint32_t* pb_l, uint32_t (&cur)[4][4], const uint32_t (&old)[4][4], int nq) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+      if (q >= nq) break;
       uint32_t nh[4], nl[4];
       sa_h += 32u;
       ldsm_x4(sa_h, nh);                       // one block beyond the last one reads the zero margin
@@ -296,14 +300,19 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
     }
   };
   const uint32_t *pb_h = Bh, *pb_l = Bl;
-  int left = geo.nblk4;
+  int left = geo.nblk;
 #pragma unroll 1
   for (; left >= 8; left -= 8) {
-    group(pb_h, pb_l, bp, bq);
-    group(pb_h + 32, pb_l + 32, bq, bp);
+    group(pb_h, pb_l, bp, bq, 4);
+    group(pb_h + 32, pb_l + 32, bq, bp, 4);
     pb_h += 64; pb_l += 64;
   }
-  if (left) group(pb_h, pb_l, bp, bq);   // nblk4 is a multiple of 4
+  if (left >= 4) {
+    group(pb_h, pb_l, bp, bq, 4);
+    if (left > 4) group(pb_h + 32, pb_l + 32, bq, bp, left - 4);
+  } else if (left) {
+    group(pb_h, pb_l, bp, bq, left);
+  }
   // tile 0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  tile 1: c2,c3 = base+128, base+129.
   val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];
   val[4] = d1[2] + d1x[2]; val[5] = d1[3] + d1x[3];
