@@ -8,6 +8,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "nsf.h"
 #include "nsf_internal.h"
 #include "nsf_kernels.cuh"
@@ -256,6 +258,33 @@ nsf_status upload_tables(nsf_ctx* ctx) {
   for (int k = 0; k < p.n_mfcc; ++k)
     for (int m = 0; m < p.n_mels; ++m) dct_t[static_cast<size_t>(m) * 32 + k] = p.dct[static_cast<size_t>(k) * p.n_mels + m];
   const size_t off_dct = put(dct_t.data(), dct_t.size() * sizeof(float));
+  // k_dct_mma: B[k][n] = 2^10 dct[n][k] (n < n_mfcc, else 0) split into fp16 hi + lo, in m16n8k16 fragment order:
+  // lane (g, tq) of k-step ks, column tile nt holds b0 = (k = 16 ks + 2 tq, + 1; n = 8 nt + g), b1 = (k + 8, k + 9)
+  std::vector<uint32_t> dct_frag;
+  const bool dct_frag_ok = p.n_mels == kDctConstMels && p.n_mfcc == kDctConstMfcc;
+  if (dct_frag_ok) {
+    dct_frag.assign(static_cast<size_t>(8) * 3 * 2 * 32 * 2, 0u);
+    auto half_bits = [](float v) { const __half h = __float2half_rn(v); uint16_t u; std::memcpy(&u, &h, 2); return u; };
+    auto half_val = [](float v) { return __half2float(__float2half_rn(v)); };
+    for (int ks = 0; ks < 8; ++ks)
+      for (int nt = 0; nt < 3; ++nt)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int g = lane >> 2, tq = lane & 3, n = 8 * nt + g;
+          for (int reg = 0; reg < 2; ++reg) {
+            uint32_t hi = 0, lo = 0;
+            for (int e = 0; e < 2; ++e) {
+              const int k = 16 * ks + 2 * tq + 8 * reg + e;
+              const float v = n < p.n_mfcc ? p.dct[static_cast<size_t>(n) * p.n_mels + k] * 1024.0f : 0.0f;
+              const float vh = half_val(v);
+              hi |= static_cast<uint32_t>(half_bits(v)) << (16 * e);
+              lo |= static_cast<uint32_t>(half_bits(v - vh)) << (16 * e);
+            }
+            dct_frag[((static_cast<size_t>(ks * 3 + nt) * 2 + 0) * 32 + lane) * 2 + reg] = hi;
+            dct_frag[((static_cast<size_t>(ks * 3 + nt) * 2 + 1) * 32 + lane) * 2 + reg] = lo;
+          }
+        }
+  }
+  const size_t off_dct_frag = dct_frag_ok ? put(dct_frag.data(), dct_frag.size() * sizeof(uint32_t)) : 0;
   ctx->dct_coef_ok = p.n_mels == kDctConstMels && p.n_mfcc == kDctConstMfcc;
   if (ctx->dct_coef_ok)
     for (int m = 0; m < kDctConstMels; ++m)
@@ -318,6 +347,7 @@ nsf_status upload_tables(nsf_ctx* ctx) {
   t.mel_ptr = reinterpret_cast<const int32_t*>(base + off_mp);
   t.mel_w = reinterpret_cast<const float*>(base + off_mw);
   t.dct_t = reinterpret_cast<const float*>(base + off_dct);
+  t.dct_frag = dct_frag_ok ? reinterpret_cast<const uint2*>(base + off_dct_frag) : nullptr;
   t.mel_col[0] = reinterpret_cast<const float4*>(base + off_melcol[0]);
   t.mel_col[1] = p.chains > 1 ? reinterpret_cast<const float4*>(base + off_melcol[1]) : nullptr;
   t.mel_col_ok = mel_col_ok;

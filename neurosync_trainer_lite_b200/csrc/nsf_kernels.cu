@@ -598,6 +598,140 @@ __global__ void __launch_bounds__(kDct2Warps * 32, 3) k_dct_const(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 on the tensor pipe: the DCT-II of the default shape (128 mels -> 23 coefficients) as warp-level MMAs
+// (mma.sync m16n8k16, fp16 split operands, fp32 accumulation).  north_star lists the DCT among the dense contractions
+// that belong on tensor cores; as FFMAs it costs 2944 instructions per frame (k_dct_const: issue bound at 0.46 of the
+// HBM roofline), as MMAs 4.5 per frame: [32 frames x 128] x [128 x 24] per warp tile = 8 k-steps x 2 row tiles x 3
+// column tiles x 3 split products.
+//   A  floored dB rows, CENTRED per row: x' = max(x, clip_max - 80) - (clip_max - 40) lies in [-40, 40], so the fp16
+//      hi + lo split carries 2^-22 x 64 = 1.5e-5 of absolute error per element instead of 3e-5 at |x| ~ 100.  The
+//      offset only reaches coefficient 0 (the other DCT rows sum to zero) and is added back there in float32.
+//   B  the DCT matrix scaled by 2^10 (exact), pre-split on the host into hi / lo and laid out in fragment order
+//      (one 64-bit shared-memory load per lane, k-step, column tile and part).
+// hi.hi + hi.lo + lo.hi: fp32-class like the other split GEMMs of the path.  Staging, store and the float64 CMVN
+// moments are those of k_dct_const.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDctMmaFragWords = 8 * 3 * 2 * 32 * 2;      // [k-step][column tile][hi, lo][lane] x {b0, b1}
+constexpr float kDctMmaScale = 1024.0f;
+
+__device__ __forceinline__ void dct_mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x0, x1) -> packed fp16 hi pair and lo pair
+__device__ __forceinline__ void dct_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(kDct2Warps * 32, 3) k_dct_mma(const uint2* __restrict__ frag, BatchView b,
+                                                                const float* __restrict__ db,
+                                                                const uint32_t* __restrict__ dbmax_key,
+                                                                float* __restrict__ mfcc_raw,
+                                                                double* __restrict__ sum, double* __restrict__ sumsq) {
+  constexpr int NM = kDctConstMels, NC = kDctConstMfcc;
+  __shared__ uint2 s_frag[kDctMmaFragWords / 2];
+  __shared__ float s_stage[kDct2Warps * 32 * NC];
+  for (int i = threadIdx.x; i < kDctMmaFragWords / 2; i += blockDim.x) s_frag[i] = __ldg(frag + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  float* s_o = s_stage + warp * 32 * NC;
+  const int64_t n_tiles = (b.total_frames + 31) / 32;
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * kDct2Warps + warp; tile < n_tiles;
+       tile += static_cast<int64_t>(gridDim.x) * kDct2Warps) {
+    const int64_t g0 = tile * 32;
+    const int nf = static_cast<int>(min(static_cast<int64_t>(32), b.total_frames - g0));
+    const bool valid = lane < nf;
+    const int clip = valid ? find_segment(b.frame_off, b.n_clips, g0 + lane) : -1;
+    const float floor_db = valid ? key_float(__ldg(dbmax_key + clip)) - 80.0f : 0.0f;   // of row `lane`
+    // the four rows this lane feeds: g, g + 8 (row tile 0), g + 16, g + 24 (row tile 1)
+    float fl[4];
+    const float* rowp[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = g + 8 * q;
+      fl[q] = __shfl_sync(0xffffffffu, floor_db, r);
+      rowp[q] = db + (g0 + (r < nf ? r : 0)) * NM + 2 * tq;     // rows beyond the batch re-read row 0 (discarded)
+    }
+    float acc[2][3][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < NM / 16; ++ks) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 x0 = __ldg(reinterpret_cast<const float2*>(rowp[q] + 16 * ks));        // k = 2 tq, 2 tq + 1
+        const float2 x1 = __ldg(reinterpret_cast<const float2*>(rowp[q] + 16 * ks + 8));    // k + 8
+        const float off = fl[q] + 40.0f;
+        const int mt = q >> 1, h = q & 1;        // fragment registers: a0 = (row g, k), a1 = (row g+8, k), a2 / a3 = k + 8
+        dct_split(fmaxf(x0.x, fl[q]) - off, fmaxf(x0.y, fl[q]) - off, ah[mt][h], al[mt][h]);
+        dct_split(fmaxf(x1.x, fl[q]) - off, fmaxf(x1.y, fl[q]) - off, ah[mt][h + 2], al[mt][h + 2]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const uint2 bh = s_frag[((ks * 3 + nt) * 2 + 0) * 32 + lane];
+        const uint2 bl = s_frag[((ks * 3 + nt) * 2 + 1) * 32 + lane];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          dct_mma_16816(acc[mt][nt], ah[mt], bh.x, bh.y);
+          dct_mma_16816(acc[mt][nt], ah[mt], bl.x, bl.y);
+          dct_mma_16816(acc[mt][nt], al[mt], bh.x, bh.y);
+        }
+      }
+    }
+    // accumulator (c0, c1) = (row g, columns 2 tq, 2 tq + 1) of the column tile, (c2, c3) = row g + 8
+    const float inv_scale = 1.0f / kDctMmaScale;
+    const float sum_row0 = 11.313708498984761f;                // sum_m D[0][m] = 128 / sqrt(128)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int q = 2 * mt + (c >> 1);
+          const int row = g + 8 * q, col = 8 * nt + 2 * tq + (c & 1);
+          float v = acc[mt][nt][c] * inv_scale;
+          if (col == 0) v = fmaf(fl[q] + 40.0f, sum_row0, v);
+          if (col < NC) s_o[row * NC + col] = row < nf ? v : 0.0f;
+        }
+    __syncwarp();
+    for (int i = lane; i < nf * NC; i += 32) mfcc_raw[g0 * NC + i] = s_o[i];
+    const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
+    const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
+    if (uniform) {
+      if (lane < NC && first_clip >= 0) {
+        double ts = 0.0, tq2 = 0.0;
+        for (int f = 0; f < nf; ++f) {
+          const double a = static_cast<double>(s_o[f * NC + lane]);
+          ts += a;
+          tq2 = fma(a, a, tq2);
+        }
+        atomicAdd(sum + static_cast<int64_t>(first_clip) * NC + lane, ts);
+        atomicAdd(sumsq + static_cast<int64_t>(first_clip) * NC + lane, tq2);
+      }
+    } else if (valid) {
+      for (int k = 0; k < NC; ++k) {
+        const double a = static_cast<double>(s_o[lane * NC + k]);
+        atomicAdd(sum + static_cast<int64_t>(clip) * NC + k, a);
+        atomicAdd(sumsq + static_cast<int64_t>(clip) * NC + k, a * a);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: CMVN -> Savitzky-Golay delta / delta-delta (width 9, edges = value at frame 4 / T-5)
 //     -> pair reduction.  Thread per (output row, channel).
 //     extract_features_utils.py:5-8,21-27,33-44; librosa.feature.delta == scipy savgol 'interp'.
@@ -1382,6 +1516,15 @@ int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, co
                    const DctCoef* coef) {
   if (t.n_mels > 128 || t.n_mfcc > 32) return -1;
   const int kp = t.n_mfcc <= 24 ? 24 : 32;
+  // default shape: the tensor-pipe kernel.  NSF_DCT_CONST=1 keeps the constant-bank FFMA kernel (validation / A-B timing)
+  static const bool force_const = std::getenv("NSF_DCT_CONST") != nullptr;
+  static const bool force_other = std::getenv("NSF_DCT_SMEM") != nullptr || std::getenv("NSF_DCT_TILE") != nullptr;
+  if (t.dct_frag && !force_const && !force_other && t.n_mels == kDctConstMels && t.n_mfcc == kDctConstMfcc) {
+    const int grid_m = grid_for((b.total_frames + 31) / 32, kDct2Warps, kSmCount * 3);
+    k_dct_mma<<<grid_m, kDct2Warps * 32, 0, s>>>(t.dct_frag, b, db, dbmax_key, mfcc_raw, sum, sumsq);
+    NSF_CHECK_LAUNCH();
+    return 1;
+  }
   // NSF_DCT_SMEM=1 keeps the shared-memory coefficient kernels for the default shape too (validation / A-B timing)
   static const bool force_smem = std::getenv("NSF_DCT_SMEM") != nullptr;
   if (coef && !force_smem && t.n_mels == kDctConstMels && t.n_mfcc == kDctConstMfcc) {

@@ -36,6 +36,7 @@ struct DeviceTables {
   const int32_t* mel_ptr;     // offset of the run's weights in mel_w
   const float* mel_w;
   const float* dct_t;         // [n_mels][32] transposed, zero padded
+  const uint2* dct_frag;      // DCT matrix x 2^10 as fp16 hi / lo MMA B fragments (k_dct_mma; default shape only, else NULL)
   // per power column of chain c (padded to whole 128-column tiles): {bits(m0), w[m0], w[m0+1], 0}.
   // A bin lies under at most two (adjacent) triangular mel filters; mel_col_ok == 0 if that ever fails.
   const float4* mel_col[2];
