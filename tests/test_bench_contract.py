@@ -49,6 +49,79 @@ def test_committed_bench_lines_follow_the_contract(path):
     assert p["mfcc_max_abs"] < 1e-3 and p["autocorr_max_abs"] < 2e-5
 
 
+R02 = [os.path.join(ROOT, "profiles", f) for f in ("bench_r02k_n1.json", "bench_r02i_n2.json", "bench_r02l_n4.json",
+                                                    "bench_r02l_n8.json")]
+
+
+@pytest.mark.parametrize("path", R02, ids=[os.path.basename(p) for p in R02])
+def test_round2_bench_lines_follow_the_contract(path):
+    d = _line(path)
+    assert REQUIRED <= set(d), REQUIRED - set(d)
+    n = d["n_gpus"]
+    assert d["metric"] == "audio_seconds_per_second" and d["unit"] == "audio-s/s" and d["higher_is_better"] is True
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32"
+    assert "workload" in d["config"] and "model" not in d["config"] and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert d["config"]["clips_per_gpu"] == 60 and d["config"]["clips_total"] == 60 * n
+    assert d["value"] == pytest.approx(d["config"]["audio_seconds_per_step"] / (d["ms_per_step"] * 1e-3), rel=1e-9)
+    for key in ("e2e", "e2e_f32_pcm"):
+        e = d[key]
+        assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] * 2 == d["e2e_f32_pcm"]["h2d_bytes_per_step"]        # int16 vs float32 PCM
+    c = d["copy_ceiling"]
+    assert c["h2d_bytes"] == d["e2e"]["h2d_bytes_per_step"] and c["ms_per_step"] > 0
+    assert c["e2e_frac_of_ceiling"] == pytest.approx(c["ms_per_step"] / d["e2e"]["ms_per_step"], rel=2e-3)
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=2e-3)
+    assert r["kernel"] == max(d["kernels"], key=lambda k: k["ms"])["kernel"] and (r["traffic"] is None or r["traffic"] > 0)
+    p = d["parity"]
+    assert p["mfcc_max_abs"] < 1e-4 and p["delta_max_abs"] < 2e-5 and p["autocorr_max_abs"] < 2e-5
+    assert d["api_e2e"]["value"] > 0 and "facial_csv_wait" in d["api_e2e"]["phases_ms"]
+    # the other BASELINE configurations ride in the same line
+    w = d["workloads"]
+    assert set(w) == {"c3", "c4", "c5"}
+    assert w["c3"]["scaling"] == "strong" and w["c3"]["clips_total"] == 60
+    assert w["c5"]["scaling"] == "strong" and w["c5"]["clips_total"] == 10000
+    assert w["c4"]["clips_this_rank"] == 60 and w["c4"]["clips_total"] == 60 * n
+    for x in w.values():
+        assert 0 < x["e2e"]["value"] < x["value"] and x["kernels"]
+    if n == 1:
+        cb = d["cpu_baseline"]
+        assert cb["kind"] == "port" and cb["threads_per_worker"] == 1 and cb["cores"] >= 1 and cb["value"] > 0
+        assert cb["value"] <= cb["value_busy_time"] * 1.05           # wall clock can only be slower than busy time
+        for name in ("c3", "c4"):
+            c3 = w[name]["cpu_baseline"]
+            assert c3["with_csv_cache_write"]["value"] < c3["value"]  # the CSV write costs the reference time
+        assert w["c5"]["cpu_baseline"]["value"] > 0
+    else:
+        g = w["c4"]["gathered_host_array"]
+        assert g["all_slices_filled"] is True and g["shape"] == [n * w["c4"]["collect_rows_this_rank"], 256]
+    if d.get("clocks"):
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_round2_reference_arm_is_consistent_per_core():
+    """The CPU oracle's per-core throughput must not depend on how bench.py was launched (round 1: 1.85x apart)."""
+    per_core = []
+    for f in ("bench_r02k_ref_n1.json", "bench_r02i_ref_n2.json", "bench_r02l_ref_n8.json"):
+        d = _line(os.path.join(ROOT, "profiles", f))
+        assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+        assert d["value"] == d["e2e"]["value"] == d["cpu_baseline"]["value"]
+        per_core.append(d["value"] / d["cpu_baseline"]["cores"])
+    assert max(per_core) / min(per_core) < 1.10, per_core
+
+
+def test_round2_scaling_lines():
+    lines = {n: _line(os.path.join(ROOT, "profiles", f)) for n, f in
+             ((1, "bench_r02k_n1.json"), (2, "bench_r02i_n2.json"), (4, "bench_r02l_n4.json"), (8, "bench_r02l_n8.json"))}
+    for n, d in lines.items():
+        assert d["n_gpus"] == n
+        assert d["value"] > 0.95 * n * lines[1]["value"]                  # device-resident: linear by clip
+        assert d["e2e"]["value"] >= lines[1]["e2e"]["value"]              # end to end: the shared host link
+    sp = _line(os.path.join(ROOT, "profiles", "bench_r02l_single_process_c4_n8.json"))
+    assert sp["gathered_host_array"]["single_process"] and sp["gathered_host_array"]["shape"] == [2994720, 256]
+    assert sp["gathered_host_array"]["all_slices_filled"] is True
+
+
 def test_weak_scaling_lines_are_consistent():
     lines = {n: _line(os.path.join(ROOT, "profiles", f"bench_r01g_n{n}.json")) for n in (1, 2, 4, 8)}
     for n, d in lines.items():
