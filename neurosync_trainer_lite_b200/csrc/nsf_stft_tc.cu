@@ -727,16 +727,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // (dm / d0 / d1) and applies them after the hand-shake with its partner (apply_deferred), so every element of
 // the mel tile still receives its contributions in a fixed order.
 struct MelDeferred { int m[2]; float s0[2], s1[2]; int n; };
+constexpr bool kDefaultRolledEpilogue = true;   // 0.653 -> 0.641 ms on C2, 2.13 -> 2.07 ms on C5 (round 2, r2o_ab)
 
-template <bool kUpper>
+// kRolled: the four 16-column chunks run as a ROLLED loop (one chunk body in the instruction stream instead of four:
+// the fully unrolled epilogue is ~2400 instructions per instantiation, ncu shows 19 % of the fused kernel's stall
+// samples as instruction-fetch starvation); the chunk in flight lands in a second register set that is copied over
+// the working set after the wait (32 moves per chunk).  Same arithmetic in the same order.
+template <bool kUpper, bool kRolled>
 __device__ __forceinline__ void mel_accumulate_half(uint32_t acc_addr, const float4* __restrict__ tab,
                                                     float* my_acc, float sc2, MelDeferred& def) {
   constexpr int kCols = BN / 2, kChunks = kCols / 16;
   constexpr int c0 = kUpper ? kCols : 0;
-  float re[2][16], im[2][16];
-  tmem_ld_32x16_async(acc_addr + c0, re[0]);
-  tmem_ld_32x16_async(acc_addr + BN + c0, im[0]);
-  tmem_wait_ld(re[0], im[0]);
   int cur_m = -1;
   float s0 = 0.0f, s1 = 0.0f;
   def.n = 0;
@@ -751,6 +752,47 @@ __device__ __forceinline__ void mel_accumulate_half(uint32_t acc_addr, const flo
       my_acc[cur_m + 1] += s1 * sc2;
     }
   };
+  if constexpr (kRolled) {
+    float re[16], im[16], nre[16], nim[16];
+    tmem_ld_32x16_async(acc_addr + c0, re);
+    tmem_ld_32x16_async(acc_addr + BN + c0, im);
+    tmem_wait_ld(re, im);
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+      if (c + 1 < kChunks) {
+        tmem_ld_32x16_async(acc_addr + c0 + 16 * (c + 1), nre);
+        tmem_ld_32x16_async(acc_addr + BN + c0 + 16 * (c + 1), nim);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 e[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) e[q] = __ldg(tab + c0 + 16 * c + 8 * h + q);     // warp-uniform addresses: broadcast
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int m0 = __float_as_int(e[q].x);
+          const float pw = fmaf(re[8 * h + q], re[8 * h + q], im[8 * h + q] * im[8 * h + q]);
+          if (m0 != cur_m) {                               // uniform branch
+            flush();
+            cur_m = m0; s0 = 0.0f; s1 = 0.0f;
+          }
+          s0 = fmaf(pw, e[q].y, s0);
+          s1 = fmaf(pw, e[q].z, s1);
+        }
+      }
+      if (c + 1 < kChunks) {
+        tmem_wait_ld(nre, nim);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { re[q] = nre[q]; im[q] = nim[q]; }
+      }
+    }
+    flush();
+    return;
+  }
+  float re[2][16], im[2][16];
+  tmem_ld_32x16_async(acc_addr + c0, re[0]);
+  tmem_ld_32x16_async(acc_addr + BN + c0, im[0]);
+  tmem_wait_ld(re[0], im[0]);
 #pragma unroll
   for (int c = 0; c < kChunks; ++c) {
     const int cur = c & 1, nxt = cur ^ 1;
@@ -807,6 +849,7 @@ constexpr size_t kMelTileBytes = (static_cast<size_t>(BM + 1) * kMelPitch * size
 constexpr size_t kFusedSmem = 1024 + static_cast<size_t>(kFStages) * kStageBytes +
                               kMelTileBytes + 256;
 
+template <bool kRolled>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               DeviceTables t, BatchView b, int64_t plane_rows, int kp, int np_ld,
@@ -930,8 +973,8 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
         tcgen05_fence_after();
         MelDeferred def;
-        if (upper) mel_accumulate_half<true>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
-        else mel_accumulate_half<false>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
+        if (upper) mel_accumulate_half<true, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
+        else mel_accumulate_half<false, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
         // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the routine)
         tcgen05_fence_before();
         __syncwarp();
@@ -1004,6 +1047,7 @@ constexpr int kPStageBytes = 2 * kPTileA + 2 * kPTileB;
 constexpr size_t kPairSmem = 1024 + static_cast<size_t>(kPStages) * kPStageBytes +
                              kMelTileBytes + 256;
 
+template <bool kRolled>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
 k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    DeviceTables t, BatchView b, int64_t plane_rows, int kp, int np_ld,
@@ -1131,8 +1175,8 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
         tcgen05_fence_after();
         MelDeferred def;
-        if (upper) mel_accumulate_half<true>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
-        else mel_accumulate_half<false>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
+        if (upper) mel_accumulate_half<true, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
+        else mel_accumulate_half<false, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
         // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the routine)
         tcgen05_fence_before();
         __syncwarp();
@@ -1328,6 +1372,11 @@ int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTable
   if (!encode_map(&map_a, v.planes, static_cast<uint64_t>(tc.chains) * 4 * v.rows, tc.kp, BM)) return -1;
   // NSF_STFT_1CTA=1 keeps the single-CTA kernel (validation / A-B timing)
   static const bool one_cta = std::getenv("NSF_STFT_1CTA") != nullptr;
+  // NSF_STFT_EPILOGUE=rolled|unrolled: the mel epilogue's chunk loop (A/B timing; identical results)
+  static const bool rolled = [] {
+    const char* v = std::getenv("NSF_STFT_EPILOGUE");
+    return v ? v[0] == 'r' : kDefaultRolledEpilogue;
+  }();
   // short K (16 kHz: two 64-column stages per accumulator) leaves the pair's longer hand-off exposed:
   // measured 3.31 vs 3.06 ms on the C5 batch, so pairs are used from four K stages on
   const int kblocks = (tc.kp + BK - 1) / BK;
@@ -1335,15 +1384,23 @@ int launch_stft_tc_mel(cudaStream_t s, const StftTcTables& tc, const DeviceTable
     int64_t pairs = v.rows / (2 * BM);
     if (pairs > 74) pairs = 74;
     if (pairs < 1) pairs = 1;
-    k_tc_stft_mel_pair<<<static_cast<unsigned>(2 * pairs), kFusedThreads, kPairSmem, s>>>(
-        map_a, tc.map_b_half, t, b, v.rows, tc.kp, tc.np_ld, v.row_exp, db, dbmax_key);
+    if (rolled)
+      k_tc_stft_mel_pair<true><<<static_cast<unsigned>(2 * pairs), kFusedThreads, kPairSmem, s>>>(
+          map_a, tc.map_b_half, t, b, v.rows, tc.kp, tc.np_ld, v.row_exp, db, dbmax_key);
+    else
+      k_tc_stft_mel_pair<false><<<static_cast<unsigned>(2 * pairs), kFusedThreads, kPairSmem, s>>>(
+          map_a, tc.map_b_half, t, b, v.rows, tc.kp, tc.np_ld, v.row_exp, db, dbmax_key);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
   int64_t grid = v.rows / BM;
   if (grid > 148) grid = 148;
   if (grid < 1) grid = 1;
-  k_tc_stft_mel<<<static_cast<unsigned>(grid), kFusedThreads, kFusedSmem, s>>>(map_a, tc.map_b, t, b, v.rows, tc.kp, tc.np_ld,
-                                                                            v.row_exp, db, dbmax_key);
+  if (rolled)
+    k_tc_stft_mel<true><<<static_cast<unsigned>(grid), kFusedThreads, kFusedSmem, s>>>(map_a, tc.map_b, t, b, v.rows, tc.kp,
+                                                                                   tc.np_ld, v.row_exp, db, dbmax_key);
+  else
+    k_tc_stft_mel<false><<<static_cast<unsigned>(grid), kFusedThreads, kFusedSmem, s>>>(map_a, tc.map_b, t, b, v.rows, tc.kp,
+                                                                                    tc.np_ld, v.row_exp, db, dbmax_key);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -1371,8 +1428,10 @@ bool init_stft_tc_attributes() {
   };
   set(k_tc_fold_r<2>, 220 * 1024); set(k_tc_fold_r<3>, 220 * 1024); set(k_tc_fold_r<4>, 220 * 1024);
   set(k_tc_fold_r<6>, 220 * 1024); set(k_tc_fold_r<8>, 220 * 1024); set(k_tc_fold, 220 * 1024);
-  set(k_tc_stft_mel_pair, static_cast<int>(kPairSmem));
-  set(k_tc_stft_mel, static_cast<int>(kFusedSmem));
+  set(k_tc_stft_mel_pair<false>, static_cast<int>(kPairSmem));
+  set(k_tc_stft_mel_pair<true>, static_cast<int>(kPairSmem));
+  set(k_tc_stft_mel<false>, static_cast<int>(kFusedSmem));
+  set(k_tc_stft_mel<true>, static_cast<int>(kFusedSmem));
   set(k_tc_gemm, static_cast<int>(kSmemBytes));
   return ok;
 }

@@ -161,3 +161,17 @@ def test_build_stamp_is_path_independent_and_build_is_locked(tmp_path, monkeypat
     assert b._digest() == here
     src = open(b.__file__).read()
     assert "fcntl.flock" in src and "os.replace(lib_tmp, LIB_PATH)" in src
+
+
+def test_chunk_count_matches_the_reference_loop(nv):
+    """nsf_chunk_count == the number of iterations of process_audio_features' while loop
+    (utils/audio/processing/audio_processing.py:62-84); invalid geometries give 0."""
+    for n in (1, 7, 50, 112, 113, 128, 129, 230, 240, 300, 1801):
+        for frame, overlap in ((128, 16), (64, 8), (128, 32), (64, 0)):
+            count, start = 0, 0
+            while start < n:
+                count += 1
+                start += frame - overlap
+            assert nv.lib.nsf_chunk_count(n, frame, overlap) == count
+    assert nv.lib.nsf_chunk_count(0, 128, 16) == 0 and nv.lib.nsf_chunk_count(10, 16, 16) == 0
+    assert nv.lib.nsf_chunk_count(10, 0, 0) == 0 and nv.lib.nsf_chunk_count(10, 16, -1) == 0
