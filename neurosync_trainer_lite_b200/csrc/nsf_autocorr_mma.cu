@@ -34,6 +34,8 @@ constexpr int kSmCount = 148;
 constexpr int kFrontMargin = 16;   // halfs of zeros before X(0)  (B reads back to X(-7))
 constexpr int kBackMargin = 160;   // halfs of zeros after the last K-block (the A prefetch of one block beyond reads up to +151)
 constexpr int kVals = 6;           // lags per thread that can be <= 191
+constexpr int kExtraFront = 112;   // halfs of zeros in front of every warp's copies: the five-tile loop (am_mma5)
+                                   // reads A fragments of the blocks m = -8 .. -1, i.e. back to X(-128)
 
 struct AmGeom { int nblk; int nblk4; int len; };   // K-blocks that hold samples, rounded up to a multiple of 4, halfs per copy
 __host__ __device__ inline AmGeom am_geom(int F) {
@@ -325,6 +327,123 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   __syncwarp();
 }
 
+// Five MMAs per K-block instead of six (round 2, the product loop).  With x = h + l (fp16 each)
+//     r[lag] = HH[lag] + C[lag] + C[-lag],   HH[lag] = sum_s h(s + lag) h(s),   C[lag] = sum_s h(s + lag) l(s),
+// because sum_s l(s + lag) h(s) = C[-lag]: the two cross products are ONE cross-correlation seen at both signs of the
+// lag.  am_mma computes them as two products of two tiles each (A_h x B_l and A_l x B_h: 4 MMAs for 2 x 256 lag slots
+// of which 2 x 188 are used); here C[-192 .. 191] comes from THREE tiles that all take the A_h fragment of the block:
+//     tile (A_h(m), B_p(m'))  ->  lags 16 (m - m') + 8 i + j
+//     cC: B_l(m + 12) -> [-192, -65]     cA: B_l(m + 4) -> [-64, 63]     cB: B_l(m - 4) -> [64, 191]
+// (383 of 384 slots used) next to hh0: B_h(m) -> [0, 127] and hh1: B_h(m - 4) -> [64, 191] as before.  The A_l
+// fragment is never loaded: one ldmatrix.x4 and four 32-bit loads per five MMAs (8 shared-memory wavefronts per block
+// instead of 12).  The B_l fragments live in a ring of sixteen blocks (loaded twelve blocks ahead of their A block,
+// last used four blocks behind it), the B_h fragments in a ring of eight; both rings are indexed by compile-time
+// constants inside a body unrolled sixteen times, so nothing is ever copied.  Blocks m = -8 .. -1 (A rows that start
+// before the frame but end inside it) only feed cC and cA and read zeros from kExtraFront; the tiles whose B block lies
+// beyond the frame are skipped at the far end, so a frame costs 5 nblk - 12 MMAs.
+__device__ __forceinline__ void am_mma5(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
+  const uint32_t* E_lo = E_hi + geo.len / 2;
+  const uint32_t* O_hi = E_lo + geo.len / 2;
+  const uint32_t* O_lo = O_hi + geo.len / 2;
+  const int mi = lane >> 3, mr = lane & 7;
+  const uint32_t a_off = 2u * static_cast<uint32_t>(kFrontMargin + 8 * mr + (mi & 1) * 64 + (mi >> 1) * 8);
+  const uint32_t sa0 = am_smem_u32(copies) + a_off;               // A_h(0); block m is 32 m bytes further
+  const int boff = kFrontMargin + 2 * tq - g - (g & 1);
+  const uint32_t* Bh = ((g & 1) ? O_hi : E_hi) + boff / 2;        // block m': words 8 m' (k = 2 tq, +1) and 8 m' + 4 (k + 8)
+  const uint32_t* Bl = ((g & 1) ? O_lo : E_lo) + boff / 2;
+  const int nblk = geo.nblk;
+
+  float hh0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, hh1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float cA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cB[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cC[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  uint32_t bh[8][2], bl[16][2];                 // slot = block index mod 8 / mod 16
+#pragma unroll
+  for (int q = 4; q < 8; ++q) bh[q][0] = bh[q][1] = 0u;          // B_h(-4 .. -1): zeros
+#pragma unroll
+  for (int q = 12; q < 16; ++q) bl[q][0] = bl[q][1] = 0u;        // B_l(-4 .. -1): zeros
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { bl[q][0] = Bl[8 * q]; bl[q][1] = Bl[8 * q + 4]; }   // B_l(0 .. 3) (zero margin beyond the frame)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) bh[q][0] = bh[q][1] = 0u;          // overwritten before use; keeps the compiler quiet
+#pragma unroll
+  for (int q = 4; q < 12; ++q) bl[q][0] = bl[q][1] = 0u;
+
+  uint32_t a[4], an[4];
+  // lead-in: m = -8 .. -1
+  ldsm_x4(sa0 - 32u * 8u, a);
+#pragma unroll
+  for (int q = 8; q < 16; ++q) {
+    const int m = q - 16;
+    ldsm_x4(sa0 + static_cast<uint32_t>(32 * (m + 1)), an);      // m = -1 prefetches A_h(0)
+    if (m + 12 < nblk) {
+      bl[(q + 12) & 15][0] = Bl[8 * (m + 12)];
+      bl[(q + 12) & 15][1] = Bl[8 * (m + 12) + 4];
+    }
+    if (m >= -4 && m + 4 < nblk) mma_16816(cA, a[0], a[1], a[2], a[3], bl[(q + 4) & 15][0], bl[(q + 4) & 15][1]);
+    if (m + 12 < nblk) mma_16816(cC, a[0], a[1], a[2], a[3], bl[(q + 12) & 15][0], bl[(q + 12) & 15][1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = an[i];
+  }
+  // main loop: groups of sixteen blocks; `fast` groups need no range checks
+  uint32_t sa = sa0;                                              // address of A_h(m0)
+#pragma unroll 1
+  for (int m0 = 0; m0 < nblk; m0 += 16, sa += 32u * 16u) {
+    const uint32_t* pbh = Bh + 8 * m0;
+    const uint32_t* pbl = Bl + 8 * m0;
+    if (m0 + 27 < nblk) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        ldsm_x4(sa + static_cast<uint32_t>(32 * (q + 1)), an);
+        bh[q & 7][0] = pbh[8 * q]; bh[q & 7][1] = pbh[8 * q + 4];
+        mma_16816(cB, a[0], a[1], a[2], a[3], bl[(q + 12) & 15][0], bl[(q + 12) & 15][1]);   // B_l(m - 4)
+        bl[(q + 12) & 15][0] = pbl[8 * (q + 12)]; bl[(q + 12) & 15][1] = pbl[8 * (q + 12) + 4];   // <- B_l(m + 12)
+        mma_16816(hh1, a[0], a[1], a[2], a[3], bh[(q + 4) & 7][0], bh[(q + 4) & 7][1]);      // B_h(m - 4)
+        mma_16816(cA, a[0], a[1], a[2], a[3], bl[(q + 4) & 15][0], bl[(q + 4) & 15][1]);     // B_l(m + 4)
+        mma_16816(hh0, a[0], a[1], a[2], a[3], bh[q & 7][0], bh[q & 7][1]);                  // B_h(m)
+        mma_16816(cC, a[0], a[1], a[2], a[3], bl[(q + 12) & 15][0], bl[(q + 12) & 15][1]);   // B_l(m + 12)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = an[i];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int m = m0 + q;
+        if (m >= nblk) break;
+        ldsm_x4(sa + static_cast<uint32_t>(32 * (q + 1)), an);    // one block beyond the last reads the zero margin
+        bh[q & 7][0] = pbh[8 * q]; bh[q & 7][1] = pbh[8 * q + 4];
+        mma_16816(cB, a[0], a[1], a[2], a[3], bl[(q + 12) & 15][0], bl[(q + 12) & 15][1]);
+        if (m + 12 < nblk) { bl[(q + 12) & 15][0] = pbl[8 * (q + 12)]; bl[(q + 12) & 15][1] = pbl[8 * (q + 12) + 4]; }
+        mma_16816(hh1, a[0], a[1], a[2], a[3], bh[(q + 4) & 7][0], bh[(q + 4) & 7][1]);
+        if (m + 4 < nblk) mma_16816(cA, a[0], a[1], a[2], a[3], bl[(q + 4) & 15][0], bl[(q + 4) & 15][1]);
+        mma_16816(hh0, a[0], a[1], a[2], a[3], bh[q & 7][0], bh[q & 7][1]);
+        if (m + 12 < nblk) mma_16816(cC, a[0], a[1], a[2], a[3], bl[(q + 12) & 15][0], bl[(q + 12) & 15][1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = an[i];
+      }
+    }
+  }
+  // Lane (g, tq) holds rows g (c0, c1) and g + 8 (c2, c3), columns 2 tq, 2 tq + 1 of every tile.  With u = 8 g + 2 tq + e:
+  //   hh0: u, 64 + u    hh1: (64 + u), 128 + u    cA: -64 + u, u    cB: 64 + u, 128 + u    cC: -192 + u, -128 + u
+  // C[-(64 k + u)] = entry 64 - u of the tile that starts at -64 (k + 1): for odd u that is lane 31 - L (same e), for
+  // even u lane 32 - L - and for L = 0 (u = 0) the first entry of the NEXT tile, which lane 0 holds itself.
+  const int src_e = (32 - lane) & 31, src_o = 31 - lane;
+  float n0e = __shfl_sync(0xffffffffu, cA[0], src_e), n0o = __shfl_sync(0xffffffffu, cA[1], src_o);
+  float n1e = __shfl_sync(0xffffffffu, cC[2], src_e), n1o = __shfl_sync(0xffffffffu, cC[3], src_o);
+  float n2e = __shfl_sync(0xffffffffu, cC[0], src_e), n2o = __shfl_sync(0xffffffffu, cC[1], src_o);
+  if (lane == 0) { n0e = cA[2]; n1e = cA[0]; n2e = cC[2]; }
+  val[0] = hh0[0] + (cA[2] + n0e); val[1] = hh0[1] + (cA[3] + n0o);
+  val[2] = hh0[2] + (cB[0] + n1e); val[3] = hh0[3] + (cB[1] + n1o);
+  val[4] = hh1[2] + (cB[2] + n2e); val[5] = hh1[3] + (cB[3] + n2o);
+  const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
+  if (r0 != 0.0f) {
+    const float inv = __fdiv_rn(1.0f, r0);
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) val[v] *= inv;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane, int n_lags, float thr) {
   bool small = true;
 #pragma unroll
@@ -472,7 +591,16 @@ __global__ void __launch_bounds__(kAmPairs * 64, 2) k_autocorr_mma(DeviceTables 
 // ------------------------------------------------------------------------------------------------
 constexpr int kSymWarps = 8;       // per block, two blocks per SM
 
-template <int kIters, bool kExact>
+#ifdef NSF_AC_TRACE
+// Debug build only (scripts/build_variant.sh ... -DNSF_AC_TRACE): per warp, the SM clock at the start of the staging
+// half, the start and the end of the MMA loop of its first kTraceFrames frames; read back with nsf_debug_ac_trace.
+constexpr int kTraceFrames = 40;
+__device__ long long g_ac_trace[296 * 8 * kTraceFrames * 3];
+__device__ int g_ac_smid[296];
+#endif
+
+// kFive: the five-tile loop am_mma5 (product path) instead of the six-MMA loop am_mma (NSF_AC_LOOP=six, validation).
+template <int kIters, bool kExact, bool kFive>
 __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables t, BatchView b,
                                                                     const float* __restrict__ y, bool reduce,
                                                                     float* __restrict__ out, int64_t out_ld, int col0) {
@@ -480,18 +608,23 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
   const AmGeom geo = am_geom(t.F);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_warps = static_cast<int>(blockDim.x >> 5);
-  __half* copies = s_am + static_cast<size_t>(warp) * 4 * geo.len;
-  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(n_warps) * 4 * geo.len);
+  const size_t region = kExtraFront + 4 * static_cast<size_t>(geo.len);   // halfs per warp: [zeros | E_hi | E_lo | O_hi | O_lo]
+  __half* copies = s_am + static_cast<size_t>(warp) * region + kExtraFront;
+  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(n_warps) * region);
   const int n_it = (t.F / 2 + 1 + 31) / 32;
   for (int n = threadIdx.x; n < 64 * n_it; n += blockDim.x) hann[n] = n < t.F ? __ldg(t.hann_sym + n) : 0.0f;
   // zero once: the margins are never written again, the frame region is rewritten per frame
-  for (int i = lane; i < 4 * geo.len / 2; i += 32) reinterpret_cast<uint32_t*>(copies)[i] = 0u;
+  for (int i = lane; i < static_cast<int>(region / 2); i += 32) reinterpret_cast<uint32_t*>(copies - kExtraFront)[i] = 0u;
   __syncthreads();
   const int64_t n_warps_total = static_cast<int64_t>(gridDim.x) * n_warps;
   const int64_t chunk = (b.total_rows + n_warps_total - 1) / n_warps_total;
   const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * n_warps + warp) * chunk;
   const int64_t r_end = min(r_begin + chunk, b.total_rows);
   int64_t base = 0, len = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
+#ifdef NSF_AC_TRACE
+  int trace_i = 0;
+  if (threadIdx.x == 0 && blockIdx.x < 296) { int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_ac_smid[blockIdx.x] = sm; }
+#endif
   for (int64_t r = r_begin; r < r_end; ++r) {
     if (r >= clip_row_end) {
       const int clip = find_segment(b.row_off, b.n_clips, r);
@@ -510,6 +643,11 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
     for (int f = 0; f < n_frames; ++f) {
       const int64_t tf = tf0 + f;
       const AmSrc src = am_src(t, b, y, base, len, tf, n_it);
+#ifdef NSF_AC_TRACE
+      const bool tr = lane == 0 && trace_i < kTraceFrames && blockIdx.x < 296 && warp < 8;
+      long long* trp = g_ac_trace + ((static_cast<size_t>(blockIdx.x) * 8 + warp) * kTraceFrames + trace_i) * 3;
+      if (tr) trp[0] = clock64();
+#endif
       if (src.fast) {
         float v0[kIters], v1[kIters];
         am_issue_fast<kIters, kExact>(src.clip + src.first, n_it, lane, v0, v1);
@@ -517,11 +655,20 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
       } else {
         am_fill_simple(t, hann, src, copies, geo, lane);
       }                                                   // both end with __syncwarp
+#ifdef NSF_AC_TRACE
+      if (tr) trp[1] = clock64();
+#endif
       float val[kVals];
-      am_mma(copies, geo, lane, val);                     // ends with __syncwarp: the buffer may be rewritten
+      if (kFive) am_mma5(copies, geo, lane, val);         // both end with __syncwarp: the buffer may be rewritten
+      else am_mma(copies, geo, lane, val);
+#ifdef NSF_AC_TRACE
+      if (tr) trp[2] = clock64();
+      ++trace_i;
+#endif
       if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
         am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
-        am_mma(copies, geo, lane, val);
+        if (kFive) am_mma5(copies, geo, lane, val);
+        else am_mma(copies, geo, lane, val);
       }
 #pragma unroll
       for (int v = 0; v < kVals; ++v) acc[v] += val[v];
@@ -549,12 +696,22 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
     const char* v = std::getenv("NSF_AC_KERNEL");
     return v != nullptr && v[0] == 'p';
   }();
-  // symmetric kernel: as many warps per block as fit twice per SM (eight up to F ~ 1530, fewer for long frames)
+  // MMA loop of the symmetric kernel: the five-tile loop (am_mma5) for frames of at least 44 K-blocks (F >= 689:
+  // 44.1 kHz and up), where most blocks run in its unchecked body; the six-MMA loop (am_mma) for short frames, where the
+  // eight lead-in blocks and the range checks of the five-tile loop cost more than the MMAs it saves (B200, F = 266:
+  // 3.35 vs 3.12 ms on C5; F = 1470: 1.11 vs 1.24 ms on C2).  NSF_AC_LOOP=five / six forces one (validation, A/B).
+  static const int loop_env = [] {
+    const char* v = std::getenv("NSF_AC_LOOP");
+    return v == nullptr ? 0 : (v[0] == 's' ? 6 : (v[0] == 'f' ? 5 : 0));
+  }();
+  const bool use_six = loop_env == 6 || (loop_env == 0 && geo.nblk < 44);
+  // symmetric kernel: as many warps per block as fit twice per SM (eight up to F ~ 1530, fewer for long frames);
+  // two blocks of 113 KB (+ 1 KB reserved each) are what an SM's 228 KB hold
   int warps = kSymWarps;
   size_t sym_smem = 0;
   for (; warps >= 1; --warps) {
-    sym_smem = static_cast<size_t>(warps) * 4 * geo.len * sizeof(__half) + hann_bytes;
-    if (sym_smem <= (warps > 2 ? 110 : 220) * 1024) break;      // long frames: one block per SM
+    sym_smem = static_cast<size_t>(warps) * (kExtraFront + 4 * static_cast<size_t>(geo.len)) * sizeof(__half) + hann_bytes;
+    if (sym_smem <= (warps > 2 ? 113 : 220) * 1024) break;      // long frames: one block per SM
   }
   // pairs kernel: four (consumer, producer) pairs per block when their eight frame buffers fit, else three or two
   int pairs = kAmPairs;
@@ -568,7 +725,7 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   int64_t grid;
   int threads;
   if (sym) {
-    const int per_sm = sym_smem <= 110 * 1024 ? 2 : 1;
+    const int per_sm = sym_smem <= 113 * 1024 ? 2 : 1;
     grid = (b.total_rows + warps - 1) / warps;
     if (grid > static_cast<int64_t>(kSmCount) * per_sm) grid = static_cast<int64_t>(kSmCount) * per_sm;
     threads = warps * 32;
@@ -582,18 +739,21 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
     threads = pairs * 64;
   }
   if (grid < 1) grid = 1;
-  auto go = [&](auto k_sym, auto k_pairs) {
-    if (sym) k_sym<<<static_cast<int>(grid), threads, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+  auto go = [&](auto k_five, auto k_six, auto k_pairs) {
+    if (sym && !use_six) k_five<<<static_cast<int>(grid), threads, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+    else if (sym) k_six<<<static_cast<int>(grid), threads, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     else k_pairs<<<static_cast<int>(grid), threads, smem, s>>>(t, b, y, reduce, out, out_ld, col0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   };
-  if (iters == 23) return go(k_autocorr_sym<23, true>, k_autocorr_mma<23, true>);    // 88.2 kHz: F = 1470
-  if (iters == 5) return go(k_autocorr_sym<5, true>, k_autocorr_mma<5, true>);      // 16 kHz: F = 266
-  if (iters <= 6) return go(k_autocorr_sym<6, false>, k_autocorr_mma<6, false>);    // F <= 382   (22.05 kHz: 367)
-  if (iters <= 12) return go(k_autocorr_sym<12, false>, k_autocorr_mma<12, false>); // F <= 766   (44.1 kHz: 735)
-  if (iters <= 24) return go(k_autocorr_sym<24, false>, k_autocorr_mma<24, false>); // F <= 1534  (48 kHz: 800)
-  if (iters <= 40) return go(k_autocorr_sym<40, false>, k_autocorr_mma<40, false>); // F <= 2558
-  return go(k_autocorr_sym<66, false>, k_autocorr_mma<66, false>);                  // F <= 4096  (plan limit)
+#define NSF_AC_GO(IT, EX) go(k_autocorr_sym<IT, EX, true>, k_autocorr_sym<IT, EX, false>, k_autocorr_mma<IT, EX>)
+  if (iters == 23) return NSF_AC_GO(23, true);    // 88.2 kHz: F = 1470
+  if (iters == 5) return NSF_AC_GO(5, true);      // 16 kHz: F = 266
+  if (iters <= 6) return NSF_AC_GO(6, false);     // F <= 382   (22.05 kHz: 367)
+  if (iters <= 12) return NSF_AC_GO(12, false);   // F <= 766   (44.1 kHz: 735)
+  if (iters <= 24) return NSF_AC_GO(24, false);   // F <= 1534  (48 kHz: 800)
+  if (iters <= 40) return NSF_AC_GO(40, false);   // F <= 2558
+  return NSF_AC_GO(66, false);                    // F <= 4096  (plan limit)
+#undef NSF_AC_GO
 }
 
 // Opt-in shared-memory limit of every instantiation, once per device (called by nsf_ctx_create after
@@ -606,10 +766,20 @@ bool init_autocorr_mma_attributes() {
   set(k_autocorr_mma<23, true>); set(k_autocorr_mma<5, true>); set(k_autocorr_mma<6, false>);
   set(k_autocorr_mma<12, false>); set(k_autocorr_mma<24, false>); set(k_autocorr_mma<40, false>);
   set(k_autocorr_mma<66, false>);
-  set(k_autocorr_sym<23, true>); set(k_autocorr_sym<5, true>); set(k_autocorr_sym<6, false>);
-  set(k_autocorr_sym<12, false>); set(k_autocorr_sym<24, false>); set(k_autocorr_sym<40, false>);
-  set(k_autocorr_sym<66, false>);
+#define NSF_AC_SET(IT, EX) set(k_autocorr_sym<IT, EX, true>); set(k_autocorr_sym<IT, EX, false>)
+  NSF_AC_SET(23, true); NSF_AC_SET(5, true); NSF_AC_SET(6, false); NSF_AC_SET(12, false);
+  NSF_AC_SET(24, false); NSF_AC_SET(40, false); NSF_AC_SET(66, false);
+#undef NSF_AC_SET
   return ok;
 }
 
 }  // namespace nsf
+
+#ifdef NSF_AC_TRACE
+extern "C" __attribute__((visibility("default"))) int nsf_debug_ac_trace(long long* trace, int* smid) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(trace, nsf::g_ac_trace, sizeof(nsf::g_ac_trace)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(smid, nsf::g_ac_smid, sizeof(nsf::g_ac_smid)) != cudaSuccess) return -1;
+  return nsf::kTraceFrames;
+}
+#endif

@@ -180,3 +180,49 @@ def test_back_to_back_device_calls_do_not_share_descriptor_staging(engine, oracl
         assert got.shape == want.shape
         d = np.abs(got - want)
         assert d[:, :23].max() <= TOL_MFCC and d[:, 23:69].max() <= TOL_DELTA and d[:, 69:].max() <= TOL_AC
+
+
+# ---- the two MMA loops of the autocorrelation kernel (five tiles / six MMAs per K-block) ---------------------------
+@pytest.mark.parametrize("sr", [16000, 44100, 88200])
+def test_autocorr_loops_agree(sr, engine, oracle, tmp_path):
+    """k_autocorr_sym runs the five-tile loop (am_mma5: HH + C[lag] + C[-lag], A_l never loaded) for F >= 689 and the
+    six-MMA loop (am_mma) below; NSF_AC_LOOP forces one.  Same products, another summation order: the two agree to
+    2e-6 on the autocorrelation columns (identical MFCC columns) and each is within TOL_AC of the oracle - ragged
+    batch whose clips include the shortest legal one, an odd frame count and near-silent edge frames."""
+    import subprocess
+    import sys
+    F, H = oracle.frame_params(sr)
+    lens = [9 * H + 3, 2 * sr + 17, sr // 2, 33 * H, 3 * sr // 2 + F]
+    clips = []
+    for i, n in enumerate(lens):
+        c = synth.synth_clip(n / sr + 0.01, sr, seed=900 + i, kind=("voiced", "gated", "noise")[i % 3])[:n].copy()
+        if i == 1:
+            c[: 2 * F] *= 1e-6          # near-silent first frames: the edge-frame fix is exercised
+        clips.append(c)
+    y = np.concatenate(clips).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in clips])]).astype(np.int64)
+    np.save(tmp_path / "y.npy", y)
+    np.save(tmp_path / "off.npy", off)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for loop in ("five", "six"):
+        out = tmp_path / (loop + ".npy")
+        code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+                "from neurosync_trainer_lite_b200 import engine\n"
+                "y, off = np.load(%r), np.load(%r)\n"
+                "np.save(%r, engine.get_engine(%d, %d, %d).extract_host(y, off, 0))\n"
+                % (root, str(tmp_path / "y.npy"), str(tmp_path / "off.npy"), str(out), sr, F, H))
+        subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, NSF_AC_LOOP=loop), timeout=600)
+        res[loop] = np.load(out)
+    assert res["five"].shape == res["six"].shape and res["five"].shape[0] > 0
+    assert np.array_equal(res["five"][:, :69], res["six"][:, :69])
+    assert np.abs(res["five"][:, 69:] - res["six"][:, 69:]).max() <= 2e-6
+    default = engine.get_engine(sr, F, H).extract_host(y, off, 0)
+    assert np.array_equal(default, res["five" if F >= 689 else "six"])      # the automatic choice
+    roff = engine.get_engine(sr, F, H).row_offsets(off)
+    for i, c in enumerate(clips):
+        want = oracle.extract_and_combine_features(c, sr, F, H)
+        for loop in ("five", "six"):
+            got = res[loop][roff[i]:roff[i + 1]]
+            assert got.shape == want.shape
+            assert np.abs(got[:, 69:] - want[:, 69:]).max() <= TOL_AC, (loop, i)
