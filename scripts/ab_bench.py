@@ -21,14 +21,15 @@ def child(workload):
     import torch
     import bench
     from neurosync_trainer_lite_b200 import engine
-    sr, Fr, Hr, n_clips, seconds, _ = bench.WORKLOADS[workload]
+    w = bench.WORKLOADS[workload]
+    sr, Fr, Hr = w["sr"], w["F"], w["H"]
     eng = engine.get_engine(sr, Fr, Hr, device=0)
-    packed, off, base = bench.make_inputs(workload, 0)
+    packed, off, base, _mine, _n = bench.make_inputs(workload, 0, 1, "weak")
     dev = torch.device("cuda", 0)
     pcm = torch.from_numpy(packed).to(dev)
     rows = int(eng.row_offsets(off)[-1])
     out = torch.empty((rows, 256), dtype=torch.float32, device=dev)
-    ws = torch.empty(eng.workspace_bytes(len(packed), n_clips), dtype=torch.uint8, device=dev)
+    ws = torch.empty(eng.workspace_bytes(len(packed), len(off) - 1), dtype=torch.uint8, device=dev)
     for _ in range(3):
         eng.extract_device(pcm, off, 0, out=out, workspace=ws)
     torch.cuda.synchronize()
@@ -52,7 +53,8 @@ def child(workload):
     want = fo.extract_and_combine_features(base[0], sr, Fr, Hr)
     d = np.abs(got - want)
     print(json.dumps({"ms": round(ms, 4), "stages": {k: round(v, 4) for k, v in acc.items() if v > 0},
-                      "mfcc_err": float(d[:, :69].max()), "ac_err": float(d[:, 69:].max())}))
+                      "mfcc_err": float(d[:, :23].max()), "delta_err": float(d[:, 23:69].max()),
+                      "ac_err": float(d[:, 69:].max()), "checksum": float(out[::997].abs().sum().item())}))
 
 
 def main():
