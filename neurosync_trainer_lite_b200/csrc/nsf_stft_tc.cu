@@ -289,6 +289,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
 // Where hop-frame g lives: its clip, the index of its first sample relative to the clip (negative /
 // beyond the end = zero padding) and whether a 16-byte aligned superset of it can be bulk-copied.
 struct FrameRef {
+  int clip;
   int64_t base, first, len;
   const float* aligned;   // 16-byte aligned start of the bulk copy (fast path only)
   uint32_t bytes;         // multiple of 16
@@ -298,7 +299,14 @@ struct FrameRef {
 
 // Clip descriptor of the frame run a warp is walking: refreshed only when the run enters the next clip
 // (the lookup is a chain of dependent loads).
-struct ClipCache { int64_t f0 = 0, f_end = -1, base = 0, len = 0; };
+struct ClipCache { int64_t f0 = 0, f_end = -1, base = 0, len = 0; int clip = 0; };
+
+// One int32 per hop-frame travels from the fold kernel to the GEMM epilogues: the frame's power-of-two exponent
+// (|e| <= 100) in the low byte and the index of its clip above it, so the epilogue that needs the clip for the
+// per-clip dB maximum does not repeat the binary search (14 dependent loads per row for a 10 000-clip batch).
+__device__ __forceinline__ int32_t pack_row_info(int clip, int e2) { return (clip << 8) | (e2 & 0xff); }
+__device__ __forceinline__ int row_info_exp(int32_t v) { return (v << 24) >> 24; }
+__device__ __forceinline__ int row_info_clip(int32_t v) { return v >> 8; }
 
 __device__ __forceinline__ FrameRef locate_frame(const DeviceTables& t, const BatchView& b, const float* y, int64_t g,
                                                  ClipCache& cc) {
@@ -309,8 +317,10 @@ __device__ __forceinline__ FrameRef locate_frame(const DeviceTables& t, const Ba
     cc.f_end = __ldg(b.frame_off + clip + 1);
     cc.base = __ldg(b.clip_off + clip);
     cc.len = __ldg(b.clip_off + clip + 1) - cc.base;
+    cc.clip = clip;
   }
   const int64_t tf = g - cc.f0;
+  r.clip = cc.clip;
   r.base = cc.base;
   r.len = cc.len;
   r.first = tf * t.H - t.pad;
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_tc_fold(DeviceTables t, Bat
       e2 = max(-100, min(100, e2));
     }
     const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
-    if (lane == 0) row_exp[g] = e2;
+    if (lane == 0) row_exp[g] = pack_row_info(cur.clip, e2);
     // eight planes, one half2 store each: base pointer and plane stride hoisted, the (chain, part)
     // loop fully unrolled (planes of the absent chain of an odd F are simply skipped)
     __half2* dst0 = reinterpret_cast<__half2*>(planes + g * kp) + lane;
@@ -557,7 +567,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_tc_fold_r(DeviceTables t, B
       e2 = max(-100, min(100, e2));
     }
     const float scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
-    if (lane == 0) row_exp[g] = e2;
+    if (lane == 0) row_exp[g] = pack_row_info(cur.clip, e2);
     // pass 2: scale, split, store (eight planes, one half2 store each)
     __half2* dst0 = reinterpret_cast<__half2*>(planes + g * kp) + lane;
 #pragma unroll
@@ -677,7 +687,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     tcgen05_fence_after();
     const int64_t g = g0 + quarter * 32 + lane;
     const bool row_ok = g < total_frames;
-    const float sc = row_ok ? ldexpf(1.0f, -(__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+    const float sc = row_ok ? ldexpf(1.0f, -(row_info_exp(__ldg(row_exp + g)) + kTcBScaleExp)) : 0.0f;
     const int col_base = (chain == 0 ? 0 : col_off1) + n0;
     float* out_row = power + (row_ok ? g : 0) * bins_ld + col_base;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -733,9 +743,12 @@ constexpr bool kDefaultRolledEpilogue = true;   // 0.653 -> 0.641 ms on C2, 2.13
 // the fully unrolled epilogue is ~2400 instructions per instantiation, ncu shows 19 % of the fused kernel's stall
 // samples as instruction-fetch starvation); the chunk in flight lands in a second register set that is copied over
 // the working set after the wait (32 moves per chunk).  Same arithmetic in the same order.
+// c_begin, c_end (rolled loop only): the 16-column chunks this warp walks.  The callers split the LIVE chunks of the
+// sub-tile between the two warps (67 of 128 columns hold bins at F = 266: chunks 0-2 and 3-4 instead of four chunks
+// each, of which the upper warp's were 61 / 64 padding); the unrolled variant keeps the fixed 4 + 4 split.
 template <bool kUpper, bool kRolled>
 __device__ __forceinline__ void mel_accumulate_half(uint32_t acc_addr, const float4* __restrict__ tab,
-                                                    float* my_acc, float sc2, MelDeferred& def) {
+                                                    float* my_acc, float sc2, MelDeferred& def, int c_begin, int c_end) {
   constexpr int kCols = BN / 2, kChunks = kCols / 16;
   constexpr int c0 = kUpper ? kCols : 0;
   int cur_m = -1;
@@ -753,21 +766,22 @@ __device__ __forceinline__ void mel_accumulate_half(uint32_t acc_addr, const flo
     }
   };
   if constexpr (kRolled) {
+    if (c_begin >= c_end) return;
     float re[16], im[16], nre[16], nim[16];
-    tmem_ld_32x16_async(acc_addr + c0, re);
-    tmem_ld_32x16_async(acc_addr + BN + c0, im);
+    tmem_ld_32x16_async(acc_addr + 16 * c_begin, re);
+    tmem_ld_32x16_async(acc_addr + BN + 16 * c_begin, im);
     tmem_wait_ld(re, im);
 #pragma unroll 1
-    for (int c = 0; c < kChunks; ++c) {
-      if (c + 1 < kChunks) {
-        tmem_ld_32x16_async(acc_addr + c0 + 16 * (c + 1), nre);
-        tmem_ld_32x16_async(acc_addr + BN + c0 + 16 * (c + 1), nim);
+    for (int c = c_begin; c < c_end; ++c) {
+      if (c + 1 < c_end) {
+        tmem_ld_32x16_async(acc_addr + 16 * (c + 1), nre);
+        tmem_ld_32x16_async(acc_addr + BN + 16 * (c + 1), nim);
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float4 e[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) e[q] = __ldg(tab + c0 + 16 * c + 8 * h + q);     // warp-uniform addresses: broadcast
+        for (int q = 0; q < 8; ++q) e[q] = __ldg(tab + 16 * c + 8 * h + q);     // warp-uniform addresses: broadcast
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int m0 = __float_as_int(e[q].x);
@@ -780,7 +794,7 @@ __device__ __forceinline__ void mel_accumulate_half(uint32_t acc_addr, const flo
           s1 = fmaf(pw, e[q].z, s1);
         }
       }
-      if (c + 1 < kChunks) {
+      if (c + 1 < c_end) {
         tmem_wait_ld(nre, nim);
 #pragma unroll
         for (int q = 0; q < 16; ++q) { re[q] = nre[q]; im[q] = nim[q]; }
@@ -963,7 +977,8 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       const int64_t tile0 = tile * BM;
       const int64_t g = tile0 + row;
       const bool row_ok = g < b.total_frames;
-      const float sc2 = row_ok ? ldexpf(1.0f, -2 * (__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+      const int32_t row_info = row_ok ? __ldg(row_exp + g) : 0;
+      const float sc2 = row_ok ? ldexpf(1.0f, -2 * (row_info_exp(row_info) + kTcBScaleExp)) : 0.0f;
       float* acc_row = row_ok ? my_acc : scratch_row;
       for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
         const int chain = sub < ntile[0] ? 0 : 1;
@@ -973,8 +988,9 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
         tcgen05_fence_after();
         MelDeferred def;
-        if (upper) mel_accumulate_half<true, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
-        else mel_accumulate_half<false, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
+        const int live_chunks = (min(BN, t.np[chain] - n0) + 15) / 16, lower_chunks = (live_chunks + 1) / 2;
+        if (upper) mel_accumulate_half<true, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def, lower_chunks, live_chunks);
+        else mel_accumulate_half<false, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def, 0, lower_chunks);
         // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the routine)
         tcgen05_fence_before();
         __syncwarp();
@@ -986,7 +1002,20 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       // tile finished: dB (each warp its 64 mels), per-clip maximum, coalesced store, reset of the rows
       const int m_lo = upper ? t.n_mels / 2 : 0, m_hi = upper ? t.n_mels : t.n_mels / 2;
       float vmax = -INFINITY;
-      for (int m = m_lo; m < m_hi; ++m) {
+      int m = m_lo;
+      for (; m + 8 <= m_hi; m += 8) {               // eight independent load -> log -> store chains in flight
+        float v8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v8[i] = my_acc[m + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v8[i] = 10.0f * log10f(fmaxf(1e-10f, v8[i]));
+          vmax = fmaxf(vmax, v8[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) my_acc[m + i] = v8[i];
+      }
+      for (; m < m_hi; ++m) {
         const float v = 10.0f * log10f(fmaxf(1e-10f, my_acc[m]));
         my_acc[m] = v;
         vmax = fmaxf(vmax, v);
@@ -1002,7 +1031,7 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       pair_sync(quarter);
       for (int m = upper ? kMelPitch / 2 : 0; m < (upper ? kMelPitch : kMelPitch / 2); ++m) my_acc[m] = 0.0f;
       {
-        const int clip = row_ok ? find_segment(b.frame_off, b.n_clips, g) : -1;
+        const int clip = row_ok ? row_info_clip(row_info) : -1;      // written by the fold kernel
         const uint32_t key = row_ok ? float_key(vmax) : 0u;
         const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
         const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
@@ -1165,7 +1194,8 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int64_t tile0 = pt * 2 * BM + static_cast<int64_t>(rank) * BM;
       const int64_t g = tile0 + row;
       const bool row_ok = g < b.total_frames;
-      const float sc2 = row_ok ? ldexpf(1.0f, -2 * (__ldg(row_exp + g) + kTcBScaleExp)) : 0.0f;
+      const int32_t row_info = row_ok ? __ldg(row_exp + g) : 0;
+      const float sc2 = row_ok ? ldexpf(1.0f, -2 * (row_info_exp(row_info) + kTcBScaleExp)) : 0.0f;
       float* acc_row = row_ok ? my_acc : scratch_row;
       for (int sub = 0; sub < n_sub; ++sub, ++acc_it) {
         const int chain = sub < ntile[0] ? 0 : 1;
@@ -1175,8 +1205,9 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(tmem_full + buf, (acc_it >> 1) & 1u);
         tcgen05_fence_after();
         MelDeferred def;
-        if (upper) mel_accumulate_half<true, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
-        else mel_accumulate_half<false, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def);
+        const int live_chunks = (min(BN, t.np[chain] - n0) + 15) / 16, lower_chunks = (live_chunks + 1) / 2;
+        if (upper) mel_accumulate_half<true, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def, lower_chunks, live_chunks);
+        else mel_accumulate_half<false, kRolled>(lane_addr + buf * 256u, tab, acc_row, sc2, def, 0, lower_chunks);
         // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the routine)
         tcgen05_fence_before();
         __syncwarp();
@@ -1188,7 +1219,20 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // tile finished: dB (each warp its 64 mels), per-clip maximum, coalesced store, reset of the rows
       const int m_lo = upper ? t.n_mels / 2 : 0, m_hi = upper ? t.n_mels : t.n_mels / 2;
       float vmax = -INFINITY;
-      for (int m = m_lo; m < m_hi; ++m) {
+      int m = m_lo;
+      for (; m + 8 <= m_hi; m += 8) {               // eight independent load -> log -> store chains in flight
+        float v8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v8[i] = my_acc[m + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v8[i] = 10.0f * log10f(fmaxf(1e-10f, v8[i]));
+          vmax = fmaxf(vmax, v8[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) my_acc[m + i] = v8[i];
+      }
+      for (; m < m_hi; ++m) {
         const float v = 10.0f * log10f(fmaxf(1e-10f, my_acc[m]));
         my_acc[m] = v;
         vmax = fmaxf(vmax, v);
@@ -1204,7 +1248,7 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
       pair_sync(quarter);
       for (int m = upper ? kMelPitch / 2 : 0; m < (upper ? kMelPitch : kMelPitch / 2); ++m) my_acc[m] = 0.0f;
       {
-        const int clip = row_ok ? find_segment(b.frame_off, b.n_clips, g) : -1;
+        const int clip = row_ok ? row_info_clip(row_info) : -1;      // written by the fold kernel
         const uint32_t key = row_ok ? float_key(vmax) : 0u;
         const int first_clip = __shfl_sync(0xffffffffu, clip, 0);
         const bool uniform = __all_sync(0xffffffffu, clip == first_clip || clip < 0);
