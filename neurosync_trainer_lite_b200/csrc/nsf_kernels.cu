@@ -1201,22 +1201,31 @@ __global__ void __launch_bounds__(128) k_collect(CollectView v, const T* __restr
 // registers - it was recomputed, behind a chain of dependent loads, by all 128 threads of a block for every
 // single row - and the lanes stream the 256 + 61 columns of the row with fully coalesced 128-byte requests.
 // Same arithmetic (Arith<T>, linspace_at, version_value), so the float64 variant stays bit-exact.
+#ifndef NSF_COLLECT_RUN
+#define NSF_COLLECT_RUN 4
+#endif
+constexpr int kCollectRun = NSF_COLLECT_RUN;      // consecutive rows per warp and tile
 template <typename T>
-__global__ void __launch_bounds__(256) k_collect_rows(CollectView v, const T* __restrict__ audio, int a_cols,
+__global__ void __launch_bounds__(256, 5) k_collect_rows(CollectView v, const T* __restrict__ audio, int a_cols,
                                                       const T* __restrict__ facial, int f_cols,
                                                       T* __restrict__ out_audio, T* __restrict__ out_facial) {
   using A = Arith<T>;
   const int lane = threadIdx.x & 31, wr = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * wpb;
-  const int64_t chunk = (v.total_out_rows + n_warps - 1) / n_warps;
-  const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * wpb + wr) * chunk;
-  const int64_t r_end = min(r_begin + chunk, v.total_out_rows);
+  // Row order: the grid sweeps the output in TILES of wpb x kCollectRun consecutive rows (block b takes tiles b,
+  // b + gridDim.x, ...; a warp takes kCollectRun consecutive rows of the tile), so at any time all resident warps
+  // read and write ONE compact region (~25 MB) of each stream.  With one long run per warp (round 1 / early round 2)
+  // the 5 920 resident warps touched 5 920 x 4 scattered 1 KB rows at a time: every access opened its own DRAM
+  // page and the kernel sat at 30 % of the DRAM peak with all stalls on the loads (ncu, round 2).
+  const int64_t tile_rows = static_cast<int64_t>(wpb) * kCollectRun;
+  const int64_t n_tiles = (v.total_out_rows + tile_rows - 1) / tile_rows;
   int64_t clip_o0 = 0, clip_o_end = -1, a0 = 0, f0 = 0;
   int ver[3] = {0, 0, 0};
   int nv = 0;
   int64_t len_before[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
-  for (int64_t r = r_begin; r < r_end; ++r) {
-    if (r >= clip_o_end) {
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  for (int64_t r = tile * tile_rows + static_cast<int64_t>(wr) * kCollectRun,
+               r_end = min(r + kCollectRun, v.total_out_rows); r < r_end; ++r) {
+    if (r >= clip_o_end || r < clip_o0) {
       const int clip = find_segment(v.o_off, v.n_clips, r);
       clip_o0 = __ldg(v.o_off + clip);
       clip_o_end = __ldg(v.o_off + clip + 1);
@@ -1252,6 +1261,49 @@ __global__ void __launch_bounds__(256) k_collect_rows(CollectView v, const T* __
       const int64_t L = len_before[level], k = nb[level];
       if (p >= L) { term_ver = ver[level]; term_row = p - L + k; break; }
       if (p >= L - k) { blend_level[n_blend] = level; blend_q[n_blend] = p - (L - k); ++n_blend; }
+    }
+    if (sizeof(T) == 4 && n_blend == 0 && a_cols == 256 && f_cols <= 64) {
+      // Rows outside the cross-fade zones (all but 2 x blend_frames per clip) of the float32 default shape: every
+      // value is a fixed expression of at most TWO adjacent source rows of its stream -
+      //   original / fast: at(r)        slow, odd row k: (at(k/2) + at(k/2 + 1)) / 2
+      //   facial slow rows also carry smooth_facial_data: (slow(j-1) + slow(j)) / 2, again rows (j-1)/2 and (j-1)/2 + 1
+      // so the row's eight loads (two float4 columns and two facial columns from two rows each) are issued back to
+      // back and the warp pays ONE memory round trip per row instead of one per column group (ncu, round 2: 7 k cycles
+      // per row, 30 % of the DRAM peak).  Same operations in the same order as version_value / version_value4.
+      const float* asrc = reinterpret_cast<const float*>(audio) + a0 * 256;
+      const float* fsrc = reinterpret_cast<const float*>(facial) + f0 * f_cols;
+      int64_t ra = term_row, rf = term_row;      // first source row of the audio / facial expression
+      int a_kind = 0, f_kind = 0;                // 0: at(r)   1: (at(r) + at(r+1)) / 2   facial 2, 3: smoothed slow rows
+      if (term_ver == 1) { ra = 2 * term_row; rf = ra; }
+      if (term_ver == 2) {
+        ra = term_row >> 1;
+        a_kind = static_cast<int>(term_row & 1);
+        if (term_row == 0) { rf = 0; f_kind = 0; }
+        else if (term_row & 1) { rf = term_row >> 1; f_kind = 2; }     // (at(p) + (at(p) + at(p+1)) / 2) / 2
+        else { rf = (term_row >> 1) - 1; f_kind = 3; }                 // ((at(q-1) + at(q)) / 2 + at(q)) / 2
+      }
+      const float4* a_r0 = reinterpret_cast<const float4*>(asrc + ra * 256);
+      const float4* a_r1 = reinterpret_cast<const float4*>(asrc + (ra + (a_kind ? 1 : 0)) * 256);
+      const float* f_r0 = fsrc + rf * f_cols;
+      const float* f_r1 = fsrc + (rf + (f_kind ? 1 : 0)) * f_cols;
+      const int fc0 = lane, fc1 = lane + 32;
+      const float4 x0 = __ldg(a_r0 + lane), x1 = __ldg(a_r0 + lane + 32);
+      const float4 y0 = __ldg(a_r1 + lane), y1 = __ldg(a_r1 + lane + 32);
+      const float p0 = fc0 < f_cols ? __ldg(f_r0 + fc0) : 0.0f, p1 = fc1 < f_cols ? __ldg(f_r0 + fc1) : 0.0f;
+      const float q0 = fc0 < f_cols ? __ldg(f_r1 + fc0) : 0.0f, q1 = fc1 < f_cols ? __ldg(f_r1 + fc1) : 0.0f;
+      float4* adst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_audio) + r * 256);
+      adst[lane] = a_kind ? mul4(add4(x0, y0), 0.5f) : x0;
+      adst[lane + 32] = a_kind ? mul4(add4(x1, y1), 0.5f) : x1;
+      auto fexpr = [&](float u, float w) -> float {
+        if (f_kind == 0) return u;
+        const float h = __fmul_rn(__fadd_rn(u, w), 0.5f);
+        if (f_kind == 1) return h;
+        return f_kind == 2 ? __fmul_rn(__fadd_rn(u, h), 0.5f) : __fmul_rn(__fadd_rn(h, w), 0.5f);
+      };
+      float* fdst = reinterpret_cast<float*>(out_facial) + r * f_cols;
+      if (fc0 < f_cols) fdst[fc0] = fexpr(p0, q0);
+      if (fc1 < f_cols) fdst[fc1] = fexpr(p1, q1);
+      continue;
     }
     T w1[2] = {static_cast<T>(0), static_cast<T>(0)}, w2[2] = {static_cast<T>(0), static_cast<T>(0)};
     for (int bi = 0; bi < n_blend; ++bi) {
@@ -1592,7 +1644,9 @@ int launch_collect(cudaStream_t s, int dtype, const CollectView& v, const void* 
   // NSF_COLLECT_BLOCKROW=1 keeps the block-per-row kernel (validation / A-B timing)
   static const bool block_row = std::getenv("NSF_COLLECT_BLOCKROW") != nullptr;
   if (!block_row) {
-    const int grid = grid_for(v.total_out_rows, 8 * 8, kSmCount * 8);       // >= 8 rows per warp when there are enough
+    // one wave of resident blocks (48 registers: five blocks of 256 threads per SM), >= 8 rows per warp when there are
+    // enough: with 8 blocks per SM the second wave ran 60 % full (ncu: 1.6 waves)
+    const int grid = grid_for(v.total_out_rows, 8 * 8, kSmCount * 5);
     if (dtype == NSF_F64)
       k_collect_rows<double><<<grid, 256, 0, s>>>(v, static_cast<const double*>(audio), a_cols,
                                                   static_cast<const double*>(facial), f_cols,

@@ -226,3 +226,70 @@ def test_autocorr_loops_agree(sr, engine, oracle, tmp_path):
             got = res[loop][roff[i]:roff[i + 1]]
             assert got.shape == want.shape
             assert np.abs(got[:, 69:] - want[:, 69:]).max() <= TOL_AC, (loop, i)
+
+
+# ---- collect_features in float32 (what load_data returns): single-round-trip row path of k_collect_rows ----
+def _collect_f32_emulation(a, f, include_fast, include_slow, blend, k):
+    """data_processing.py:126-197 restated in float32 with the device's operation order (the float64 oracle rounds
+    the facial smoothing in float64): version rows are bit-exact targets, cross-fade rows are returned as NaN."""
+    h = np.float32(0.5)
+    n = min(len(a), len(f))
+    la, lf = len(a), len(f)
+    a = a[(la - n) // 2:(la - n) // 2 + n] if la > lf else a[:n]
+    f = f[(lf - n) // 2:(lf - n) // 2 + n] if lf > la else f[:n]
+
+    def slower(d):
+        out = np.zeros((2 * len(d) - 1, d.shape[1]), np.float32)
+        out[0::2] = d
+        out[1::2] = (d[:-1] + d[1:]) * h
+        return out
+
+    def smooth(d):
+        out = d.copy()
+        out[1:] = (d[:-1] + d[1:]) * h
+        return out
+
+    va, vf = [a], [f]
+    if include_fast:
+        va.append(a[::2]); vf.append(f[::2])
+    if include_slow:
+        va.append(slower(a)); vf.append(smooth(slower(f)))
+
+    def stack(vs):
+        acc = vs[0]
+        for s in vs[1:]:
+            nb = min(k, len(acc), len(s)) if blend else 0
+            if nb <= 0:
+                acc = np.vstack([acc, s])
+            else:
+                acc = np.vstack([acc[:-nb], np.full((nb, s.shape[1]), np.nan, np.float32), s[nb:]])
+        return acc
+    return stack(va), stack(vf)
+
+
+@pytest.mark.parametrize("kw", [dict(include_fast=True, include_slow=True, blend_boundaries=False),
+                                dict(include_fast=True, include_slow=True, blend_boundaries=True),
+                                dict(include_fast=False, include_slow=True, blend_boundaries=True),
+                                dict(include_fast=True, include_slow=False, blend_boundaries=True)])
+def test_collect_float32_rows_bit_exact(kw, engine, oracle):
+    eng = engine.get_engine(88200, 1470, 735)
+    rng = np.random.default_rng(11)
+    sizes = [(1801, 1800), (300, 305), (64, 64), (31, 40), (2, 2)]
+    audio = [rng.standard_normal((na, 256)).astype(np.float32) for na, _ in sizes]
+    facial = [rng.uniform(0, 1, (nf, 61)).astype(np.float32) for _, nf in sizes]
+    a_off = np.concatenate([[0], np.cumsum([len(a) for a in audio])]).astype(np.int64)
+    f_off = np.concatenate([[0], np.cumsum([len(f) for f in facial])]).astype(np.int64)
+    oa, of, o_off = eng.collect_host(np.concatenate(audio), a_off, np.concatenate(facial), f_off,
+                                     kw["include_fast"], kw["include_slow"], kw["blend_boundaries"], 30)
+    for i, (a, f) in enumerate(zip(audio, facial)):
+        wa, wf = _collect_f32_emulation(a, f, kw["include_fast"], kw["include_slow"], kw["blend_boundaries"], 30)
+        ga, gf = oa[o_off[i]:o_off[i + 1]], of[o_off[i]:o_off[i + 1]]
+        assert ga.shape == wa.shape and gf.shape == wf.shape
+        keep = ~np.isnan(wa[:, 0])
+        np.testing.assert_array_equal(ga[keep], wa[keep])               # version rows: bit-exact
+        np.testing.assert_array_equal(gf[keep], wf[keep])
+        # cross-fade rows (and everything else) against the float64 oracle
+        ra, rf = oracle.collect_from_arrays(a.astype(np.float64), f.astype(np.float64), kw["include_fast"],
+                                            kw["include_slow"], kw["blend_boundaries"], 30)
+        np.testing.assert_allclose(ga, ra, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(gf, rf, rtol=0, atol=1e-6)
