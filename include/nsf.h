@@ -101,6 +101,14 @@ NSF_API int64_t nsf_guard_frames(int64_t n_samples, int32_t frame_length, int32_
 NSF_API int64_t nsf_hop_frames(int64_t n_samples, int32_t frame_length, int32_t hop_length);
 /* R = ceil(T / 2): rows after reduce_features              extract_features_utils.py:33-44 */
 NSF_API int64_t nsf_feature_rows(int64_t n_samples, int32_t frame_length, int32_t hop_length);
+/* Prefix sum of the per-clip row counts of a packed batch: row_offsets[0] = 0, row_offsets[i + 1] =
+ * row_offsets[i] + rows of clip i under `flags` (nsf_feature_rows; nsf_hop_frames with NSF_NO_REDUCE;
+ * whole un-padded frames with NSF_AC_NO_PAD).  The packing nsf_extract_batch uses when its
+ * out_row_offsets is NULL; one call for the batch instead of one nsf_feature_rows call per clip (a
+ * binding's per-clip loop costs more than the kernels for batches of thousands of short clips).
+ * row_offsets has n_clips + 1 entries.                      extract_features_utils.py:33-44 */
+NSF_API nsf_status nsf_row_offsets(int32_t frame_length, int32_t hop_length, const int64_t* clip_offsets,
+                                   int32_t n_clips, uint32_t flags, int64_t* row_offsets);
 /* Output columns for a flag set (256 by default, 69 without autocorr, ...). */
 NSF_API int32_t nsf_feature_cols(const nsf_plan* plan, uint32_t flags);
 /* Rows collect_features yields for given stream lengths    data_processing.py:126-197 */

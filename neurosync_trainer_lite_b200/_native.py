@@ -63,6 +63,7 @@ _SIGS = {
     "nsf_guard_frames": (_i64, [_i64, _i32, _i32]),
     "nsf_hop_frames": (_i64, [_i64, _i32, _i32]),
     "nsf_feature_rows": (_i64, [_i64, _i32, _i32]),
+    "nsf_row_offsets": (_i32, [_i32, _i32, _i64p, _i32, _u32, _i64p]),
     "nsf_feature_cols": (_i32, [_vp, _u32]),
     "nsf_collect_rows": (_i64, [_i64, _i64, _u32, _i32]),
     "nsf_plan_create": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),

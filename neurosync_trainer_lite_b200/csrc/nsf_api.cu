@@ -149,6 +149,11 @@ inline int64_t group_budget(int turn) {
   static const int64_t big = env_mi("NSF_GROUP_MI", kGroupSamples), first = env_mi("NSF_FIRST_MI", kFirstGroupSamples);
   return turn < 2 ? first : big;
 }
+// (Tapering the last groups - a third of the remaining samples each, so that the kernels and the download that follow
+// the final upload belong to one small group - was measured in round 2 and made the pass SLOWER, 6.83 against 6.77 ms
+// on C2: every extra group costs more than the shorter tail saves.)
+// Grid caps of the two front-end kernels inside the pipelined passes (nsf_kernels.cu, launch_absmax).
+constexpr int kPipelinedAbsmaxBlocks = 74, kPipelinedNormalizeBlocks = 148;
 
 struct Slot {  // one in-flight clip group of the host pipeline
   cudaStream_t stream = nullptr;
@@ -197,6 +202,7 @@ struct nsf_ctx {
   nsf::Slot slot[nsf::kSlots];
   int64_t launches = 0;
   bool profiling = false;
+  bool pipelined = false;     // set by the host passes around their nsf_extract_batch calls (front-end grid caps)
   cudaEvent_t stage_ev[nsf::kStages + 1] = {};
   bool stage_valid = false;
   nsf::Arena collect_in_a, collect_in_f, collect_out_a, collect_out_f, collect_desc;
@@ -657,8 +663,9 @@ nsf_status nsf_extract_batch(nsf_ctx* ctx, void* cuda_stream, const void* pcm_de
   const float* y = static_cast<const float*>(pcm_dev);
   if (need_y) {
     float* ydst = y_norm_dev ? y_norm_dev : L.y;
-    if (normalize) NSF_LAUNCH(launch_absmax(s, pcm_dev, pcm_format, b, L.peak_bits));
-    NSF_LAUNCH(launch_normalize(s, pcm_dev, pcm_format, b, L.peak_bits, normalize, ydst));
+    const bool capped = ctx->pipelined;           // inside a pipelined host pass: stay off the copy engine's HBM share
+    if (normalize) NSF_LAUNCH(launch_absmax(s, pcm_dev, pcm_format, b, L.peak_bits, capped ? kPipelinedAbsmaxBlocks : 0));
+    NSF_LAUNCH(launch_normalize(s, pcm_dev, pcm_format, b, L.peak_bits, normalize, ydst, capped ? kPipelinedNormalizeBlocks : 0));
     y = ydst;
   } else if (y_norm_dev) {
     NSF_CUDA(cudaMemcpyAsync(y_norm_dev, pcm_dev, hd.total_samples * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -841,10 +848,12 @@ nsf_status nsf_extract_host(nsf_ctx* ctx, const void* pcm_host, int32_t pcm_form
       src = static_cast<const char*>(sl->stage_in.ptr);
     }
     NSF_CUDA(cudaMemcpyAsync(sl->pcm.ptr, src, samples * esz, cudaMemcpyHostToDevice, sl->stream));
+    ctx->pipelined = true;
     st = nsf_extract_batch(ctx, sl->stream, sl->pcm.ptr, pcm_format, clip_offsets + first, gn, flags,
                            static_cast<float*>(sl->out.ptr), cols, nullptr,
                            y_norm_host ? static_cast<float*>(sl->ynorm.ptr) : nullptr, sl->work.ptr,
                            static_cast<int64_t>(sl->work.bytes));
+    ctx->pipelined = false;
     if (st != NSF_OK) return st;
     float* dst = out_host + all.row_off[first] * out_ld;
     if (!out_dma) {
@@ -1144,9 +1153,11 @@ nsf_status nsf_extract_collect_host(nsf_ctx* ctx, const void* pcm_host, int32_t 
     int64_t* d = static_cast<int64_t*>(sl->col_desc.ptr);
     NSF_CUDA(cudaMemcpyAsync(d, h, 3 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, sl->stream));
     if ((st = desc_commit(de, sl->stream)) != NSF_OK) return st;
+    ctx->pipelined = true;
     st = nsf_extract_batch(ctx, sl->stream, sl->pcm.ptr, pcm_format, clip_offsets + first, gn, flags,
                            static_cast<float*>(sl->out.ptr), cols, nullptr, nullptr, sl->work.ptr,
                            static_cast<int64_t>(sl->work.bytes));
+    ctx->pipelined = false;
     if (st != NSF_OK) return st;
     CollectView v;
     v.a_off = d; v.f_off = d + n1; v.o_off = d + 2 * n1;

@@ -37,18 +37,67 @@ template <> __device__ __forceinline__ float decode_pcm<int16_t>(int16_t v) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kChunk = 16384;
 
-template <typename T>
+// 16-byte vectors of the PCM stream (8 int16 or 4 float32 samples); kVec = false is the scalar form for caller
+// pointers that are not 16-byte aligned.
+template <typename T> struct PcmVec;
+template <> struct PcmVec<int16_t> {
+  static constexpr int kN = 8;
+  static __device__ __forceinline__ void load(const int16_t* p, float (&v)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = decode_pcm<int16_t>(static_cast<int16_t>(w[i] & 0xffffu));
+      v[2 * i + 1] = decode_pcm<int16_t>(static_cast<int16_t>(w[i] >> 16));
+    }
+  }
+};
+template <> struct PcmVec<float> {
+  static constexpr int kN = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+};
+
+// [s, e) of the packed signal as scalar head, 16-byte aligned vector body, scalar tail (indices relative to the
+// array, whose base is 16-byte aligned when kVec)
+template <typename T, bool kVec>
+struct PcmSpan {
+  int64_t head_end, body_end;     // [s, head_end) scalar, [head_end, body_end) vectors, [body_end, e) scalar
+  __device__ __forceinline__ PcmSpan(int64_t s, int64_t e) {
+    constexpr int n = PcmVec<T>::kN;
+    if (kVec) {
+      head_end = min(e, (s + n - 1) / n * n);
+      body_end = max(head_end, e / n * n);
+    } else {
+      head_end = e;
+      body_end = e;
+    }
+  }
+};
+
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(256) k_absmax(const T* __restrict__ pcm, BatchView b,
                                                 uint32_t* __restrict__ peak_bits) {
   __shared__ float s_part[8];
-  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kChunk;
+  constexpr int n = PcmVec<T>::kN;
+  for (int64_t c0 = static_cast<int64_t>(blockIdx.x) * kChunk; c0 < b.total_samples; c0 += static_cast<int64_t>(gridDim.x) * kChunk) {
   const int64_t c1 = min(c0 + kChunk, b.total_samples);
   int clip = find_segment(b.clip_off, b.n_clips, c0);
   int64_t s = c0;
   while (s < c1) {
     const int64_t e = min(c1, __ldg(b.clip_off + clip + 1));
+    const PcmSpan<T, kVec> sp(s, e);
     float m = 0.0f;
-    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) m = fmaxf(m, fabsf(decode_pcm<T>(pcm[i])));
+    for (int64_t i = s + threadIdx.x; i < sp.head_end; i += blockDim.x) m = fmaxf(m, fabsf(decode_pcm<T>(pcm[i])));
+    for (int64_t i = sp.head_end + static_cast<int64_t>(threadIdx.x) * n; i < sp.body_end; i += static_cast<int64_t>(blockDim.x) * n) {
+      float v[n];
+      PcmVec<T>::load(pcm + i, v);
+#pragma unroll
+      for (int k = 0; k < n; ++k) m = fmaxf(m, fabsf(v[k]));
+    }
+    for (int64_t i = sp.body_end + threadIdx.x; i < e; i += blockDim.x) m = fmaxf(m, fabsf(decode_pcm<T>(pcm[i])));
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = m;
     __syncthreads();
@@ -61,28 +110,41 @@ __global__ void __launch_bounds__(256) k_absmax(const T* __restrict__ pcm, Batch
     s = e;
     ++clip;
   }
+  }
 }
 
-template <typename T>
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(256) k_normalize(const T* __restrict__ pcm, BatchView b,
                                                    const uint32_t* __restrict__ peak_bits,
                                                    bool use_peak, float* __restrict__ y) {
-  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kChunk;
+  constexpr int n = PcmVec<T>::kN;
+  for (int64_t c0 = static_cast<int64_t>(blockIdx.x) * kChunk; c0 < b.total_samples; c0 += static_cast<int64_t>(gridDim.x) * kChunk) {
   const int64_t c1 = min(c0 + kChunk, b.total_samples);
   int clip = find_segment(b.clip_off, b.n_clips, c0);
   int64_t s = c0;
   while (s < c1) {
     const int64_t e = min(c1, __ldg(b.clip_off + clip + 1));
     const float peak = use_peak ? __uint_as_float(__ldg(peak_bits + clip)) : 0.0f;
-    if (peak > 0.0f) {
-      // IEEE division: bit-identical to numpy's float32 y / max_val
-      for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x)
-        y[i] = __fdiv_rn(decode_pcm<T>(pcm[i]), peak);
-    } else {
-      for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) y[i] = decode_pcm<T>(pcm[i]);
+    const bool div = peak > 0.0f;
+    const PcmSpan<T, kVec> sp(s, e);
+    // IEEE division: bit-identical to numpy's float32 y / max_val
+    auto one = [&](int64_t i) { const float v = decode_pcm<T>(pcm[i]); y[i] = div ? __fdiv_rn(v, peak) : v; };
+    for (int64_t i = s + threadIdx.x; i < sp.head_end; i += blockDim.x) one(i);
+    for (int64_t i = sp.head_end + static_cast<int64_t>(threadIdx.x) * n; i < sp.body_end; i += static_cast<int64_t>(blockDim.x) * n) {
+      float v[n];
+      PcmVec<T>::load(pcm + i, v);
+      if (div) {
+#pragma unroll
+        for (int k = 0; k < n; ++k) v[k] = __fdiv_rn(v[k], peak);
+      }
+#pragma unroll
+      for (int k = 0; k < n; k += 4)                      // i is a multiple of n >= 4: 16-byte aligned stores
+        *reinterpret_cast<float4*>(y + i + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
     }
+    for (int64_t i = sp.body_end + threadIdx.x; i < e; i += blockDim.x) one(i);
     s = e;
     ++clip;
+  }
   }
 }
 
@@ -811,22 +873,21 @@ __global__ void __launch_bounds__(256, 3) k_delta_reduce(BatchView b, const floa
             cached_mu = mu; cached_inv = inv;
           }
         }
+        // the window holds CENTRED values (x - mu, formed once when a frame is loaded: constants give exact 0);
+        // it is dropped whenever the clip - and with it mu - changes
         const float* p = in + (f0 + ta - 4) * in_ld + ch;
         if (win_clip == clip && win_ta + 2 == ta) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) win[k] = win[k + 2];
-          win[8] = __ldg(p + 8 * in_ld);
-          win[9] = __ldg(p + 9 * in_ld);
+          win[8] = __ldg(p + 8 * in_ld) - mu;
+          win[9] = __ldg(p + 9 * in_ld) - mu;
         } else {
 #pragma unroll
-          for (int k = 0; k < 10; ++k) win[k] = __ldg(p + k * in_ld);
+          for (int k = 0; k < 10; ++k) win[k] = __ldg(p + k * in_ld) - mu;
         }
-        float xa[9], xb[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { xa[k] = win[k] - mu; xb[k] = win[k + 1] - mu; }   // centred: constants give exact 0
-        const float va = 0.5f * ((win[4] - mu) * inv + (win[5] - mu) * inv);
-        const float d1 = 0.5f * (sg_d1(xa) + sg_d1(xb)) * inv;
-        const float d2 = 0.5f * (sg_d2(xa) + sg_d2(xb)) * inv;
+        const float va = 0.5f * (win[4] * inv + win[5] * inv);
+        const float d1 = 0.5f * (sg_d1(win) + sg_d1(win + 1)) * inv;
+        const float d2 = 0.5f * (sg_d2(win) + sg_d2(win + 1)) * inv;
         float* o = out + r * out_ld + col0;
         o[ch] = va;
         o[C + ch] = d1;
@@ -1496,25 +1557,44 @@ int grid_for(int64_t items, int per_block, int max_blocks) {
 #define NSF_CHECK_LAUNCH() \
   do { if (cudaGetLastError() != cudaSuccess) return -1; } while (0)
 
-int launch_absmax(cudaStream_t s, const void* pcm, int fmt, const BatchView& b, uint32_t* peak_bits) {
+// 16-byte vector loads / stores need 16-byte aligned array bases (library arenas always are; caller-owned device
+// pointers of the stream-ordered entry points may not be: those take the scalar instantiation)
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// max_blocks > 0 caps the grid (the kernels stride over the 16 K-sample chunks).  The pipelined host entry points
+// pass a cap: these two kernels are pure HBM streams, and whenever a kernel saturates HBM the copy engine's upload of
+// the NEXT clip group stalls - measured on C2 end to end (int16 host PCM -> host rows, B200): 6.45 ms with the grid
+// capped at 74 / 148 blocks against 6.78 ms uncapped, although the uncapped kernels are 3x shorter (round 2,
+// profiles/experiments/README.md).  Device-resident callers run them uncapped.
+int launch_absmax(cudaStream_t s, const void* pcm, int fmt, const BatchView& b, uint32_t* peak_bits, int max_blocks) {
   if (b.total_samples == 0) return 0;
-  const int grid = static_cast<int>((b.total_samples + kChunk - 1) / kChunk);
-  if (fmt == NSF_PCM_I16)
-    k_absmax<int16_t><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(pcm), b, peak_bits);
-  else
-    k_absmax<float><<<grid, 256, 0, s>>>(static_cast<const float*>(pcm), b, peak_bits);
+  int grid = static_cast<int>((b.total_samples + kChunk - 1) / kChunk);
+  if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;
+  const bool vec = aligned16(pcm);
+  if (fmt == NSF_PCM_I16) {
+    if (vec) k_absmax<int16_t, true><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(pcm), b, peak_bits);
+    else k_absmax<int16_t, false><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(pcm), b, peak_bits);
+  } else {
+    if (vec) k_absmax<float, true><<<grid, 256, 0, s>>>(static_cast<const float*>(pcm), b, peak_bits);
+    else k_absmax<float, false><<<grid, 256, 0, s>>>(static_cast<const float*>(pcm), b, peak_bits);
+  }
   NSF_CHECK_LAUNCH();
   return 1;
 }
 
 int launch_normalize(cudaStream_t s, const void* pcm, int fmt, const BatchView& b,
-                     const uint32_t* peak_bits, bool use_peak, float* y) {
+                     const uint32_t* peak_bits, bool use_peak, float* y, int max_blocks) {
   if (b.total_samples == 0) return 0;
-  const int grid = static_cast<int>((b.total_samples + kChunk - 1) / kChunk);
-  if (fmt == NSF_PCM_I16)
-    k_normalize<int16_t><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(pcm), b, peak_bits, use_peak, y);
-  else
-    k_normalize<float><<<grid, 256, 0, s>>>(static_cast<const float*>(pcm), b, peak_bits, use_peak, y);
+  int grid = static_cast<int>((b.total_samples + kChunk - 1) / kChunk);
+  if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;
+  const bool vec = aligned16(pcm) && aligned16(y);
+  if (fmt == NSF_PCM_I16) {
+    if (vec) k_normalize<int16_t, true><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(pcm), b, peak_bits, use_peak, y);
+    else k_normalize<int16_t, false><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(pcm), b, peak_bits, use_peak, y);
+  } else {
+    if (vec) k_normalize<float, true><<<grid, 256, 0, s>>>(static_cast<const float*>(pcm), b, peak_bits, use_peak, y);
+    else k_normalize<float, false><<<grid, 256, 0, s>>>(static_cast<const float*>(pcm), b, peak_bits, use_peak, y);
+  }
   NSF_CHECK_LAUNCH();
   return 1;
 }
@@ -1610,7 +1690,9 @@ int launch_dct_sum(cudaStream_t s, const DeviceTables& t, const BatchView& b, co
 int launch_delta_reduce(cudaStream_t s, const BatchView& b, const float* in, int C, int in_ld,
                         const double* sum, const double* sumsq, bool cmvn, bool deltas, bool reduce,
                         float* out, int64_t out_ld, int col0) {
-  const int grid = grid_for(b.total_rows, 8, kSmCount * 8);
+  // one wave of resident blocks (three per SM): the first row of a warp's run costs several times an interior row
+  // (clip lookup, float64 CMVN constants, ten window loads), so runs are as long as the grid allows
+  const int grid = grid_for(b.total_rows, 8, kSmCount * 3);
   k_delta_reduce<<<grid, 256, 0, s>>>(b, in, C, in_ld, sum, sumsq, cmvn, deltas, reduce, out, out_ld, col0);
   NSF_CHECK_LAUNCH();
   return 1;

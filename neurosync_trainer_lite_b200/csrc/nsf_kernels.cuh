@@ -56,10 +56,12 @@ struct ExtractBuffers {
   float* ac_raw;           // [total_frames][n_lags] (only with autocorr deltas)
 };
 
+// max_blocks: 0 = as many blocks as there are 16 K-sample chunks; > 0 caps the grid (pipelined host paths, see
+// nsf_kernels.cu: an HBM-saturating kernel stalls the copy engine's upload of the next clip group)
 int launch_absmax(cudaStream_t s, const void* pcm, int pcm_format, const BatchView& b,
-                  uint32_t* peak_bits);
+                  uint32_t* peak_bits, int max_blocks = 0);
 int launch_normalize(cudaStream_t s, const void* pcm, int pcm_format, const BatchView& b,
-                     const uint32_t* peak_bits, bool use_peak, float* y_out);
+                     const uint32_t* peak_bits, bool use_peak, float* y_out, int max_blocks = 0);
 int launch_fold32(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
                   float* a32);
 int launch_dft_simt(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* a32,

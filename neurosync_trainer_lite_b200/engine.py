@@ -166,17 +166,11 @@ class Engine:
 
     # ---- geometry ------------------------------------------------------------------------
     def row_offsets(self, offsets, flags=0):
-        lens = np.diff(np.asarray(offsets, dtype=np.int64))
-        if flags & nv.AC_NO_PAD:          # pad_signal=False: as many whole frames as fit
-            rows = [max(0, self.plan.guard_frames(n)) if n >= self.plan.F else 0 for n in lens]
-            if not flags & nv.NO_REDUCE:
-                rows = [(t + 1) // 2 for t in rows]
-        elif flags & nv.NO_REDUCE:
-            rows = [self.plan.hop_frames(n) for n in lens]
-        else:
-            rows = [self.plan.feature_rows(n) for n in lens]
-        out = np.zeros(len(lens) + 1, dtype=np.int64)
-        np.cumsum(rows, out=out[1:])
+        """Prefix sum of the per-clip row counts (``nsf_row_offsets``: one call for the whole batch)."""
+        off, off_p = nv.i64_array(offsets)
+        out = np.empty(len(off), dtype=np.int64)
+        nv.check(nv.lib.nsf_row_offsets(self.plan.F, self.plan.H, off_p, len(off) - 1, int(flags),
+                                        out.ctypes.data_as(nv._i64p)))
         return out
 
     @staticmethod

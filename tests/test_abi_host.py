@@ -64,6 +64,41 @@ def test_frame_counts_against_reference_kats(nv, oracle, golden):
                 assert nv.lib.nsf_feature_rows(n, F, H) == oracle.feature_rows(n, F, H)
 
 
+def test_row_offsets_is_the_prefix_sum_of_the_per_clip_counts(nv, oracle):
+    """nsf_row_offsets (one call per batch) against the per-clip functions and the oracle, for every flag
+    that changes the row count; 10 000 clips must not cost a per-clip binding call each."""
+    import time
+    rng = np.random.default_rng(5)
+    for F, H in [(1470, 735), (266, 133), (735, 367)]:
+        lens = rng.integers(0, 200000, size=500).astype(np.int64)
+        lens[:4] = [0, F - 1, F, F + H]
+        off = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        off += 12345                                       # offsets need not start at 0
+        for flags in (0, nv.NO_REDUCE, nv.AC_NO_PAD, nv.AC_NO_PAD | nv.NO_REDUCE):
+            got = np.full(len(off), -1, dtype=np.int64)
+            assert nv.lib.nsf_row_offsets(F, H, off.ctypes.data_as(nv._i64p), len(lens), flags,
+                                          got.ctypes.data_as(nv._i64p)) == nv.OK
+            want = [0]
+            for n in lens:
+                n = int(n)
+                if flags & nv.AC_NO_PAD:
+                    t = max(0, oracle.guard_frames(n, F, H)) if n >= F else 0
+                else:
+                    t = nv.lib.nsf_hop_frames(n, F, H)
+                    assert t == oracle.hop_frames(n, F, H)
+                want.append(want[-1] + (t if flags & nv.NO_REDUCE else (t + 1) // 2))
+            assert got.tolist() == want
+    bad = np.array([0, 10, 5], dtype=np.int64)
+    out = np.zeros(3, dtype=np.int64)
+    assert nv.lib.nsf_row_offsets(266, 133, bad.ctypes.data_as(nv._i64p), 2, 0, out.ctypes.data_as(nv._i64p)) == nv.ERR_BAD_ARG
+    off = np.arange(10001, dtype=np.int64) * 32000
+    out = np.zeros(10001, dtype=np.int64)
+    t0 = time.perf_counter()
+    assert nv.lib.nsf_row_offsets(266, 133, off.ctypes.data_as(nv._i64p), 10000, 0, out.ctypes.data_as(nv._i64p)) == nv.OK
+    assert time.perf_counter() - t0 < 2e-3 and out[-1] == 10000 * nv.lib.nsf_feature_rows(32000, 266, 133)
+
+
 def test_collect_rows_match_oracle(nv, oracle):
     for n in [0, 1, 2, 5, 29, 30, 31, 59, 60, 61, 1800, 1801]:
         for fast in (False, True):

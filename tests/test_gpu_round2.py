@@ -293,3 +293,24 @@ def test_collect_float32_rows_bit_exact(kw, engine, oracle):
                                             kw["include_slow"], kw["blend_boundaries"], 30)
         np.testing.assert_allclose(ga, ra, rtol=0, atol=2e-6)
         np.testing.assert_allclose(gf, rf, rtol=0, atol=1e-6)
+
+
+def test_front_end_kernels_do_not_depend_on_pointer_alignment(nv, engine):
+    """k_absmax / k_normalize read 16-byte vectors when the caller's device pointer allows it and fall back to the scalar
+    form otherwise: int16 and float32 PCM at an odd element offset give the rows of the aligned call, bit for bit."""
+    import torch
+    eng = engine.get_engine(88200, 1470, 735)
+    clips = [synth.synth_clip(0.7, 88200, seed=21, kind="voiced"), synth.synth_clip(0.41, 88200, seed=22, kind="noise")]
+    packed, off = engine.pack_clips(clips)
+    pcm16 = np.clip(np.round(packed * 32767.0), -32768, 32767).astype(np.int16)
+    dev = torch.device("cuda", 0)
+    for host in (pcm16, packed.astype(np.float32)):
+        t = torch.from_numpy(host).to(dev)
+        want, _ = eng.extract_device(t, off, nv.PEAK_NORMALIZE)
+        for shift in (1, 3, 5):
+            buf = torch.empty(len(host) + 8, dtype=t.dtype, device=dev)
+            buf[shift:shift + len(host)] = t
+            view = buf[shift:shift + len(host)]
+            assert view.data_ptr() % 16 != 0
+            got, _ = eng.extract_device(view, off, nv.PEAK_NORMALIZE)
+            assert torch.equal(got, want)
