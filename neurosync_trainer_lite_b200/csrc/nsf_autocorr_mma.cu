@@ -21,6 +21,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "nsf.h"
 #include "nsf_device_utils.cuh"
@@ -280,7 +281,12 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   // one group = 4 K-blocks; `cur` receives this group's B fragments, `old` holds the previous group's
   // nq: blocks of the group that hold samples (4, or fewer in the frame's last group: blocks beyond the frame are
   // all-zero A fragments, e.g. 3 of the 20 blocks at F = 266, and contribute nothing to either tile)
-  auto group = [&](const uint32_t* pb_h, const uint32_t* pb_l, uint32_t (&cur)[4][4], const uint32_t (&old)[4][4], int nq) {
+  // first (a std::true_type for the frame's first group): `old` would be the four blocks BEFORE the frame - zero
+  // fragments - so the three tile-1 MMAs of each of these blocks are not issued (12 of 102 MMAs at F = 266; adding
+  // exact zeros to zero accumulators, so the rows are bit-identical)
+  auto group = [&](const uint32_t* pb_h, const uint32_t* pb_l, uint32_t (&cur)[4][4], const uint32_t (&old)[4][4], int nq,
+                   auto first) {
+    constexpr bool kTile1 = !decltype(first)::value;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (q >= nq) break;
@@ -292,28 +298,34 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
       cur[q][2] = pb_l[8 * q]; cur[q][3] = pb_l[8 * q + 4];
       // the two cross products of a tile are placed four MMAs apart (dependent accumulator)
       mma_16816(d0x, ah[0], ah[1], ah[2], ah[3], cur[q][2], cur[q][3]);
-      mma_16816(d1x, ah[0], ah[1], ah[2], ah[3], old[q][2], old[q][3]);
+      if constexpr (kTile1) mma_16816(d1x, ah[0], ah[1], ah[2], ah[3], old[q][2], old[q][3]);
       mma_16816(d0, ah[0], ah[1], ah[2], ah[3], cur[q][0], cur[q][1]);
-      mma_16816(d1, ah[0], ah[1], ah[2], ah[3], old[q][0], old[q][1]);
+      if constexpr (kTile1) mma_16816(d1, ah[0], ah[1], ah[2], ah[3], old[q][0], old[q][1]);
       mma_16816(d0x, al[0], al[1], al[2], al[3], cur[q][0], cur[q][1]);
-      mma_16816(d1x, al[0], al[1], al[2], al[3], old[q][0], old[q][1]);
+      if constexpr (kTile1) mma_16816(d1x, al[0], al[1], al[2], al[3], old[q][0], old[q][1]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { ah[i] = nh[i]; al[i] = nl[i]; }
     }
   };
   const uint32_t *pb_h = Bh, *pb_l = Bl;
   int left = geo.nblk;
+  {
+    const int nq = left < 4 ? left : 4;
+    group(pb_h, pb_l, bp, bq, nq, std::true_type{});
+    left -= nq;
+    pb_h += 32; pb_l += 32;
+  }
 #pragma unroll 1
   for (; left >= 8; left -= 8) {
-    group(pb_h, pb_l, bp, bq, 4);
-    group(pb_h + 32, pb_l + 32, bq, bp, 4);
+    group(pb_h, pb_l, bq, bp, 4, std::false_type{});
+    group(pb_h + 32, pb_l + 32, bp, bq, 4, std::false_type{});
     pb_h += 64; pb_l += 64;
   }
   if (left >= 4) {
-    group(pb_h, pb_l, bp, bq, 4);
-    if (left > 4) group(pb_h + 32, pb_l + 32, bq, bp, left - 4);
+    group(pb_h, pb_l, bq, bp, 4, std::false_type{});
+    if (left > 4) group(pb_h + 32, pb_l + 32, bp, bq, left - 4, std::false_type{});
   } else if (left) {
-    group(pb_h, pb_l, bp, bq, left);
+    group(pb_h, pb_l, bq, bp, left, std::false_type{});
   }
   // tile 0: c0,c1 = lags base, base+1; c2,c3 = base+64, base+65.  tile 1: c2,c3 = base+128, base+129.
   val[0] = d0[0] + d0x[0]; val[1] = d0[1] + d0x[1]; val[2] = d0[2] + d0x[2]; val[3] = d0[3] + d0x[3];

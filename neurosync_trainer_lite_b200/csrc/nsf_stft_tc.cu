@@ -857,6 +857,32 @@ __device__ __forceinline__ void pair_sync(int quarter) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kFStages = 2;
 constexpr int kMelPitch = 129;                       // floats per frame row of the mel tile
+// Finished dB rows of the mel tile -> global memory, one warp per 16 consecutive frame rows (`src` = the first of them in
+// the tile, `g0` its frame index).  Four rows (sixteen loads) are in flight per warp: as one load -> store pair per
+// iteration the loop was pure shared-memory latency, 17 % of the single-CTA kernel's stall samples on C5
+// (ncu source page of capture r02m, round 2).
+__device__ __forceinline__ void store_db_rows(const float* __restrict__ src, float* __restrict__ db, int64_t g0,
+                                              int64_t total_frames, int n_mels, int lane) {
+  const int64_t left = total_frames - g0;
+  const int rows = left >= 16 ? 16 : (left > 0 ? static_cast<int>(left) : 0);
+  float* dst = db + g0 * n_mels;
+  int r = 0;
+  if (n_mels == 128) {
+    for (; r + 4 <= rows; r += 4) {
+      float v[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] = src[(r + i) * kMelPitch + lane + 32 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[(r + i) * 128 + lane + 32 * j] = v[i][j];
+    }
+  }
+  for (; r < rows; ++r)
+    for (int m = lane; m < n_mels; m += 32) dst[static_cast<int64_t>(r) * n_mels + m] = src[r * kMelPitch + m];
+}
 // BM frame rows + one scratch row (sink for rows beyond the batch), rounded so the mbarriers that follow
 // stay 8-byte aligned
 constexpr size_t kMelTileBytes = (static_cast<size_t>(BM + 1) * kMelPitch * sizeof(float) + 15) / 16 * 16;
@@ -1022,12 +1048,8 @@ k_tc_stft_mel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       }
       pair_sync(quarter);
       const int64_t gw = tile0 + quarter * 32;          // first frame of this quarter's 32 rows
-      for (int r = upper ? 16 : 0; r < (upper ? 32 : 16); ++r) {
-        if (gw + r < b.total_frames) {
-          const float* src = mel_acc + (quarter * 32 + r) * kMelPitch;
-          for (int m = lane; m < t.n_mels; m += 32) db[(gw + r) * t.n_mels + m] = src[m];
-        }
-      }
+      store_db_rows(mel_acc + (quarter * 32 + (upper ? 16 : 0)) * kMelPitch, db, gw + (upper ? 16 : 0), b.total_frames,
+                    t.n_mels, lane);
       pair_sync(quarter);
       for (int m = upper ? kMelPitch / 2 : 0; m < (upper ? kMelPitch : kMelPitch / 2); ++m) my_acc[m] = 0.0f;
       {
@@ -1239,12 +1261,8 @@ k_tc_stft_mel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       pair_sync(quarter);
       const int64_t gw = tile0 + quarter * 32;          // first frame of this quarter's 32 rows
-      for (int r = upper ? 16 : 0; r < (upper ? 32 : 16); ++r) {
-        if (gw + r < b.total_frames) {
-          const float* src = mel_acc + (quarter * 32 + r) * kMelPitch;
-          for (int m = lane; m < t.n_mels; m += 32) db[(gw + r) * t.n_mels + m] = src[m];
-        }
-      }
+      store_db_rows(mel_acc + (quarter * 32 + (upper ? 16 : 0)) * kMelPitch, db, gw + (upper ? 16 : 0), b.total_frames,
+                    t.n_mels, lane);
       pair_sync(quarter);
       for (int m = upper ? kMelPitch / 2 : 0; m < (upper ? kMelPitch : kMelPitch / 2); ++m) my_acc[m] = 0.0f;
       {
