@@ -556,11 +556,15 @@ def measure_workload(name, scaling, steps, warmup, D, rank, world, local_rank, d
         ms = k["ms"] * 1e-3
         if k["kernel"] == "autocorr":
             nblk = (Fr + 15) // 16                      # K-blocks that hold samples (all-zero blocks are skipped)
-            ex = frames * nblk * 6 * 4096 / ms / 1e12
+            # MMAs the kernel issues per frame (nsf_autocorr_mma.cu, launch_autocorr_mma): the five-tile loop from 44
+            # K-blocks up (5 nblk - 12), the six-MMA loop below (6 nblk minus the 12 zero-operand MMAs of the first group)
+            five = os.environ.get("NSF_AC_LOOP", "")[:1] == "f" or (os.environ.get("NSF_AC_LOOP", "")[:1] != "s" and nblk >= 44)
+            mmas = max((5 if five else 6) * nblk - 12, nblk)
+            ex = frames * mmas * 4096 / ms / 1e12
             # the lag products are a banded Toeplitz matrix-VECTOR product per frame (no operand shared between
             # frames), which only the warp-level HMMA pipe can fill: its measured peak is the relevant ceiling,
             # and the same FLOPs on the fp32 FMA pipe (the reference algorithm's pipe) are given for scale
-            k.update(executed_tflops=round(ex, 1), executed_pipe="mma.sync (HMMA), 3 split-fp16 products",
+            k.update(executed_tflops=round(ex, 1), executed_pipe=f"mma.sync (HMMA), split-fp16 products, {mmas} MMAs per frame",
                      executed_peak=hmma_peak, executed_frac=round(ex / hmma_peak, 4),
                      fp32_fma_peak=round(fma_peak, 1), frac_of_fp32_fma_peak=round(k["achieved"] / fma_peak, 4))
         elif k["kernel"] == "stft_gemm":
