@@ -339,6 +339,30 @@ __device__ __forceinline__ void am_mma(const __half* copies, const AmGeom& geo, 
   __syncwarp();
 }
 
+// Final step of the five-tile loops: the three cross-correlation tiles folded onto lags 0 .. 191, r[lag] / r[0].
+__device__ __forceinline__ void am_mma5_finish(const float (&hh0)[4], const float (&hh1)[4], const float (&cA)[4],
+                                               const float (&cB)[4], const float (&cC)[4], int lane, float (&val)[kVals]) {
+  // Lane (g, tq) holds rows g (c0, c1) and g + 8 (c2, c3), columns 2 tq, 2 tq + 1 of every tile.  With u = 8 g + 2 tq + e:
+  //   hh0: u, 64 + u    hh1: (64 + u), 128 + u    cA: -64 + u, u    cB: 64 + u, 128 + u    cC: -192 + u, -128 + u
+  // C[-(64 k + u)] = entry 64 - u of the tile that starts at -64 (k + 1): for odd u that is lane 31 - L (same e), for
+  // even u lane 32 - L - and for L = 0 (u = 0) the first entry of the NEXT tile, which lane 0 holds itself.
+  const int src_e = (32 - lane) & 31, src_o = 31 - lane;
+  float n0e = __shfl_sync(0xffffffffu, cA[0], src_e), n0o = __shfl_sync(0xffffffffu, cA[1], src_o);
+  float n1e = __shfl_sync(0xffffffffu, cC[2], src_e), n1o = __shfl_sync(0xffffffffu, cC[3], src_o);
+  float n2e = __shfl_sync(0xffffffffu, cC[0], src_e), n2o = __shfl_sync(0xffffffffu, cC[1], src_o);
+  if (lane == 0) { n0e = cA[2]; n1e = cA[0]; n2e = cC[2]; }
+  val[0] = hh0[0] + (cA[2] + n0e); val[1] = hh0[1] + (cA[3] + n0o);
+  val[2] = hh0[2] + (cB[0] + n1e); val[3] = hh0[3] + (cB[1] + n1o);
+  val[4] = hh1[2] + (cB[2] + n2e); val[5] = hh1[3] + (cB[3] + n2o);
+  const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
+  if (r0 != 0.0f) {
+    const float inv = __fdiv_rn(1.0f, r0);
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) val[v] *= inv;
+  }
+  __syncwarp();
+}
+
 // Five MMAs per K-block instead of six (round 2, the product loop).  With x = h + l (fp16 each)
 //     r[lag] = HH[lag] + C[lag] + C[-lag],   HH[lag] = sum_s h(s + lag) h(s),   C[lag] = sum_s h(s + lag) l(s),
 // because sum_s l(s + lag) h(s) = C[-lag]: the two cross products are ONE cross-correlation seen at both signs of the
@@ -435,25 +459,54 @@ __device__ __forceinline__ void am_mma5(const __half* copies, const AmGeom& geo,
       }
     }
   }
-  // Lane (g, tq) holds rows g (c0, c1) and g + 8 (c2, c3), columns 2 tq, 2 tq + 1 of every tile.  With u = 8 g + 2 tq + e:
-  //   hh0: u, 64 + u    hh1: (64 + u), 128 + u    cA: -64 + u, u    cB: 64 + u, 128 + u    cC: -192 + u, -128 + u
-  // C[-(64 k + u)] = entry 64 - u of the tile that starts at -64 (k + 1): for odd u that is lane 31 - L (same e), for
-  // even u lane 32 - L - and for L = 0 (u = 0) the first entry of the NEXT tile, which lane 0 holds itself.
-  const int src_e = (32 - lane) & 31, src_o = 31 - lane;
-  float n0e = __shfl_sync(0xffffffffu, cA[0], src_e), n0o = __shfl_sync(0xffffffffu, cA[1], src_o);
-  float n1e = __shfl_sync(0xffffffffu, cC[2], src_e), n1o = __shfl_sync(0xffffffffu, cC[3], src_o);
-  float n2e = __shfl_sync(0xffffffffu, cC[0], src_e), n2o = __shfl_sync(0xffffffffu, cC[1], src_o);
-  if (lane == 0) { n0e = cA[2]; n1e = cA[0]; n2e = cC[2]; }
-  val[0] = hh0[0] + (cA[2] + n0e); val[1] = hh0[1] + (cA[3] + n0o);
-  val[2] = hh0[2] + (cB[0] + n1e); val[3] = hh0[3] + (cB[1] + n1o);
-  val[4] = hh1[2] + (cB[2] + n2e); val[5] = hh1[3] + (cB[3] + n2o);
-  const float r0 = __shfl_sync(0xffffffffu, val[0], 0);  // lag 0 lives in lane 0
-  if (r0 != 0.0f) {
-    const float inv = __fdiv_rn(1.0f, r0);
+  am_mma5_finish(hh0, hh1, cA, cB, cC, lane, val);
+}
+
+// am_mma5 with the number of K-blocks known at compile time (F = 266: seventeen), unrolled completely: every range check
+// of the lead-in and of the far end resolves at compile time, the rings are indexed by constants, and the tiles whose B
+// block lies before the frame (cB, hh1 for m < 4: zero fragments) are not issued either - 5 NBLK - 12 MMAs and one
+// ldmatrix.x4 + at most four 32-bit loads per block, no loop control.  Same products into the same accumulators in the
+// same order as am_mma5 (the skipped MMAs add exact zeros), so the rows are identical.  Used where the generic loop's
+// lead-in and checks cost more than the MMAs it saves over the six-MMA loop (short frames; launch_autocorr_mma).
+template <int NBLK>
+__device__ __forceinline__ void am_mma5_static(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals]) {
+  static_assert(NBLK >= 13 && NBLK <= 24, "unrolled loop: short frames only");
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
+  const uint32_t* E_lo = E_hi + geo.len / 2;
+  const uint32_t* O_hi = E_lo + geo.len / 2;
+  const uint32_t* O_lo = O_hi + geo.len / 2;
+  const int mi = lane >> 3, mr = lane & 7;
+  const uint32_t a_off = 2u * static_cast<uint32_t>(kFrontMargin + 8 * mr + (mi & 1) * 64 + (mi >> 1) * 8);
+  const uint32_t sa0 = am_smem_u32(copies) + a_off;
+  const int boff = kFrontMargin + 2 * tq - g - (g & 1);
+  const uint32_t* Bh = ((g & 1) ? O_hi : E_hi) + boff / 2;
+  const uint32_t* Bl = ((g & 1) ? O_lo : E_lo) + boff / 2;
+  float hh0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, hh1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float cA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cB[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cC[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  uint32_t bh[8][2], bl[16][2];                 // slot = block index mod 8 / mod 16
 #pragma unroll
-    for (int v = 0; v < kVals; ++v) val[v] *= inv;
+  for (int q = 0; q < 8; ++q) bh[q][0] = bh[q][1] = 0u;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) bl[q][0] = bl[q][1] = 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { bl[q][0] = Bl[8 * q]; bl[q][1] = Bl[8 * q + 4]; }   // B_l(0 .. 3)
+  uint32_t a[4], an[4];
+  ldsm_x4(sa0 - 32u * 8u, a);
+#pragma unroll
+  for (int m = -8; m < NBLK; ++m) {
+    ldsm_x4(sa0 + static_cast<uint32_t>(32 * (m + 1)), an);      // the block beyond the last reads the zero margin
+    if (m >= 0) { bh[m & 7][0] = Bh[8 * m]; bh[m & 7][1] = Bh[8 * m + 4]; }
+    if (m >= 4) mma_16816(cB, a[0], a[1], a[2], a[3], bl[(m - 4) & 15][0], bl[(m - 4) & 15][1]);            // B_l(m - 4)
+    if (m + 12 < NBLK) { bl[(m + 12) & 15][0] = Bl[8 * (m + 12)]; bl[(m + 12) & 15][1] = Bl[8 * (m + 12) + 4]; }
+    if (m >= 4) mma_16816(hh1, a[0], a[1], a[2], a[3], bh[(m - 4) & 7][0], bh[(m - 4) & 7][1]);             // B_h(m - 4)
+    if (m >= -4 && m + 4 < NBLK) mma_16816(cA, a[0], a[1], a[2], a[3], bl[(m + 4) & 15][0], bl[(m + 4) & 15][1]);
+    if (m >= 0) mma_16816(hh0, a[0], a[1], a[2], a[3], bh[m & 7][0], bh[m & 7][1]);                         // B_h(m)
+    if (m + 12 < NBLK) mma_16816(cC, a[0], a[1], a[2], a[3], bl[(m + 12) & 15][0], bl[(m + 12) & 15][1]);   // B_l(m + 12)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = an[i];
   }
-  __syncwarp();
+  am_mma5_finish(hh0, hh1, cA, cB, cC, lane, val);
 }
 
 __device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane, int n_lags, float thr) {
@@ -633,6 +686,18 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
   const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * n_warps + warp) * chunk;
   const int64_t r_end = min(r_begin + chunk, b.total_rows);
   int64_t base = 0, len = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
+  // the MMA half of a frame: six-MMA loop, five-tile loop, or (F = 266, the 16 kHz plan: seventeen K-blocks) the
+  // five-tile loop unrolled at compile time
+  auto run_mma = [&](float (&val)[kVals]) {
+    if constexpr (kFive) {
+      if constexpr (kIters == 5 && kExact) {
+        if (geo.nblk == 17) { am_mma5_static<17>(copies, geo, lane, val); return; }
+      }
+      am_mma5(copies, geo, lane, val);
+    } else {
+      am_mma(copies, geo, lane, val);
+    }
+  };
 #ifdef NSF_AC_TRACE
   int trace_i = 0;
   if (threadIdx.x == 0 && blockIdx.x < 296) { int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_ac_smid[blockIdx.x] = sm; }
@@ -671,16 +736,14 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
       if (tr) trp[1] = clock64();
 #endif
       float val[kVals];
-      if (kFive) am_mma5(copies, geo, lane, val);         // both end with __syncwarp: the buffer may be rewritten
-      else am_mma(copies, geo, lane, val);
+      run_mma(val);                                       // ends with __syncwarp: the buffer may be rewritten
 #ifdef NSF_AC_TRACE
       if (tr) trp[2] = clock64();
       ++trace_i;
 #endif
       if (T > 1 && (tf == 0 || tf == T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
         am_fill_simple(t, hann, am_src(t, b, y, base, len, tf == 0 ? 1 : T - 2, n_it), copies, geo, lane);
-        if (kFive) am_mma5(copies, geo, lane, val);
-        else am_mma(copies, geo, lane, val);
+        run_mma(val);
       }
 #pragma unroll
       for (int v = 0; v < kVals; ++v) acc[v] += val[v];
@@ -716,7 +779,10 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
     const char* v = std::getenv("NSF_AC_LOOP");
     return v == nullptr ? 0 : (v[0] == 's' ? 6 : (v[0] == 'f' ? 5 : 0));
   }();
-  const bool use_six = loop_env == 6 || (loop_env == 0 && geo.nblk < 44);
+  // F = 266 (iters == 5, seventeen K-blocks) has the five-tile loop unrolled at compile time (am_mma5_static), which
+  // has neither the lead-in overhead nor the checks
+  const bool static_five = iters == 5 && geo.nblk == 17;
+  const bool use_six = loop_env == 6 || (loop_env == 0 && geo.nblk < 44 && !static_five);
   // symmetric kernel: as many warps per block as fit twice per SM (eight up to F ~ 1530, fewer for long frames);
   // two blocks of 113 KB (+ 1 KB reserved each) are what an SM's 228 KB hold
   int warps = kSymWarps;
