@@ -7,6 +7,7 @@ TAG=$1
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"
+python __graft_entry__.py --smoke > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"
 python bench.py > $O/${TAG}_n1.json 2> $O/${TAG}_n1.err; echo "bench rc=$?"
 python bench.py --impl reference > $O/${TAG}_ref_n1.json 2> $O/${TAG}_ref_n1.err; echo "ref rc=$?"
 python bench.py --steps 2 --warmup 1 --no-extras --no-cpu-baseline > $O/${TAG}_plain.log 2>&1 &&
