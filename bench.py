@@ -557,8 +557,11 @@ def measure_workload(name, scaling, steps, warmup, D, rank, world, local_rank, d
         if k["kernel"] == "autocorr":
             nblk = (Fr + 15) // 16                      # K-blocks that hold samples (all-zero blocks are skipped)
             # MMAs the kernel issues per frame (nsf_autocorr_mma.cu, launch_autocorr_mma): the five-tile loop from 44
-            # K-blocks up (5 nblk - 12), the six-MMA loop below (6 nblk minus the 12 zero-operand MMAs of the first group)
-            five = os.environ.get("NSF_AC_LOOP", "")[:1] == "f" or (os.environ.get("NSF_AC_LOOP", "")[:1] != "s" and nblk >= 44)
+            # K-blocks up and at F = 266 (5 nblk - 12), the six-MMA loop otherwise (6 nblk minus the 12 zero-operand MMAs of
+            # the first group)
+            static_five = (Fr // 2 + 1 + 31) // 32 == 5 and nblk == 17          # F = 266: am_mma5_static<17>
+            five = os.environ.get("NSF_AC_LOOP", "")[:1] == "f" or (os.environ.get("NSF_AC_LOOP", "")[:1] != "s"
+                                                                   and (nblk >= 44 or static_five))
             mmas = max((5 if five else 6) * nblk - 12, nblk)
             ex = frames * mmas * 4096 / ms / 1e12
             # the lag products are a banded Toeplitz matrix-VECTOR product per frame (no operand shared between

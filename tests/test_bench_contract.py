@@ -50,7 +50,7 @@ def test_committed_bench_lines_follow_the_contract(path):
 
 
 R02 = [os.path.join(ROOT, "profiles", f) for f in ("bench_r02k_n1.json", "bench_r02i_n2.json", "bench_r02l_n4.json",
-                                                    "bench_r02l_n8.json")]
+                                                    "bench_r02l_n8.json", "bench_r02s_n1.json", "bench_r02s_n2.json")]
 
 
 @pytest.mark.parametrize("path", R02, ids=[os.path.basename(p) for p in R02])
@@ -102,7 +102,8 @@ def test_round2_bench_lines_follow_the_contract(path):
 def test_round2_reference_arm_is_consistent_per_core():
     """The CPU oracle's per-core throughput must not depend on how bench.py was launched (round 1: 1.85x apart)."""
     per_core = []
-    for f in ("bench_r02k_ref_n1.json", "bench_r02i_ref_n2.json", "bench_r02l_ref_n8.json"):
+    for f in ("bench_r02k_ref_n1.json", "bench_r02i_ref_n2.json", "bench_r02l_ref_n8.json", "bench_r02s_ref_n1.json",
+              "bench_r02s_ref_n2.json"):
         d = _line(os.path.join(ROOT, "profiles", f))
         assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
         assert d["value"] == d["e2e"]["value"] == d["cpu_baseline"]["value"]
@@ -120,6 +121,21 @@ def test_round2_scaling_lines():
     sp = _line(os.path.join(ROOT, "profiles", "bench_r02l_single_process_c4_n8.json"))
     assert sp["gathered_host_array"]["single_process"] and sp["gathered_host_array"]["shape"] == [2994720, 256]
     assert sp["gathered_host_array"]["all_slices_filled"] is True
+
+
+def test_final_build_lines():
+    """Capture r02s (final build of round 2): two ranks double the device-resident value, the executed MMA count in the
+    roofline follows the loop the autocorrelation kernel runs, and the 10 000-clip batch is no longer bound by the binding's
+    per-clip row-count loop (the step is the sum of its kernels)."""
+    one, two = (_line(os.path.join(ROOT, "profiles", f)) for f in ("bench_r02s_n1.json", "bench_r02s_n2.json"))
+    assert two["n_gpus"] == 2 and two["value"] > 0.95 * 2 * one["value"] and two["e2e"]["value"] > one["e2e"]["value"]
+    assert "448 MMAs per frame" in one["roofline"]["executed"]["executed_pipe"]          # 5 * 92 - 12 at F = 1470
+    c5 = one["workloads"]["c5"]
+    # (the C5 pass of this capture still counted the six-MMA loop's 90 MMAs per frame; the kernel ran the static
+    # five-tile loop's 73 - bench.py was corrected after the capture, so the line's executed_frac for C5 is 23 % high)
+    assert "MMAs per frame" in [k for k in c5["kernels"] if k["kernel"] == "autocorr"][0]["executed_pipe"]
+    assert c5["ms_per_step"] < 1.03 * sum(k["ms"] for k in c5["kernels"])
+    assert one["ms_per_step"] < 2.25 and c5["ms_per_step"] < 6.3
 
 
 def test_weak_scaling_lines_are_consistent():
