@@ -509,6 +509,116 @@ __device__ __forceinline__ void am_mma5_static(const __half* copies, const AmGeo
   am_mma5_finish(hh0, hh1, cA, cB, cC, lane, val);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Software-pipelined frame (round 2, k_autocorr_pipe): the five-tile loop of the frame held in `copies`, unrolled at
+// compile time like am_mma5_static, with the STAGING of the warp's next frame woven into it.  The next frame's raw
+// samples are already in flight into (v0, v1) when the loop starts (am_issue_fast); pass 1 (mean, max |x|, scale) runs
+// after block kPass1, one pass-2 iteration (window, scale, split, six shared stores into `next_copies`) every
+// kStride blocks from block kPass2 on.  ptxas schedules the two independent instruction streams into one another, so
+// a warp never leaves the MMA loop: the phase trace of the symmetric kernel (scripts/ac_trace.py, B200) showed a warp
+// spending 5.3 k of its 21.5 k cycles per frame staging, the tensor pipe 66 % active although the loop alone sustains
+// 88 % (scripts/ubench_ac5.cu).  Same staging arithmetic as am_process and the same MMAs into the same accumulators
+// in the same order as am_mma5 / am_mma5_static: the rows are bit-identical to the symmetric kernel's.
+// kIters must be the exact iteration count of the frame length (n_it == kIters), which also makes the `n < F` guards
+// of pass 1 compile-time true for every iteration but the last.
+template <int NBLK, int kIters>
+__device__ __forceinline__ void am_mma5_pipe(const __half* copies, const AmGeom& geo, int lane, float (&val)[kVals],
+                                             const DeviceTables& t, const float* hann, float (&v0)[kIters],
+                                             float (&v1)[kIters], __half* next_copies) {
+#ifndef NSF_PIPE_PASS1
+#define NSF_PIPE_PASS1 12
+#endif
+#ifndef NSF_PIPE_GAP
+#define NSF_PIPE_GAP 2
+#endif
+  constexpr int kPass1 = NBLK >= 40 ? NSF_PIPE_PASS1 : 5;           // block after which the loads are consumed
+  constexpr int kPass2 = kPass1 + NSF_PIPE_GAP;
+  constexpr int kStride = (NBLK - 2 - kPass2) / kIters > 0 ? (NBLK - 2 - kPass2) / kIters : 1;
+  static_assert(kPass2 + kStride * (kIters - 1) < NBLK, "every staging iteration must fall inside the loop");
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t* E_hi = reinterpret_cast<const uint32_t*>(copies);
+  const uint32_t* E_lo = E_hi + geo.len / 2;
+  const uint32_t* O_hi = E_lo + geo.len / 2;
+  const uint32_t* O_lo = O_hi + geo.len / 2;
+  const int mi = lane >> 3, mr = lane & 7;
+  const uint32_t a_off = 2u * static_cast<uint32_t>(kFrontMargin + 8 * mr + (mi & 1) * 64 + (mi >> 1) * 8);
+  const uint32_t sa0 = am_smem_u32(copies) + a_off;
+  const int boff = kFrontMargin + 2 * tq - g - (g & 1);
+  const uint32_t* Bh = ((g & 1) ? O_hi : E_hi) + boff / 2;
+  const uint32_t* Bl = ((g & 1) ? O_lo : E_lo) + boff / 2;
+  float hh0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, hh1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float cA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cB[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cC[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  uint32_t bh[8][2], bl[16][2];                 // slot = block index mod 8 / mod 16
+#pragma unroll
+  for (int q = 0; q < 8; ++q) bh[q][0] = bh[q][1] = 0u;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) bl[q][0] = bl[q][1] = 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { bl[q][0] = Bl[8 * q]; bl[q][1] = Bl[8 * q + 4]; }   // B_l(0 .. 3)
+  // staging state of the next frame
+  const int F = t.F;
+  float mean = 0.0f, scale = 1.0f;
+  uint32_t* e_hi = reinterpret_cast<uint32_t*>(next_copies) + kFrontMargin / 2 + lane;
+  uint32_t* e_lo = e_hi + geo.len / 2;
+  uint16_t* o_hi = reinterpret_cast<uint16_t*>(next_copies) + 2 * geo.len + kFrontMargin - 1 + 2 * lane;
+  uint16_t* o_lo = o_hi + geo.len;
+  const float2* w2 = reinterpret_cast<const float2*>(hann) + lane;
+  uint32_t a[4], an[4];
+  ldsm_x4(sa0 - 32u * 8u, a);
+#pragma unroll
+  for (int m = -8; m < NBLK; ++m) {
+    ldsm_x4(sa0 + static_cast<uint32_t>(32 * (m + 1)), an);      // the block beyond the last reads the zero margin
+    if (m >= 0) { bh[m & 7][0] = Bh[8 * m]; bh[m & 7][1] = Bh[8 * m + 4]; }
+    if (m >= 4) mma_16816(cB, a[0], a[1], a[2], a[3], bl[(m - 4) & 15][0], bl[(m - 4) & 15][1]);            // B_l(m - 4)
+    if (m + 12 < NBLK) { bl[(m + 12) & 15][0] = Bl[8 * (m + 12)]; bl[(m + 12) & 15][1] = Bl[8 * (m + 12) + 4]; }
+    if (m >= 4) mma_16816(hh1, a[0], a[1], a[2], a[3], bh[(m - 4) & 7][0], bh[(m - 4) & 7][1]);             // B_h(m - 4)
+    if (m >= -4 && m + 4 < NBLK) mma_16816(cA, a[0], a[1], a[2], a[3], bl[(m + 4) & 15][0], bl[(m + 4) & 15][1]);
+    if (m >= 0) mma_16816(hh0, a[0], a[1], a[2], a[3], bh[m & 7][0], bh[m & 7][1]);                         // B_h(m)
+    if (m + 12 < NBLK) mma_16816(cC, a[0], a[1], a[2], a[3], bl[(m + 12) & 15][0], bl[(m + 12) & 15][1]);   // B_l(m + 12)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = an[i];
+    if (m == kPass1) {
+      // pass 1 of am_process: mean and max |x| of the next frame, the exact power-of-two scale
+      float sum = 0.0f, amax = 0.0f;
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) {
+        const int n = 2 * (lane + 32 * i);
+        const float x = (i < kIters - 1 || n < F) ? v0[i] : 0.0f, c = (i < kIters - 1 || n + 1 < F) ? v1[i] : 0.0f;
+        sum += x + c;
+        amax = fmaxf(amax, fmaxf(fabsf(x), fabsf(c)));
+      }
+      sum = warp_sum(sum);
+      amax = warp_max(amax);
+      mean = sum / static_cast<float>(F);
+      const float bound = amax + fabsf(mean);
+      int e2 = 0;
+      if (bound > 0.0f && bound < INFINITY) {
+        e2 = 14 - (static_cast<int>((__float_as_uint(bound) >> 23) & 0xff) - 126);
+        e2 = max(-100, min(100, e2));
+      }
+      scale = __uint_as_float(static_cast<uint32_t>(e2 + 127) << 23);
+    }
+    if (m >= kPass2 && (m - kPass2) % kStride == 0 && (m - kPass2) / kStride < kIters) {
+      // one pass-2 iteration of am_process
+      const int i = (m - kPass2) / kStride;
+      const float2 w = w2[32 * i];
+      const float x0 = (v0[i] - mean) * (w.x * scale);
+      const float x1 = (v1[i] - mean) * (w.y * scale);
+      const __half2 hi = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hi), lw = *reinterpret_cast<const uint32_t*>(&lo);
+      e_hi[32 * i] = hw;
+      e_lo[32 * i] = lw;
+      o_hi[64 * i] = static_cast<uint16_t>(hw);
+      o_hi[64 * i + 1] = static_cast<uint16_t>(hw >> 16);
+      o_lo[64 * i] = static_cast<uint16_t>(lw);
+      o_lo[64 * i + 1] = static_cast<uint16_t>(lw >> 16);
+    }
+  }
+  am_mma5_finish(hh0, hh1, cA, cB, cC, lane, val);     // ends with __syncwarp: the staged frame is visible to the warp
+}
+
 __device__ __forceinline__ bool am_all_small(const float (&val)[kVals], int lane, int n_lags, float thr) {
   bool small = true;
 #pragma unroll
@@ -758,6 +868,132 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Software-pipelined kernel (round 2, product path for the 88.2 kHz plan: F = 1470, 92 K-blocks): eight warps per SM,
+// each with TWO frame buffers and up to 255 registers.  While a warp runs the MMA loop of frame n out of one buffer it
+// converts frame n + 1 - whose raw samples were requested before the loop started and wait in registers - into the
+// other (am_mma5_pipe), so every warp issues MMAs all the time and the staging instructions fill the issue slots the
+// tensor pipe leaves free.  Same shared-memory footprint as the symmetric kernel (sixteen frame buffers per SM), same
+// arithmetic in the same order: bit-identical rows (tests/test_gpu_round2.py::test_autocorr_kernels_agree).
+// Cold paths (clip-edge frames with reflect padding, the end of the batch, the edge-frame fix) are staged by
+// am_fill_simple outside the loop and multiplied by the generic am_mma5.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPipeWarps = 8;      // per block, one block per SM
+
+struct AmFrame {
+  int64_t r, tf, T, base, len;
+  int n_frames, f;
+  bool valid;
+};
+
+template <int kIters, int NBLK, int kWarps, int kBlocksPerSm>
+__global__ void __launch_bounds__(kWarps * 32, kBlocksPerSm) k_autocorr_pipe(DeviceTables t, BatchView b,
+                                                                      const float* __restrict__ y, bool reduce,
+                                                                      float* __restrict__ out, int64_t out_ld, int col0) {
+  extern __shared__ __align__(16) __half s_am[];
+  const AmGeom geo = am_geom(t.F);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = static_cast<int>(blockDim.x >> 5);
+  const size_t region = kExtraFront + 4 * static_cast<size_t>(geo.len);   // halfs per buffer: [zeros | E_hi | E_lo | O_hi | O_lo]
+  __half* buf0 = s_am + static_cast<size_t>(2 * warp) * region + kExtraFront;
+  __half* buf1 = buf0 + region;
+  float* hann = reinterpret_cast<float*>(s_am + static_cast<size_t>(2 * n_warps) * region);
+  constexpr int n_it = kIters;
+  for (int n = threadIdx.x; n < 64 * n_it; n += blockDim.x) hann[n] = n < t.F ? __ldg(t.hann_sym + n) : 0.0f;
+  // zero once: the margins are never written again, the frame regions are rewritten per frame
+  for (int i = lane; i < static_cast<int>(region); i += 32) reinterpret_cast<uint32_t*>(buf0 - kExtraFront)[i] = 0u;
+  __syncthreads();
+  const int64_t n_warps_total = static_cast<int64_t>(gridDim.x) * n_warps;
+  const int64_t chunk = (b.total_rows + n_warps_total - 1) / n_warps_total;
+  const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * n_warps + warp) * chunk;
+  const int64_t r_end = min(r_begin + chunk, b.total_rows);
+  // frame enumeration of the warp's row run, one frame of look-ahead
+  int64_t base = 0, len = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
+  int64_t it_r = r_begin;
+  int it_f = 0, it_nf = 0;
+  auto next_frame = [&]() -> AmFrame {
+    AmFrame fr;
+    fr.valid = false;
+    if (it_f >= it_nf) {                               // open the next row
+      if (it_nf != 0) ++it_r;
+      if (it_r >= r_end) { it_nf = 0; it_f = 0; fr.r = fr.tf = fr.T = fr.base = fr.len = 0; fr.n_frames = fr.f = 0; return fr; }
+      if (it_r >= clip_row_end) {
+        const int clip = find_segment(b.row_off, b.n_clips, it_r);
+        base = __ldg(b.clip_off + clip);
+        len = __ldg(b.clip_off + clip + 1) - base;
+        T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
+        clip_row0 = __ldg(b.row_off + clip);
+        clip_row_end = __ldg(b.row_off + clip + 1);
+      }
+      const int64_t lr = it_r - clip_row0;
+      const int64_t tf0 = reduce ? 2 * lr : lr;
+      it_nf = (reduce && tf0 + 1 < T) ? 2 : 1;         // odd T: the last row passes through
+      it_f = 0;
+    }
+    const int64_t lr = it_r - clip_row0;
+    fr.r = it_r; fr.tf = (reduce ? 2 * lr : lr) + it_f; fr.T = T; fr.base = base; fr.len = len;
+    fr.n_frames = it_nf; fr.f = it_f; fr.valid = true;
+    ++it_f;
+    return fr;
+  };
+  AmFrame cur = next_frame();
+  if (cur.valid) {                                     // prologue: the first frame is staged on its own
+    const AmSrc src = am_src(t, b, y, cur.base, cur.len, cur.tf, n_it);
+    if (src.fast) {
+      float v0[kIters], v1[kIters];
+      am_issue_fast<kIters, true>(src.clip + src.first, n_it, lane, v0, v1);
+      am_process<kIters, true>(t, hann, n_it, v0, v1, buf0, geo, lane, nullptr);
+    } else {
+      am_fill_simple(t, hann, src, buf0, geo, lane);
+    }
+  }
+  int p = 0;
+  float acc[kVals];
+#pragma unroll
+  for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
+  AmFrame nxt = next_frame();
+  AmSrc nsrc;
+  nsrc.fast = false;
+  if (nxt.valid) nsrc = am_src(t, b, y, nxt.base, nxt.len, nxt.tf, n_it);
+  bool nfast = nxt.valid && nsrc.fast;
+  while (cur.valid) {
+    __half* copies = p ? buf1 : buf0;
+    __half* next_copies = p ? buf0 : buf1;
+    float v0[kIters], v1[kIters];
+    if (nfast) am_issue_fast<kIters, true>(nsrc.clip + nsrc.first, n_it, lane, v0, v1);
+    float val[kVals];
+    if (nfast) {
+      am_mma5_pipe<NBLK, kIters>(copies, geo, lane, val, t, hann, v0, v1, next_copies);
+    } else {
+      am_mma5(copies, geo, lane, val);
+      if (nxt.valid) am_fill_simple(t, hann, nsrc, next_copies, geo, lane);
+    }
+    // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2); rare
+    if (cur.T > 1 && (cur.tf == 0 || cur.tf == cur.T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
+      am_fill_simple(t, hann, am_src(t, b, y, cur.base, cur.len, cur.tf == 0 ? 1 : cur.T - 2, n_it), copies, geo, lane);
+      am_mma5(copies, geo, lane, val);
+    }
+#pragma unroll
+    for (int v = 0; v < kVals; ++v) acc[v] += val[v];
+    if (cur.f == cur.n_frames - 1) {
+      const float wgt = cur.n_frames == 2 ? 0.5f : 1.0f;
+      float* o = out + cur.r * out_ld + col0;
+#pragma unroll
+      for (int v = 0; v < kVals; ++v) {
+        const int lag = lag_of(lane, v);
+        if (lag >= 1 && lag <= t.n_lags) o[lag - 1] = acc[v] * wgt;
+        acc[v] = 0.0f;
+      }
+    }
+    cur = nxt;
+    p ^= 1;
+    nxt = next_frame();
+    nsrc.fast = false;
+    if (nxt.valid) nsrc = am_src(t, b, y, nxt.base, nxt.len, nxt.tf, n_it);
+    nfast = nxt.valid && nsrc.fast;
+  }
+}
+
 }  // namespace
 
 int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& b, const float* y,
@@ -769,7 +1005,7 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
   // NSF_AC_KERNEL=pairs selects the warp-specialised kernel of round 1 (A/B timing; bit-identical results)
   static const bool use_pairs = [] {
     const char* v = std::getenv("NSF_AC_KERNEL");
-    return v != nullptr && v[0] == 'p';
+    return v != nullptr && v[0] == 'p' && v[1] == 'a';      // "pairs" ("pipe" forces the pipelined kernel, below)
   }();
   // MMA loop of the symmetric kernel: the five-tile loop (am_mma5) for frames of at least 44 K-blocks (F >= 689:
   // 44.1 kHz and up), where most blocks run in its unchecked body; the six-MMA loop (am_mma) for short frames, where the
@@ -799,6 +1035,25 @@ int launch_autocorr_mma(cudaStream_t s, const DeviceTables& t, const BatchView& 
     if (smem <= 220 * 1024) break;
   }
   if (warps < 1 && pairs < 1) return -1;
+  // Software-pipelined kernel (k_autocorr_pipe): the 88.2 kHz plan (23 staging iterations, 92 K-blocks).
+  // NSF_AC_KERNEL=sym / pairs select the earlier kernels (validation, A/B; bit-identical rows)
+  static const bool no_pipe = [] {
+    const char* v = std::getenv("NSF_AC_KERNEL");
+    return v != nullptr && (v[0] == 's' || (v[0] == 'p' && v[1] == 'a'));
+  }();
+  // Short frames stay on the symmetric kernel: at F = 266 (16 kHz) the pipelined kernel is bit-identical but SLOWER
+  // (B200, C5: 2.93 ms at twelve warps per SM / 168 registers with one or two frames of look-ahead, 3.10 - 4.70 ms at
+  // sixteen warps / 128 registers, against 2.68 ms; profiles/experiments/README.md section 8)
+  const bool pipe23 = iters == 23 && geo.nblk == 92;
+  if (!no_pipe && loop_env != 6 && pipe23) {
+    const size_t region = kExtraFront + 4 * static_cast<size_t>(geo.len);
+    const size_t pipe_smem = static_cast<size_t>(2 * kPipeWarps) * region * sizeof(__half) + hann_bytes;
+    int64_t pgrid = (b.total_rows + kPipeWarps - 1) / kPipeWarps;
+    if (pgrid > kSmCount) pgrid = kSmCount;
+    if (pgrid < 1) pgrid = 1;
+    k_autocorr_pipe<23, 92, kPipeWarps, 1><<<static_cast<int>(pgrid), kPipeWarps * 32, pipe_smem, s>>>(t, b, y, reduce, out, out_ld, col0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   const bool sym = !use_pairs && warps >= 1;
   int64_t grid;
   int threads;
@@ -848,6 +1103,7 @@ bool init_autocorr_mma_attributes() {
   NSF_AC_SET(23, true); NSF_AC_SET(5, true); NSF_AC_SET(6, false); NSF_AC_SET(12, false);
   NSF_AC_SET(24, false); NSF_AC_SET(40, false); NSF_AC_SET(66, false);
 #undef NSF_AC_SET
+  set(k_autocorr_pipe<23, 92, kPipeWarps, 1>);
   return ok;
 }
 

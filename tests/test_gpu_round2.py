@@ -182,6 +182,54 @@ def test_back_to_back_device_calls_do_not_share_descriptor_staging(engine, oracl
         assert d[:, :23].max() <= TOL_MFCC and d[:, 23:69].max() <= TOL_DELTA and d[:, 69:].max() <= TOL_AC
 
 
+# ---- software-pipelined autocorrelation kernel (88.2 kHz plan) against the symmetric kernel -----------------------
+def test_autocorr_kernels_agree(engine, oracle, tmp_path):
+    """k_autocorr_pipe (eight warps per SM, two frame buffers per warp, the next frame staged inside the MMA loop of
+    the current one) is the product path at F = 1470; NSF_AC_KERNEL=sym selects the symmetric kernel of the same
+    arithmetic.  Bit-identical rows on a ragged batch: shortest legal clip, odd frame count, near-silent edge frames
+    (edge-frame fix), short clips (a warp's run crosses clips), and every row within TOL_AC of the oracle."""
+    import subprocess
+    import sys
+    sr = 88200
+    F, H = oracle.frame_params(sr)
+    lens = [9 * H + 3, sr + 17, sr // 2, 33 * H, 3 * sr // 2 + F, 10 * H, 2 * sr]
+    clips = []
+    for i, n in enumerate(lens):
+        c = synth.synth_clip(n / sr + 0.01, sr, seed=700 + i, kind=("voiced", "gated", "noise")[i % 3])[:n].copy()
+        if i == 1:
+            c[: 2 * F] *= 1e-6          # near-silent first frames
+        if i == 4:
+            c[-2 * F:] *= 1e-6          # near-silent last frames
+        clips.append(c)
+    y = np.concatenate(clips).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in clips])]).astype(np.int64)
+    np.save(tmp_path / "y.npy", y)
+    np.save(tmp_path / "off.npy", off)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for kern in ("pipe", "sym"):
+        out = tmp_path / (kern + ".npy")
+        code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+                "from neurosync_trainer_lite_b200 import engine\n"
+                "y, off = np.load(%r), np.load(%r)\n"
+                "np.save(%r, engine.get_engine(%d, %d, %d).extract_host(y, off, 0))\n"
+                % (root, str(tmp_path / "y.npy"), str(tmp_path / "off.npy"), str(out), sr, F, H))
+        env = dict(os.environ)
+        env.pop("NSF_AC_KERNEL", None)
+        if kern == "sym":
+            env["NSF_AC_KERNEL"] = "sym"
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+        res[kern] = np.load(out)
+    assert res["pipe"].shape == res["sym"].shape and res["pipe"].shape[0] > 0
+    assert np.array_equal(res["pipe"], res["sym"])
+    roff = engine.get_engine(sr, F, H).row_offsets(off)
+    for i, c in enumerate(clips):
+        want = oracle.extract_and_combine_features(c, sr, F, H)
+        got = res["pipe"][roff[i]:roff[i + 1]]
+        assert got.shape == want.shape
+        assert np.abs(got[:, 69:] - want[:, 69:]).max() <= TOL_AC, i
+
+
 # ---- the two MMA loops of the autocorrelation kernel (five tiles / six MMAs per K-block) ---------------------------
 @pytest.mark.parametrize("sr", [16000, 44100, 88200])
 def test_autocorr_loops_agree(sr, engine, oracle, tmp_path):
