@@ -138,6 +138,32 @@ def test_final_build_lines():
     assert one["ms_per_step"] < 2.25 and c5["ms_per_step"] < 6.3
 
 
+def test_pipelined_build_lines():
+    """Capture r02t (software-pipelined autocorrelation kernel at F = 1470), 1 / 2 / 4 / 8 GPUs under torchrun: the
+    device-resident value is linear in the ranks, every line follows the contract, the autocorrelation stage is faster
+    than the symmetric kernel's 1.12 ms in every pass that is not the power-capped headline pass, and the 8-GPU line
+    carries C4's rows gathered into one page-locked host array."""
+    lines = {n: _line(os.path.join(ROOT, "profiles", f"bench_r02t_n{n}.json")) for n in (1, 2, 4, 8)}
+    for n, d in lines.items():
+        assert REQUIRED <= set(d), REQUIRED - set(d)
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["gpu_launches"] > 0
+        assert d["value"] > 0.97 * n * lines[1]["value"]
+        assert d["e2e"]["value"] > 0.9 * (lines[1]["e2e"]["value"] if n == 1 else 1.5 * lines[1]["e2e"]["value"])
+        assert 0.9 <= d["copy_ceiling"]["e2e_frac_of_ceiling"] <= 1.25
+        assert d["parity"]["autocorr_max_abs"] < 2e-5 and d["parity"]["mfcc_max_abs"] < 1e-4
+    one = lines[1]
+    assert one["ms_per_step"] < 2.12 and one["roofline"]["kernel"] == "autocorr" and one["roofline"]["ms_per_launch"] < 1.11
+    assert "448 MMAs per frame" in one["roofline"]["executed"]["executed_pipe"]
+    assert one["roofline"]["traffic_source"] == "profiles/ncu_traffic_r02s.json" or "r02" in one["roofline"]["traffic_source"]
+    for w in ("c3", "c4"):
+        ac = [k for k in one["workloads"][w]["kernels"] if k["kernel"] == "autocorr"][0]
+        assert ac["ms"] < 1.08
+    g = lines[8]["workloads"]["c4"]["gathered_host_array"]
+    assert g["shape"] == [2994720, 256] and g["all_slices_filled"] is True
+    ref = _line(os.path.join(ROOT, "profiles", "bench_r02t_ref_n1.json"))
+    assert ref["impl"] == "reference" and ref["gpu_launches"] == 0 and ref["value"] == ref["cpu_baseline"]["value"]
+
+
 def test_weak_scaling_lines_are_consistent():
     lines = {n: _line(os.path.join(ROOT, "profiles", f"bench_r01g_n{n}.json")) for n in (1, 2, 4, 8)}
     for n, d in lines.items():
