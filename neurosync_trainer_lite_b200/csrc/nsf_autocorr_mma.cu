@@ -18,6 +18,13 @@
 // Precision: X is the mean-removed, windowed frame scaled by an exact power of two and split into
 // fp16 hi + lo; hi.hi + hi.lo + lo.hi carries ~22 mantissa bits (fp32 class).  The scale cancels in
 // r[lag] / r[0].
+//
+// Kernels (all give bit-identical rows; launch_autocorr_mma picks one):
+//   k_autocorr_pipe  88.2 kHz plan (F = 1470): eight warps per SM, two frame buffers per warp, the staging of the next
+//                    frame woven into the compile-time unrolled five-tile MMA loop of the current one (am_mma5_pipe)
+//   k_autocorr_sym   every other frame length: every warp stages, then multiplies, its own frames (am_mma5 /
+//                    am_mma5_static<17> / am_mma); NSF_AC_KERNEL=sym forces it at F = 1470
+//   k_autocorr_mma   warp-specialised producer / consumer pairs of round 1 (NSF_AC_KERNEL=pairs)
 #include <cuda_fp16.h>
 
 #include <cstdlib>
