@@ -887,10 +887,12 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
 // ------------------------------------------------------------------------------------------------
 constexpr int kPipeWarps = 8;      // per block, one block per SM
 
+// One hop-frame of a warp's row run: output row, frame index inside its clip, position inside the row's frame pair.
+// `crossed`: the frame is the first one of the next clip (the clip state of the enumeration has moved on).
 struct AmFrame {
-  int64_t r, tf, T, base, len;
-  int n_frames, f;
-  bool valid;
+  int64_t r;
+  int tf, n_frames, f;
+  bool valid, crossed;
 };
 
 template <int kIters, int NBLK, int kWarps, int kBlocksPerSm>
@@ -914,38 +916,58 @@ __global__ void __launch_bounds__(kWarps * 32, kBlocksPerSm) k_autocorr_pipe(Dev
   const int64_t chunk = (b.total_rows + n_warps_total - 1) / n_warps_total;
   const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * n_warps + warp) * chunk;
   const int64_t r_end = min(r_begin + chunk, b.total_rows);
-  // frame enumeration of the warp's row run, one frame of look-ahead
-  int64_t base = 0, len = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
-  int64_t it_r = r_begin;
-  int it_f = 0, it_nf = 0;
-  auto next_frame = [&]() -> AmFrame {
+  // Frame enumeration of the warp's row run with one frame of look-ahead.  Inside a clip the next frame is an
+  // increment: the clip state - and the range [tf_lo, tf_hi) of its `fast` frames (am_src: inside the clip and 64 n_it
+  // samples before the end of the packed signal) - is derived once per clip; the clip before is kept for the edge
+  // fix of its last frame, which is handled after the enumeration has moved on.
+  int64_t base = 0, len = 0, clip_row0 = 0, clip_row_end = -1, pbase = 0, plen = 0;
+  int T = 0, pT = 0, tf_lo = 0, tf_hi = 0;
+  auto open_clip = [&](int64_t r) {
+    pbase = base; plen = len; pT = T;
+    const int clip = find_segment(b.row_off, b.n_clips, r);
+    base = __ldg(b.clip_off + clip);
+    len = __ldg(b.clip_off + clip + 1) - base;
+    T = static_cast<int>(__ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip));
+    clip_row0 = __ldg(b.row_off + clip);
+    clip_row_end = __ldg(b.row_off + clip + 1);
+    const int64_t in_clip = len - t.F + t.pad, in_batch = b.total_samples - base - 64 * n_it + t.pad;
+    const int64_t last = min(in_clip, in_batch);          // tf H <= last
+    tf_lo = (t.pad + t.H - 1) / t.H;
+    tf_hi = last >= 0 ? static_cast<int>(min(last / t.H, static_cast<int64_t>(T))) + 1 : 0;
+  };
+  auto first_frame = [&]() -> AmFrame {
     AmFrame fr;
-    fr.valid = false;
-    if (it_f >= it_nf) {                               // open the next row
-      if (it_nf != 0) ++it_r;
-      if (it_r >= r_end) { it_nf = 0; it_f = 0; fr.r = fr.tf = fr.T = fr.base = fr.len = 0; fr.n_frames = fr.f = 0; return fr; }
-      if (it_r >= clip_row_end) {
-        const int clip = find_segment(b.row_off, b.n_clips, it_r);
-        base = __ldg(b.clip_off + clip);
-        len = __ldg(b.clip_off + clip + 1) - base;
-        T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
-        clip_row0 = __ldg(b.row_off + clip);
-        clip_row_end = __ldg(b.row_off + clip + 1);
-      }
-      const int64_t lr = it_r - clip_row0;
-      const int64_t tf0 = reduce ? 2 * lr : lr;
-      it_nf = (reduce && tf0 + 1 < T) ? 2 : 1;         // odd T: the last row passes through
-      it_f = 0;
+    fr.r = r_begin; fr.tf = 0; fr.n_frames = 1; fr.f = 0; fr.crossed = false;
+    fr.valid = r_begin < r_end;
+    if (fr.valid) {
+      open_clip(r_begin);
+      const int64_t lr = r_begin - clip_row0;
+      fr.tf = static_cast<int>(reduce ? 2 * lr : lr);
+      fr.n_frames = (reduce && fr.tf + 1 < T) ? 2 : 1;     // odd T: the last row passes through
     }
-    const int64_t lr = it_r - clip_row0;
-    fr.r = it_r; fr.tf = (reduce ? 2 * lr : lr) + it_f; fr.T = T; fr.base = base; fr.len = len;
-    fr.n_frames = it_nf; fr.f = it_f; fr.valid = true;
-    ++it_f;
     return fr;
   };
-  AmFrame cur = next_frame();
+  auto next_frame = [&](const AmFrame& prev) -> AmFrame {
+    AmFrame fr = prev;
+    fr.crossed = false;
+    if (prev.f + 1 < prev.n_frames) { fr.f = prev.f + 1; fr.tf = prev.tf + 1; return fr; }
+    fr.r = prev.r + 1;
+    fr.f = 0;
+    if (fr.r >= r_end) { fr.valid = false; return fr; }
+    if (fr.r >= clip_row_end) {
+      open_clip(fr.r);
+      fr.crossed = true;
+      const int64_t lr = fr.r - clip_row0;
+      fr.tf = static_cast<int>(reduce ? 2 * lr : lr);
+    } else {
+      fr.tf = prev.tf + 1;
+    }
+    fr.n_frames = (reduce && fr.tf + 1 < T) ? 2 : 1;
+    return fr;
+  };
+  AmFrame cur = first_frame();
   if (cur.valid) {                                     // prologue: the first frame is staged on its own
-    const AmSrc src = am_src(t, b, y, cur.base, cur.len, cur.tf, n_it);
+    const AmSrc src = am_src(t, b, y, base, len, cur.tf, n_it);
     if (src.fast) {
       float v0[kIters], v1[kIters];
       am_issue_fast<kIters, true>(src.clip + src.first, n_it, lane, v0, v1);
@@ -958,26 +980,26 @@ __global__ void __launch_bounds__(kWarps * 32, kBlocksPerSm) k_autocorr_pipe(Dev
   float acc[kVals];
 #pragma unroll
   for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
-  AmFrame nxt = next_frame();
-  AmSrc nsrc;
-  nsrc.fast = false;
-  if (nxt.valid) nsrc = am_src(t, b, y, nxt.base, nxt.len, nxt.tf, n_it);
-  bool nfast = nxt.valid && nsrc.fast;
   while (cur.valid) {
     __half* copies = p ? buf1 : buf0;
     __half* next_copies = p ? buf0 : buf1;
-    float v0[kIters], v1[kIters];
-    if (nfast) am_issue_fast<kIters, true>(nsrc.clip + nsrc.first, n_it, lane, v0, v1);
+    const AmFrame nxt = next_frame(cur);               // may move the clip state on (nxt.crossed)
+    const bool nfast = nxt.valid && nxt.tf >= tf_lo && nxt.tf < tf_hi;
     float val[kVals];
     if (nfast) {
+      float v0[kIters], v1[kIters];
+      am_issue_fast<kIters, true>(y + base + (static_cast<int64_t>(nxt.tf) * t.H - t.pad), n_it, lane, v0, v1);
       am_mma5_pipe<NBLK, kIters>(copies, geo, lane, val, t, hann, v0, v1, next_copies);
     } else {
       am_mma5(copies, geo, lane, val);
-      if (nxt.valid) am_fill_simple(t, hann, nsrc, next_copies, geo, lane);
+      if (nxt.valid) am_fill_simple(t, hann, am_src(t, b, y, base, len, nxt.tf, n_it), next_copies, geo, lane);
     }
     // fix_edge_frames_autocorr: a near-silent first (last) frame takes the values of frame 1 (T-2); rare
-    if (cur.T > 1 && (cur.tf == 0 || cur.tf == cur.T - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
-      am_fill_simple(t, hann, am_src(t, b, y, cur.base, cur.len, cur.tf == 0 ? 1 : cur.T - 2, n_it), copies, geo, lane);
+    const bool moved = nxt.valid && nxt.crossed;       // cur belongs to the clip before
+    const int cT = moved ? pT : T;
+    if (cT > 1 && (cur.tf == 0 || cur.tf == cT - 1) && am_all_small(val, lane, t.n_lags, t.edge_thr)) {
+      am_fill_simple(t, hann, am_src(t, b, y, moved ? pbase : base, moved ? plen : len, cur.tf == 0 ? 1 : cT - 2, n_it),
+                     copies, geo, lane);
       am_mma5(copies, geo, lane, val);
     }
 #pragma unroll
@@ -994,10 +1016,6 @@ __global__ void __launch_bounds__(kWarps * 32, kBlocksPerSm) k_autocorr_pipe(Dev
     }
     cur = nxt;
     p ^= 1;
-    nxt = next_frame();
-    nsrc.fast = false;
-    if (nxt.valid) nsrc = am_src(t, b, y, nxt.base, nxt.len, nxt.tf, n_it);
-    nfast = nxt.valid && nsrc.fast;
   }
 }
 
