@@ -802,7 +802,8 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
   const int64_t chunk = (b.total_rows + n_warps_total - 1) / n_warps_total;
   const int64_t r_begin = (static_cast<int64_t>(blockIdx.x) * n_warps + warp) * chunk;
   const int64_t r_end = min(r_begin + chunk, b.total_rows);
-  int64_t base = 0, len = 0, T = 0, clip_row0 = 0, clip_row_end = -1;
+  int64_t base = 0, len = 0, clip_row0 = 0, clip_row_end = -1;
+  int T = 0, tf_lo = 0, tf_hi = 0;      // frames of the clip; its `fast` frames (am_src) are tf_lo <= tf < tf_hi
   // the MMA half of a frame: six-MMA loop, five-tile loop, or (F = 266, the 16 kHz plan: seventeen K-blocks) the
   // five-tile loop unrolled at compile time
   auto run_mma = [&](float (&val)[kVals]) {
@@ -824,30 +825,36 @@ __global__ void __launch_bounds__(kSymWarps * 32, 2) k_autocorr_sym(DeviceTables
       const int clip = find_segment(b.row_off, b.n_clips, r);
       base = __ldg(b.clip_off + clip);
       len = __ldg(b.clip_off + clip + 1) - base;
-      T = __ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip);
+      T = static_cast<int>(__ldg(b.frame_off + clip + 1) - __ldg(b.frame_off + clip));
       clip_row0 = __ldg(b.row_off + clip);
       clip_row_end = __ldg(b.row_off + clip + 1);
+      // fast frames (inside the clip, 64 n_it samples before the end of the packed signal): tf_lo <= tf < tf_hi,
+      // derived once per clip so that a frame costs two comparisons and one 32 x 32 -> 64 bit product
+      const int64_t in_clip = len - t.F + t.pad, in_batch = b.total_samples - base - 64 * static_cast<int64_t>(n_it) + t.pad;
+      const int64_t last = min(in_clip, in_batch);          // tf H <= last
+      tf_lo = (t.pad + t.H - 1) / t.H;
+      tf_hi = last >= 0 ? static_cast<int>(min(last / t.H, static_cast<int64_t>(T))) + 1 : 0;
     }
-    const int64_t lr = r - clip_row0;
-    const int64_t tf0 = reduce ? 2 * lr : lr;
+    const int lr = static_cast<int>(r - clip_row0);
+    const int tf0 = reduce ? 2 * lr : lr;
     const int n_frames = (reduce && tf0 + 1 < T) ? 2 : 1;   // odd T: the last row passes through
     float acc[kVals];
 #pragma unroll
     for (int v = 0; v < kVals; ++v) acc[v] = 0.0f;
     for (int f = 0; f < n_frames; ++f) {
-      const int64_t tf = tf0 + f;
-      const AmSrc src = am_src(t, b, y, base, len, tf, n_it);
+      const int tf = tf0 + f;
+      const bool fast = tf >= tf_lo && tf < tf_hi;
 #ifdef NSF_AC_TRACE
       const bool tr = lane == 0 && trace_i < kTraceFrames && blockIdx.x < 296 && warp < 8;
       long long* trp = g_ac_trace + ((static_cast<size_t>(blockIdx.x) * 8 + warp) * kTraceFrames + trace_i) * 3;
       if (tr) trp[0] = clock64();
 #endif
-      if (src.fast) {
+      if (fast) {
         float v0[kIters], v1[kIters];
-        am_issue_fast<kIters, kExact>(src.clip + src.first, n_it, lane, v0, v1);
+        am_issue_fast<kIters, kExact>(y + base + (static_cast<int64_t>(tf) * t.H - t.pad), n_it, lane, v0, v1);
         am_process<kIters, kExact>(t, hann, n_it, v0, v1, copies, geo, lane, nullptr);
       } else {
-        am_fill_simple(t, hann, src, copies, geo, lane);
+        am_fill_simple(t, hann, am_src(t, b, y, base, len, tf, n_it), copies, geo, lane);
       }                                                   // both end with __syncwarp
 #ifdef NSF_AC_TRACE
       if (tr) trp[1] = clock64();
