@@ -162,6 +162,13 @@ def test_pipelined_build_lines():
     assert g["shape"] == [2994720, 256] and g["all_slices_filled"] is True
     ref = _line(os.path.join(ROOT, "profiles", "bench_r02t_ref_n1.json"))
     assert ref["impl"] == "reference" and ref["gpu_launches"] == 0 and ref["value"] == ref["cpu_baseline"]["value"]
+    # capture r02u: the final build (incremental frame bookkeeping in the autocorrelation kernels)
+    fin = _line(os.path.join(ROOT, "profiles", "bench_r02u_n1.json"))
+    assert REQUIRED <= set(fin) and fin["n_gpus"] == 1 and fin["ms_per_step"] < 2.10 and fin["value"] > 8.5e5
+    assert fin["roofline"]["traffic_source"].startswith("profiles/ncu_traffic_r02")
+    assert fin["workloads"]["c5"]["ms_per_step"] < 6.0
+    fref = _line(os.path.join(ROOT, "profiles", "bench_r02u_ref_n1.json"))
+    assert fref["impl"] == "reference" and abs(fref["value"] / fin["cpu_baseline"]["value"] - 1.0) < 0.1
 
 
 def test_weak_scaling_lines_are_consistent():
